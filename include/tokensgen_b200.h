@@ -1,0 +1,178 @@
+/* tokensgen_b200 — C ABI of the B200-native TokensGen FIFO-denoising hot path.
+ *
+ * The reference (Vicky0522/TokensGen) is 100 % Python: this path has no existing FFI.  Each entry point
+ * below replaces one group of PyTorch library calls on the reference's hot path; the comment above it
+ * cites the reference lines it replaces.  The reference-side binding is a ctypes stub (see INTEGRATION.md
+ * and tokensgen_b200/_ext.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - the caller owns every buffer (including workspaces); the library allocates nothing.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal synchronisation,
+ *     so every call is CUDA-graph capturable.
+ *   - return 0 = ok; negative = argument error (nothing was launched); positive = cudaError_t / CUresult.
+ *     tg_last_error() returns a thread-local message for the last non-zero return.
+ *   - activations / weights are bf16 (uint16_t storage) row-major; accumulation is fp32.
+ *   - "residual stream" X is [B, rows_per_batch, d] with rows ordered [text | video | vip] per batch —
+ *     the order CogVideoXPatchEmbed.forward emits (reference longvgen/models/embeddings.py:541-544).
+ */
+#ifndef TOKENSGEN_B200_H
+#define TOKENSGEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef uint16_t tg_bf16; /* raw bfloat16 bits */
+
+#define TG_VERSION 1
+#define TG_HEAD_DIM 64 /* CogVideoX attention_head_dim; the kernels are specialised for it */
+
+int tg_version(void);
+const char* tg_last_error(void);
+
+/* Row layout of the residual stream, shared by the fused epilogues:
+ * row r of a batch is text if r < n_text, video if r < n_text + n_video (frame = (r - n_text) / hw), else vip. */
+typedef struct {
+    int rows_per_batch; /* n_text + n_video + n_vip */
+    int n_text;
+    int n_video;
+    int n_vip;
+    int hw;     /* video tokens per latent frame (30*45 = 1350) */
+    int frames; /* latent frames per window (13) */
+} tg_rowmap;
+
+/* One modulation vector source: row (b*frames + f) of a [B*frames, ld] bf16 table, f = 0 unless the row is a
+ * video row.  Replaces the `repeat "b f c -> b (f hw) c"` broadcasts of
+ * longvgen/models/normalization.py:448-459 (video rows: per-frame; text rows: frame 0) and :482-487 (vip rows). */
+typedef struct {
+    const tg_bf16* text;  /* may be NULL if n_text == 0 */
+    const tg_bf16* video;
+    const tg_bf16* vip;   /* may be NULL if n_vip == 0 */
+    int64_t ld_text, ld_video, ld_vip; /* row strides in elements */
+} tg_modvec;
+
+/* ---------------------------------------------------------------------------------------------------
+ * K10  timestep embedding.  Replaces time_proj + time_embedding:
+ *   longvgen/models/cogvideox_transformer_3d.py:669-680, longvgen/models/embeddings.py:28-79,953-965.
+ * timesteps: fp32 [R].  out_emb / out_silu: bf16 [R, time_dim] (emb and SiLU(emb), the latter being the
+ * input of every AdaLN linear, normalization.py:448).  sincos_dim = 3072, flip_sin_to_cos = 1, freq_shift = 0. */
+int tg_time_embedding(const float* timesteps, int R, int sincos_dim, int time_dim, int flip_sin_to_cos,
+                      float freq_shift, const tg_bf16* w1, const tg_bf16* b1, const tg_bf16* w2,
+                      const tg_bf16* b2, tg_bf16* out_emb, tg_bf16* out_silu, tg_bf16* scratch /* [R, time_dim] */,
+                      void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K2  LayerNorm(affine, eps) then x*(1+scale)+shift with per-row modulation vectors.
+ * Replaces CogVideoXLayerNormZero / CogVideoXVIPLayerNormZero / (norm_final + AdaLayerNorm) elementwise parts:
+ *   longvgen/models/normalization.py:457-459, :487, :70-92; cogvideox_transformer_3d.py:736-747.
+ * x, out: [B*rows_per_batch, d] (may alias).  ln_w/ln_b: bf16 [d] per segment (text+video share `ln_*`,
+ * vip rows use `vip_ln_*`).  If ln2_w != NULL a second affine LayerNorm (eps2) is applied to video rows before the
+ * modulation (norm_final followed by norm_out.norm).  Rows of a segment whose shift/scale pointer is NULL are skipped
+ * (left untouched in `out`). */
+int tg_ln_modulate(const tg_bf16* x, tg_bf16* out, int B, int d, const tg_rowmap* map, const tg_bf16* ln_w,
+                   const tg_bf16* ln_b, const tg_bf16* vip_ln_w, const tg_bf16* vip_ln_b, float eps,
+                   const tg_bf16* ln2_w, const tg_bf16* ln2_b, float eps2, const tg_modvec* shift,
+                   const tg_modvec* scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * GEMM family: out = epilogue(A[M,K] @ W[N,K]^T + bias[N]) on tcgen05 tensor cores (TMA-fed, TMEM accumulators).
+ * A: bf16 row-major, leading dim lda; W: bf16 [N,K] row-major (the nn.Linear weight layout, untransposed).
+ * K % 64 == 0, N % 64 == 0, all base pointers 16-byte aligned, lda % 8 == 0. */
+enum { TG_ACT_NONE = 0, TG_ACT_GELU_TANH = 1, TG_ACT_SILU = 2 };
+
+/* K1/K8a/K9/K11: plain Linear (+activation).  Replaces nn.Linear calls at normalization.py:448,482,
+ * embeddings.py:516,521,526 (patchify conv as GEMM over tg_patchify rows), diffusers FeedForward net[0]
+ * (GELU-tanh; cogvideox_transformer_3d.py:316,322), proj_out (:748). */
+int tg_gemm_bias_act(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, tg_bf16* out,
+                     int64_t ldo, int M, int N, int K, int act, void* stream);
+
+/* K7/K8b: X[m,:] += gate(m) * (A @ W^T + bias) in place.  Replaces to_out[0] + gated residual
+ * (attention_processor.py:2143-2148 + cogvideox_transformer_3d.py:290-293) and FeedForward net[2] + gated
+ * residual (:318-324).  M = B*rows_per_batch. */
+int tg_gemm_gate_residual(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, tg_bf16* X,
+                          int64_t ldx, int B, int N, int K, const tg_rowmap* map, const tg_modvec* gate,
+                          void* stream);
+
+/* K3: fused Q/K/V projections with per-head LayerNorm(64) and 3D-RoPE in the epilogue, written head-major.
+ * Replaces attention_processor.py:2009-2056 (and :1915-1937 for the plain processor).
+ * W: [nproj*H*64, K] = rows of the projections concatenated in `proj` order.  For projection p and head h the
+ * epilogue computes y = A@W_p,h^T + bias; if ln_w: y = LN_64(y)*ln_w+ln_b (eps); then RoPE on interleaved pairs
+ * (x0,x1)->(x0*c0 - x1*s0, x1*c1 + x0*s1) with cos/sin rows taken from cos_video[r-n_text] for video rows and
+ * cos_vip[r-n_text-n_video] for vip rows (NULL table = no RoPE for that segment; text rows never rotate);
+ * result stored at out[((b*H + h)*out_rows + r)*64 ..] iff r < out_rows. */
+typedef struct {
+    tg_bf16* out;    /* [B, H, out_rows, 64] */
+    int out_rows;    /* rows of each batch kept for this projection (prefix of the batch's rows) */
+    const tg_bf16* ln_w; /* [64] or NULL */
+    const tg_bf16* ln_b;
+    const float* cos_video; /* [n_video, 64] fp32 or NULL */
+    const float* sin_video;
+    const float* cos_vip;   /* [n_vip, 64] fp32 or NULL */
+    const float* sin_vip;
+} tg_qkv_proj;
+
+int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H, int K,
+                     const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K4/K5/K6: non-causal softmax(Q K^T * scale) V, head_dim 64, tcgen05 flash attention.
+ * Replaces the three F.scaled_dot_product_attention calls at attention_processor.py:2066-2069, 2117-2125
+ * (and :1939 for the plain processor).
+ * q: [B,H,*,64] with q_rows queries starting at row q_row0 of a tensor with q_rows_alloc rows per head; k, v likewise.
+ * out: [B, out_rows_alloc, H*64] token-major; query i is written to row out_row0 + i.
+ * accumulate != 0: out = out + out_scale * attn (the `hidden + scale * text_video_hidden` of :2134), else out = attn. */
+int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
+                const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, tg_bf16* out,
+                int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,
+                float out_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K9/K11 index maps (bit-exact class).
+ * tg_patchify: latents [B,F,C,H,W] -> rows [B*F*(H/p)*(W/p), C*p*p] in Conv2d weight order (c, pi, pj);
+ *   replaces the im2col implied by embeddings.py:524-529.
+ * tg_unpatchify: rows [B*F*(H/p)*(W/p), C*p*p] -> [B,F,C,H,W]; replaces cogvideox_transformer_3d.py:754-759. */
+int tg_patchify(const tg_bf16* latents, tg_bf16* rows, int B, int F, int C, int H, int W, int p, void* stream);
+int tg_unpatchify(const tg_bf16* rows, tg_bf16* latents, int B, int F, int C, int H, int W, int p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K12: classifier-free guidance + per-frame DPM-Solver++(2M) SDE step for one window, one launch.
+ * Replaces cogvideo_sampling_mp_fifo.py:527-550 + scheduling_dpm_cogvideox.py:424-463 (13 Python iterations of
+ * ~15 elementwise launches each), and pipeline_cogvideox_mp_fifo.py:1247-1290 for the base stage.
+ *   noise_pred : bf16 [n_branches, F, chw]; n_branches = 2 -> (uncond, cond) combined as u + g*(c-u); 1 -> used as is.
+ *   coef       : fp32 [F, 8] per frame {sqrt_alpha_t, sqrt_beta_t, mult0, mult1, mult2, mult3, mult_noise, flags};
+ *                flags (as float) 1.0 = second-order frame (old x0 valid and prev_timestep >= 0), else 0.0.
+ *                The host computes them in fp64 exactly as CogVideoXDPMScheduler.get_variables/get_mult and casts.
+ *   noise1     : the draw a first-order frame uses; noise2: the draw a second-order frame uses (the reference draws
+ *                twice on that path and uses the second, scheduling_dpm_cogvideox.py:450,461).  Both bf16 [F, chw].
+ *   mode TG_DPM_BF16_CHAIN : every tensor op rounds to bf16 like the reference FIFO worker (all-bf16 tensors);
+ *        TG_DPM_BASE_CHAIN : the base pipeline's mixed chain (noise_pred.float(), fp32 x0 history, bf16 latents);
+ *   old_x0 / x0_out are bf16 in BF16_CHAIN mode, fp32 (`*_f32`) in BASE_CHAIN mode.
+ * With identical noise the result is bit-identical to the reference chain. */
+enum { TG_DPM_BF16_CHAIN = 1, TG_DPM_BASE_CHAIN = 0 };
+typedef struct {
+    const tg_bf16* noise_pred;
+    int n_branches;
+    float guidance_scale;
+    const tg_bf16* sample;     /* [F, chw] */
+    const tg_bf16* old_x0;     /* [F, chw] or NULL */
+    const float* old_x0_f32;   /* [F, chw] or NULL */
+    const tg_bf16* noise1;
+    const tg_bf16* noise2;
+    const float* coef;
+    tg_bf16* prev_sample;      /* [F, chw] */
+    tg_bf16* x0_out;           /* [F, chw] or NULL */
+    float* x0_out_f32;         /* [F, chw] or NULL */
+    int F;
+    int64_t chw;
+    int mode;
+} tg_dpm_step_args;
+int tg_cfg_dpm_step(const tg_dpm_step_args* args, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOKENSGEN_B200_H */

@@ -1,0 +1,249 @@
+"""ctypes binding of libtokensgen_b200.so (the C ABI declared in include/tokensgen_b200.h).
+
+This is the only place Python touches the native library.  There is NO fallback: if the library is missing or a
+call fails, a `TokensGenError` is raised.  PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional, Sequence
+
+import torch
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libtokensgen_b200.so"
+
+
+class TokensGenError(RuntimeError):
+    pass
+
+
+class RowMap(C.Structure):
+    _fields_ = [("rows_per_batch", C.c_int), ("n_text", C.c_int), ("n_video", C.c_int), ("n_vip", C.c_int),
+                ("hw", C.c_int), ("frames", C.c_int)]
+
+
+class ModVec(C.Structure):
+    _fields_ = [("text", C.c_void_p), ("video", C.c_void_p), ("vip", C.c_void_p),
+                ("ld_text", C.c_int64), ("ld_video", C.c_int64), ("ld_vip", C.c_int64)]
+
+
+class QkvProj(C.Structure):
+    _fields_ = [("out", C.c_void_p), ("out_rows", C.c_int), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
+                ("cos_video", C.c_void_p), ("sin_video", C.c_void_p), ("cos_vip", C.c_void_p), ("sin_vip", C.c_void_p)]
+
+
+class DpmStepArgs(C.Structure):
+    _fields_ = [("noise_pred", C.c_void_p), ("n_branches", C.c_int), ("guidance_scale", C.c_float),
+                ("sample", C.c_void_p), ("old_x0", C.c_void_p), ("old_x0_f32", C.c_void_p),
+                ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("coef", C.c_void_p),
+                ("prev_sample", C.c_void_p), ("x0_out", C.c_void_p), ("x0_out_f32", C.c_void_p),
+                ("F", C.c_int), ("chw", C.c_int64), ("mode", C.c_int)]
+
+
+ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
+DPM_BASE_CHAIN, DPM_BF16_CHAIN = 0, 1
+
+# name -> (restype, argtypes): every symbol include/tokensgen_b200.h declares.
+_VP, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SYMBOLS = {
+    "tg_version": (C.c_int, []),
+    "tg_last_error": (C.c_char_p, []),
+    "tg_time_embedding": (C.c_int, [_VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "tg_ln_modulate": (C.c_int, [_VP, _VP, _I, _I, C.POINTER(RowMap), _VP, _VP, _VP, _VP, _F, _VP, _VP, _F,
+                                 C.POINTER(ModVec), C.POINTER(ModVec), _VP]),
+    "tg_gemm_bias_act": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I, _I, _I, _I, _VP]),
+    "tg_gemm_gate_residual": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I, _I, _I, C.POINTER(RowMap),
+                                        C.POINTER(ModVec), _VP]),
+    "tg_qkv_rope_gemm": (C.c_int, [_VP, _I64, _VP, _VP, _I, _I, _I, C.POINTER(RowMap), C.POINTER(QkvProj), _I, _F, _VP]),
+    "tg_attn_fwd": (C.c_int, [_VP, _I64, _I64, _I, _VP, _VP, _I64, _I64, _I, _VP, _I64, _I64, _I, _I, _F, _I, _F, _VP]),
+    "tg_patchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "tg_unpatchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "tg_cfg_dpm_step": (C.c_int, [C.POINTER(DpmStepArgs), _VP]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Loads the native library (once).  Raises TokensGenError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise TokensGenError(
+                f"{LIB_PATH} is missing: run `python -m tokensgen_b200.build` (there is no CPU/PyTorch fallback)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.tg_version() != 1:
+            raise TokensGenError(f"ABI version mismatch: library reports {lib.tg_version()}")
+        _lib = lib
+    return _lib
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().tg_last_error().decode(errors="replace")
+        raise TokensGenError(f"{what} failed (rc={rc}): {msg}")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+        raise TokensGenError(f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device} "
+                             f"contiguous={t.is_contiguous()}")
+    return t
+
+
+def make_rowmap(n_text: int, n_video: int, n_vip: int, hw: int, frames: int) -> RowMap:
+    return RowMap(n_text + n_video + n_vip, n_text, n_video, n_vip, hw, frames)
+
+
+def make_modvec(text: Optional[torch.Tensor], video: Optional[torch.Tensor], vip: Optional[torch.Tensor]) -> ModVec:
+    """Each argument is a 2-D bf16 view [B*frames, C] whose rows may be strided (a column slice of an AdaLN table)."""
+    def ld(t):
+        if t is None:
+            return 0
+        if t.dim() != 2 or t.stride(1) != 1 or t.dtype != torch.bfloat16 or not t.is_cuda:
+            raise TokensGenError("modvec: expected 2-D CUDA bf16 with unit inner stride")
+        return t.stride(0)
+    return ModVec(_ptr(text), _ptr(video), _ptr(vip), ld(text), ld(video), ld(vip))
+
+
+# ------------------------------------------------------------------------------------------------ ops
+def time_embedding(timesteps: torch.Tensor, w1, b1, w2, b2, sincos_dim: int, flip_sin_to_cos: bool = True,
+                   freq_shift: float = 0.0):
+    lib = load()
+    ts = timesteps.to(device=w1.device, dtype=torch.float32).contiguous()
+    R, time_dim = ts.numel(), w2.shape[0]
+    emb = torch.empty(R, time_dim, device=w1.device, dtype=torch.bfloat16)
+    silu = torch.empty_like(emb)
+    scratch = torch.empty_like(emb)
+    _check(lib.tg_time_embedding(ts.data_ptr(), R, sincos_dim, time_dim, int(flip_sin_to_cos), float(freq_shift),
+                                 _bf16_cuda(w1, "w1").data_ptr(), _bf16_cuda(b1, "b1").data_ptr(),
+                                 _bf16_cuda(w2, "w2").data_ptr(), _bf16_cuda(b2, "b2").data_ptr(),
+                                 emb.data_ptr(), silu.data_ptr(), scratch.data_ptr(), _stream()), "tg_time_embedding")
+    return emb, silu
+
+
+def ln_modulate(x: torch.Tensor, out: torch.Tensor, B: int, rowmap: RowMap, ln_w, ln_b, vip_ln_w, vip_ln_b, eps: float,
+                shift: ModVec, scale: ModVec, ln2_w=None, ln2_b=None, eps2: float = 1e-5) -> None:
+    lib = load()
+    d = x.shape[-1]
+    _check(lib.tg_ln_modulate(_bf16_cuda(x, "x").data_ptr(), _bf16_cuda(out, "out").data_ptr(), B, d, C.byref(rowmap),
+                              _ptr(ln_w), _ptr(ln_b), _ptr(vip_ln_w), _ptr(vip_ln_b), float(eps), _ptr(ln2_w), _ptr(ln2_b),
+                              float(eps2), C.byref(shift), C.byref(scale), _stream()), "tg_ln_modulate")
+
+
+def gemm_bias_act(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+                  act: int = ACT_NONE) -> torch.Tensor:
+    """out[M,N] = act(a[M,K] @ w[N,K]^T + bias).  `a`/`out` may be row-strided 2-D views."""
+    lib = load()
+    if a.dim() != 2 or a.stride(1) != 1:
+        raise TokensGenError("gemm_bias_act: a must be 2-D with unit inner stride")
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
+    if out.dim() != 2 or out.stride(1) != 1 or out.shape[0] != M or out.shape[1] != N:
+        raise TokensGenError("gemm_bias_act: bad out")
+    _check(lib.tg_gemm_bias_act(a.data_ptr(), a.stride(0), _bf16_cuda(w, "w").data_ptr(), _ptr(bias), out.data_ptr(),
+                                out.stride(0), M, N, K, act, _stream()), "tg_gemm_bias_act")
+    return out
+
+
+def gemm_gate_residual(a: torch.Tensor, w: torch.Tensor, bias, x: torch.Tensor, B: int, rowmap: RowMap,
+                       gate: ModVec) -> None:
+    lib = load()
+    M, K = a.shape
+    N = w.shape[0]
+    _check(lib.tg_gemm_gate_residual(_bf16_cuda(a, "a").data_ptr(), a.stride(0), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
+                                     _bf16_cuda(x, "x").data_ptr(), x.stride(-2), B, N, K, C.byref(rowmap), C.byref(gate),
+                                     _stream()), "tg_gemm_gate_residual")
+
+
+def qkv_rope_gemm(a: torch.Tensor, w: torch.Tensor, bias, B: int, H: int, rowmap: RowMap,
+                  projs: Sequence[QkvProj], ln_eps: float) -> None:
+    lib = load()
+    K = a.shape[-1]
+    arr = (QkvProj * len(projs))(*projs)
+    _check(lib.tg_qkv_rope_gemm(_bf16_cuda(a, "a").data_ptr(), a.stride(-2), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
+                                B, H, K, C.byref(rowmap), arr, len(projs), float(ln_eps), _stream()), "tg_qkv_rope_gemm")
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, q_row0: int = 0,
+             q_rows: Optional[int] = None, kv_row0: int = 0, kv_rows: Optional[int] = None, out_row0: int = 0,
+             softmax_scale: Optional[float] = None, accumulate: bool = False, out_scale: float = 1.0) -> None:
+    """q [B,H,Nq_alloc,64], k/v [B,H,Nkv_alloc,64] (same alloc for k and v), out [B,Nout_alloc,H*64]."""
+    lib = load()
+    B, H, nq_alloc, D = q.shape
+    if D != 64:
+        raise TokensGenError("attn_fwd: head_dim must be 64")
+    nkv_alloc = k.shape[2]
+    if v.shape != k.shape:
+        raise TokensGenError("attn_fwd: k and v must have the same shape")
+    q_rows = nq_alloc - q_row0 if q_rows is None else q_rows
+    kv_rows = nkv_alloc - kv_row0 if kv_rows is None else kv_rows
+    scale = D ** -0.5 if softmax_scale is None else softmax_scale
+    _check(lib.tg_attn_fwd(_bf16_cuda(q, "q").data_ptr(), nq_alloc, q_row0, q_rows, _bf16_cuda(k, "k").data_ptr(),
+                           _bf16_cuda(v, "v").data_ptr(), nkv_alloc, kv_row0, kv_rows, _bf16_cuda(out, "out").data_ptr(),
+                           out.shape[1], out_row0, B, H, float(scale), int(accumulate), float(out_scale), _stream()),
+           "tg_attn_fwd")
+
+
+def patchify(latents: torch.Tensor, p: int) -> torch.Tensor:
+    lib = load()
+    B, F, Cc, H, W = latents.shape
+    rows = torch.empty(B * F * (H // p) * (W // p), Cc * p * p, device=latents.device, dtype=torch.bfloat16)
+    _check(lib.tg_patchify(_bf16_cuda(latents, "latents").data_ptr(), rows.data_ptr(), B, F, Cc, H, W, p, _stream()),
+           "tg_patchify")
+    return rows
+
+
+def unpatchify(rows: torch.Tensor, B: int, F: int, Cc: int, H: int, W: int, p: int) -> torch.Tensor:
+    lib = load()
+    out = torch.empty(B, F, Cc, H, W, device=rows.device, dtype=torch.bfloat16)
+    _check(lib.tg_unpatchify(_bf16_cuda(rows, "rows").data_ptr(), out.data_ptr(), B, F, Cc, H, W, p, _stream()),
+           "tg_unpatchify")
+    return out
+
+
+def cfg_dpm_step(noise_pred: torch.Tensor, sample: torch.Tensor, old_x0: Optional[torch.Tensor], noise1: torch.Tensor,
+                 noise2: torch.Tensor, coef: torch.Tensor, guidance_scale: float, mode: int):
+    """noise_pred [n_branches,F,...], sample/noise [F,...] bf16; coef fp32 [F,8] (device).  Returns (prev, x0)."""
+    lib = load()
+    nb, F = noise_pred.shape[0], noise_pred.shape[1]
+    chw = sample.numel() // F
+    prev = torch.empty_like(sample)
+    a = DpmStepArgs()
+    a.noise_pred = _bf16_cuda(noise_pred, "noise_pred").data_ptr()
+    a.n_branches = nb
+    a.guidance_scale = float(guidance_scale)
+    a.sample = _bf16_cuda(sample, "sample").data_ptr()
+    a.noise1 = _bf16_cuda(noise1, "noise1").data_ptr()
+    a.noise2 = _bf16_cuda(noise2, "noise2").data_ptr()
+    if not (coef.is_cuda and coef.dtype == torch.float32 and coef.is_contiguous() and coef.shape == (F, 8)):
+        raise TokensGenError("cfg_dpm_step: coef must be CUDA fp32 [F,8]")
+    a.coef = coef.data_ptr()
+    a.prev_sample = prev.data_ptr()
+    a.F, a.chw, a.mode = F, chw, mode
+    if mode == DPM_BF16_CHAIN:
+        x0 = torch.empty_like(sample)
+        a.x0_out = x0.data_ptr()
+        a.old_x0 = _ptr(old_x0)
+    else:
+        x0 = torch.empty(sample.shape, device=sample.device, dtype=torch.float32)
+        a.x0_out_f32 = x0.data_ptr()
+        a.old_x0_f32 = _ptr(old_x0)
+    _check(lib.tg_cfg_dpm_step(C.byref(a), _stream()), "tg_cfg_dpm_step")
+    return prev, x0

@@ -1,0 +1,72 @@
+"""Builds libtokensgen_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+Usage: python -m tokensgen_b200.build [--force] [--verbose]
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC = PKG_DIR / "csrc"
+LIB_PATH = PKG_DIR / "libtokensgen_b200.so"
+SOURCES = ["common.cu", "gemm.cu", "attn.cu", "elementwise.cu"]
+HEADERS = ["common.h", "ptx.cuh", "../../include/tokensgen_b200.h"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr",
+    "-Xcompiler", "-fPIC",
+    "-cudart", "static",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    t = LIB_PATH.stat().st_mtime
+    deps = [CSRC / s for s in SOURCES] + [(CSRC / h).resolve() for h in HEADERS] + [Path(__file__)]
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not needs_build():
+        return LIB_PATH
+    objs = []
+    build_dir = PKG_DIR / "build"
+    build_dir.mkdir(exist_ok=True)
+    procs = []
+    for s in SOURCES:
+        obj = build_dir / (s.replace(".cu", ".o"))
+        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / s), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas")
+            cmd.insert(2, "-v")
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(str(obj))
+    failed = False
+    for s, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(f"--- nvcc {s} (rc={p.returncode})\n{out}\n")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc compilation failed")
+    link = [_nvcc(), "-shared", "-cudart", "static", "-o", str(LIB_PATH), *objs]
+    subprocess.run(link, check=True)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print(path)

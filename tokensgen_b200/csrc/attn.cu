@@ -1,0 +1,347 @@
+// tcgen05 flash-attention forward, head_dim 64, non-causal.
+//
+//   O[q,:] = softmax(Q[q,:] K^T * scale) V          Q [BH, q_rows, 64], K/V [BH, kv_rows, 64] bf16
+//
+// One CTA = one (batch, head) and TWO 128-row query tiles, 384 threads:
+//   warp 0       TMA producer : Q0,Q1 once; then a ring of {K block, V block} stages (128 kv rows each)
+//   warp 1       MMA issuer   : S_t = Q_t K^T  (SS, 128x128x64)   and   O_t += P_t V  (TS: P from TMEM, V MN-major)
+//   warp 2       TMEM allocator
+//   warps 4..7   softmax for tile 0 (thread = one query row; no cross-thread reductions)
+//   warps 8..11  softmax for tile 1
+// The two tiles ping-pong: while one tile's rows are in softmax (MUFU-bound at hd=64), the tensor core runs the
+// other tile's PV and next QK^T.  S_t lives in TMEM (128 fp32 columns); P_t (bf16) overwrites the first 64
+// columns of S_t and is consumed by the PV MMA straight from TMEM.  O_t accumulates in TMEM (64 columns) and is
+// rescaled lazily (only when the running max grows by > 2^8), which keeps the exact result because P and the row
+// sum always share the same reference max.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tg {
+
+constexpr int AT_BLOCK_Q = 128;
+constexpr int AT_BLOCK_KV = 128;
+constexpr int AT_D = 64;
+constexpr int AT_STAGES = 4;
+constexpr int AT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: Q tile, K block, V block
+constexpr int AT_SMEM_BYTES = 2 * AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + 256 + 1024;
+constexpr int AT_THREADS = 384;
+
+struct AttnParams {
+    int q_rows, kv_rows;
+    int H;
+    __nv_bfloat16* out;
+    int64_t out_rows_alloc, out_row0;
+    float scale_log2;  // softmax_scale * log2(e)
+    int accumulate;
+    float out_scale;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = smem_base;                      // 2 tiles
+    const uint32_t kv_smem = smem_base + 2 * AT_TILE_BYTES;  // stages x {K, V}
+    const uint32_t bar_base = kv_smem + AT_STAGES * 2 * AT_TILE_BYTES;
+    const uint32_t q_full = bar_base;
+    auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + AT_STAGES + s); };
+    auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * AT_STAGES + t); };
+    auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * AT_STAGES + t); };
+    auto o_done = [&](int t) { return bar_base + 8u * (5 + 2 * AT_STAGES + t); };
+    const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * AT_STAGES);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bh = blockIdx.y;
+    const int q0 = blockIdx.x * (2 * AT_BLOCK_Q);
+    const int n_blocks = (p.kv_rows + AT_BLOCK_KV - 1) / AT_BLOCK_KV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < AT_STAGES; ++s) {
+            mbar_init(kv_full(s), 1);
+            mbar_init(kv_empty(s), 1);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(s_full(t), 1);
+            mbar_init(p_full(t), 4);  // one arrive per softmax warp of the tile
+            mbar_init(o_done(t), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t aliases S_t[0,64).
+    auto s_col = [&](int t) { return uint32_t(t * 128); };
+    auto o_col = [&](int t) { return uint32_t(256 + t * 64); };
+
+    if (warp < 4) {
+        reg_dealloc<80>();
+        if (warp == 0) {
+            // -------------------------------------------------------------- TMA producer
+            if (lane == 0) {
+                mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+                tma_load_3d(q_smem, &tmap_q, q_full, 0, q0, bh);
+                tma_load_3d(q_smem + AT_TILE_BYTES, &tmap_q, q_full, 0, q0 + AT_BLOCK_Q, bh);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_blocks; ++j) {
+                    mbar_wait(kv_empty(stage), phase ^ 1u, 0x201);
+                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+                    mbar_arrive_expect_tx(kv_full(stage), 2 * AT_TILE_BYTES);
+                    tma_load_3d(ks, &tmap_k, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                    tma_load_3d(ks + AT_TILE_BYTES, &tmap_v, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                    if (++stage == AT_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // -------------------------------------------------------------- MMA issuer
+            if (lane == 0) {
+                constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);  // V is MN-major
+                auto issue_qk = [&](int t, int stage) {
+                    const uint32_t qs = q_smem + t * AT_TILE_BYTES;
+                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(qs + k * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc_sw128(ks + k * 32, 16, 1024);
+                        umma_ss(tmem_base + s_col(t), da, db, idesc_qk, k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(s_full(t));
+                };
+                auto issue_pv = [&](int t, int stage, bool first) {
+                    const uint32_t vs = kv_smem + stage * 2 * AT_TILE_BYTES + AT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < AT_BLOCK_KV / 16; ++k) {
+                        // 16 kv rows per MMA = two 8-row swizzle groups (SBO 1024 B apart); N = 64 is one MN atom.
+                        const uint64_t db = make_smem_desc_sw128(vs + k * 2048, 1024, 1024);
+                        umma_ts(tmem_base + o_col(t), tmem_base + s_col(t) + uint32_t(k * 8), db, idesc_pv,
+                                (first && k == 0) ? 0u : 1u);
+                    }
+                };
+                mbar_wait(q_full, 0, 0x202);
+                mbar_wait(kv_full(0), 0, 0x203);
+                tc_fence_after();
+                issue_qk(0, 0);
+                issue_qk(1, 0);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_blocks; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == AT_STAGES) {
+                        nstage = 0;
+                        nphase ^= 1u;
+                    }
+                    const bool has_next = (j + 1 < n_blocks);
+                    for (int t = 0; t < 2; ++t) {
+                        mbar_wait(p_full(t), uint32_t(j & 1), 0x204);
+                        tc_fence_after();
+                        issue_pv(t, stage, j == 0);
+                        if (t == 1) umma_commit(kv_empty(stage));
+                        umma_commit(o_done(t));
+                        if (has_next) {
+                            if (t == 0) {
+                                mbar_wait(kv_full(nstage), nphase, 0x205);
+                                tc_fence_after();
+                            }
+                            issue_qk(t, nstage);
+                        }
+                    }
+                    stage = nstage;
+                    phase = nphase;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warpgroups
+        reg_alloc<208>();
+        const int t = (warp - 4) >> 2;  // tile
+        const int wq = warp & 3;        // TMEM lane quarter
+        const int row_in_tile = wq * 32 + lane;
+        const int q_row = q0 + t * AT_BLOCK_Q + row_in_tile;
+        const uint32_t lane_base = tmem_base + (uint32_t(wq * 32) << 16);
+        const uint32_t s_addr = lane_base + s_col(t);
+        const uint32_t o_addr = lane_base + o_col(t);
+        const float c = p.scale_log2;
+        float m_ref = -INFINITY;  // reference max (raw score units)
+        float l = 0.f;            // running sum of exp2((s - m_ref) * c)
+
+        for (int j = 0; j < n_blocks; ++j) {
+            mbar_wait(s_full(t), uint32_t(j & 1), 0x206);
+            tc_fence_after();
+            float s[128];
+            {
+                uint32_t r[32];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    tmem_ld32(s_addr + cc * 32, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) s[cc * 32 + i] = __uint_as_float(r[i]);
+                }
+            }
+            const int valid = p.kv_rows - j * AT_BLOCK_KV;
+            if (valid < AT_BLOCK_KV) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= valid) s[i] = -INFINITY;
+            }
+            float mx = s[0];
+#pragma unroll
+            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+
+            const bool need = (mx - m_ref) * c > 8.0f;  // true on the first block (m_ref = -inf)
+            if (j == 0) {
+                m_ref = mx;
+            } else if (__any_sync(0xffffffffu, need)) {
+                float alpha = 1.0f;
+                if (need) {
+                    alpha = fast_exp2((m_ref - mx) * c);
+                    m_ref = mx;
+                    l *= alpha;
+                }
+                // O_t holds PV over blocks < j: its last MMA must have landed before we touch it.
+                mbar_wait(o_done(t), uint32_t((j - 1) & 1), 0x207);
+                tc_fence_after();
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    uint32_t r[32];
+                    tmem_ld32(o_addr + cc * 32, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st32(o_addr + cc * 32, r);
+                }
+            }
+            const float mc = m_ref * c;
+            float sum = 0.f;
+#pragma unroll
+            for (int i = 0; i < 128; ++i) {
+                s[i] = fast_exp2(fmaf(s[i], c, -mc));
+                sum += s[i];
+            }
+            l += sum;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+                uint32_t r[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = pack_bf16x2(s[cc * 64 + 2 * i], s[cc * 64 + 2 * i + 1]);
+                tmem_st32(s_addr + cc * 32, r);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(t));
+        }
+
+        // ---- epilogue: O / l -> global
+        mbar_wait(o_done(t), uint32_t((n_blocks - 1) & 1), 0x208);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const bool store = q_row < p.q_rows;
+        const int b = bh / p.H, h = bh - b * p.H;
+        __nv_bfloat16* o_ptr =
+            p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D;
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+            uint32_t r[32];
+            tmem_ld32(o_addr + cc * 32, r);
+            tmem_wait_ld();
+            if (store) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(r[i + k]) * inv_l;
+                    uint4* dst = reinterpret_cast<uint4*>(o_ptr + cc * 32 + i);
+                    if (p.accumulate) {
+                        const uint4 old = *dst;
+                        f[0] = fmaf(p.out_scale, f[0], bf16_lo(old.x)); f[1] = fmaf(p.out_scale, f[1], bf16_hi(old.x));
+                        f[2] = fmaf(p.out_scale, f[2], bf16_lo(old.y)); f[3] = fmaf(p.out_scale, f[3], bf16_hi(old.y));
+                        f[4] = fmaf(p.out_scale, f[4], bf16_lo(old.z)); f[5] = fmaf(p.out_scale, f[5], bf16_hi(old.z));
+                        f[6] = fmaf(p.out_scale, f[6], bf16_lo(old.w)); f[7] = fmaf(p.out_scale, f[7], bf16_hi(old.w));
+                    }
+                    uint4 v;
+                    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+                    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+                    *dst = v;
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
+                           const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, tg_bf16* out,
+                           int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,
+                           float out_scale, void* stream) {
+    if (!q || !k || !v || !out) return fail(-1, "attn_fwd: null pointer");
+    if (B <= 0 || H <= 0 || q_rows <= 0 || kv_rows <= 0) return fail(-2, "attn_fwd: non-positive shape");
+    if (q_row0 < 0 || kv_row0 < 0 || q_row0 + q_rows > q_rows_alloc || kv_row0 + kv_rows > kv_rows_alloc)
+        return fail(-3, "attn_fwd: row window outside the allocation");
+    if (out_row0 < 0 || out_row0 + q_rows > out_rows_alloc) return fail(-4, "attn_fwd: output window outside the allocation");
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return fail(-5, "attn_fwd: pointers must be 16-byte aligned");
+    const int BH = B * H;
+    if (BH > 65535) return fail(-6, "attn_fwd: B*H too large");
+    CUtensorMap tq, tk, tv;
+    int rc = make_tmap_3d(&tq, q + q_row0 * AT_D, AT_D, uint64_t(q_rows), uint64_t(BH), AT_D * 2,
+                          uint64_t(q_rows_alloc) * AT_D * 2, AT_D, AT_BLOCK_Q);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tk, k + kv_row0 * AT_D, AT_D, uint64_t(kv_rows), uint64_t(BH), AT_D * 2,
+                      uint64_t(kv_rows_alloc) * AT_D * 2, AT_D, AT_BLOCK_KV);
+    if (rc) return rc;
+    rc = make_tmap_3d(&tv, v + kv_row0 * AT_D, AT_D, uint64_t(kv_rows), uint64_t(BH), AT_D * 2,
+                      uint64_t(kv_rows_alloc) * AT_D * 2, AT_D, AT_BLOCK_KV);
+    if (rc) return rc;
+    AttnParams p{};
+    p.q_rows = q_rows;
+    p.kv_rows = kv_rows;
+    p.H = H;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.out_rows_alloc = out_rows_alloc;
+    p.out_row0 = out_row0;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.accumulate = accumulate;
+    p.out_scale = out_scale;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
+    attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    return check_launch("attn_fwd");
+}

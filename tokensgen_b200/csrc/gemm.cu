@@ -1,0 +1,523 @@
+// tcgen05 GEMM family for the DiT projections.
+//
+//   out = epilogue(A[M,K] @ W[N,K]^T + bias)      A, W bf16 K-major; fp32 accumulation in TMEM.
+//
+// One persistent CTA per SM, 256 threads:
+//   warp 0      TMA producer   (A tile 128x64, W tile BLOCK_Nx64 per stage; 128-byte swizzle)
+//   warp 1      MMA issuer     (one elected lane: 4 x tcgen05.mma 128xBLOCK_Nx16 per stage)
+//   warp 2      TMEM allocator (2 accumulator buffers of BLOCK_N columns: epilogue of tile i overlaps mainloop of i+1)
+//   warps 4..7  epilogue       (thread = one output row: tcgen05.ld -> fused epilogue -> global)
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), tmem full/empty mbarriers (MMA <-> epilogue).
+//
+// Epilogues (all row-local because one thread owns one accumulator row):
+//   EPI_BIAS_ACT       bias (+ GELU-tanh / SiLU), bf16 store
+//   EPI_GATE_RESIDUAL  X[m,:] += gate(m) * (acc + bias), in place           (to_out / ff.net.2 + AdaLN-Zero gate)
+//   EPI_QKV            bias, per-head LayerNorm(64), 3D-RoPE, head-major store [B,H,rows,64]
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tg {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int GROUP_M = 16;  // m-tiles per scheduling group (L2 reuse of the weight tile)
+
+enum { EPI_BIAS_ACT = 0, EPI_GATE_RESIDUAL = 1, EPI_QKV = 2 };
+
+struct QkvProjDev {
+    __nv_bfloat16* out;
+    int out_rows;
+    const __nv_bfloat16* ln_w;
+    const __nv_bfloat16* ln_b;
+    const float* cos_video;
+    const float* sin_video;
+    const float* cos_vip;
+    const float* sin_vip;
+};
+
+struct GemmParams {
+    int M, N, K;
+    int m_tiles, n_tiles;
+    const __nv_bfloat16* bias;  // [N] or null
+    __nv_bfloat16* out;         // EPI_BIAS_ACT: out; EPI_GATE_RESIDUAL: X (in place)
+    int64_t ldo;
+    int act;
+    tg_rowmap map;
+    tg_modvec gate;
+    // EPI_QKV
+    QkvProjDev proj[6];
+    int heads;
+    float ln_eps;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+    static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 512 / 256 / 128
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+};
+
+struct RowInfo {
+    int b, r, seg, frame;  // seg: 0 text, 1 video, 2 vip
+};
+__device__ __forceinline__ RowInfo row_info(const tg_rowmap& m, int row) {
+    RowInfo ri;
+    ri.b = row / m.rows_per_batch;
+    ri.r = row - ri.b * m.rows_per_batch;
+    if (ri.r < m.n_text) {
+        ri.seg = 0;
+        ri.frame = 0;
+    } else if (ri.r < m.n_text + m.n_video) {
+        ri.seg = 1;
+        ri.frame = (ri.r - m.n_text) / m.hw;
+    } else {
+        ri.seg = 2;
+        ri.frame = 0;
+    }
+    return ri;
+}
+__device__ __forceinline__ const __nv_bfloat16* modvec_row(const tg_modvec& v, const tg_rowmap& m, const RowInfo& ri) {
+    const tg_bf16* p;
+    if (ri.seg == 0)
+        p = v.text ? v.text + int64_t(ri.b * m.frames) * v.ld_text : nullptr;
+    else if (ri.seg == 1)
+        p = v.video ? v.video + int64_t(ri.b * m.frames + ri.frame) * v.ld_video : nullptr;
+    else
+        p = v.vip ? v.vip + int64_t(ri.b * m.frames) * v.ld_vip : nullptr;
+    return reinterpret_cast<const __nv_bfloat16*>(p);
+}
+
+__device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, int& mt, int& nt) {
+    const int group_sz = GROUP_M * n_tiles;
+    const int g = tile / group_sz;
+    const int first_m = g * GROUP_M;
+    const int gm = min(GROUP_M, m_tiles - first_m);
+    const int in_g = tile - g * group_sz;
+    mt = first_m + in_g % gm;
+    nt = in_g / gm;
+}
+
+__device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
+    uint4 v = *reinterpret_cast<const uint4*>(p);
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ void store8_bf16(__nv_bfloat16* p, const float* f) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = v;
+}
+
+// ---- epilogue bodies: `acc` = 32 or 64 fp32 accumulator columns of one row, starting at global column n.
+template <int NC>
+__device__ __forceinline__ void add_bias(float (&acc)[NC], const __nv_bfloat16* bias, int n) {
+    if (bias == nullptr) return;
+#pragma unroll
+    for (int i = 0; i < NC; i += 8) {
+        float b[8];
+        load8_bf16(bias + n + i, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i + j] += b[j];
+    }
+}
+
+__device__ __forceinline__ void epi_bias_act(const GemmParams& p, float (&acc)[32], int row, int n) {
+    add_bias<32>(acc, p.bias, n);
+    if (p.act == TG_ACT_GELU_TANH) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = gelu_tanh(acc[i]);
+    } else if (p.act == TG_ACT_SILU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc[i] = __fdividef(acc[i], 1.0f + __expf(-acc[i]));
+    }
+    if (row < p.M) {
+        __nv_bfloat16* o = p.out + int64_t(row) * p.ldo + n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) store8_bf16(o + i, &acc[i]);
+    }
+}
+
+__device__ __forceinline__ void epi_gate_residual(const GemmParams& p, float (&acc)[32], int row, int n) {
+    add_bias<32>(acc, p.bias, n);
+    if (row < p.M) {
+        const RowInfo ri = row_info(p.map, row);
+        const __nv_bfloat16* g = modvec_row(p.gate, p.map, ri);
+        __nv_bfloat16* x = p.out + int64_t(row) * p.ldo + n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+            float gv[8], xv[8];
+            load8_bf16(g + n + i, gv);
+            load8_bf16(x + i, xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) xv[j] = fmaf(gv[j], acc[i + j], xv[j]);
+            store8_bf16(x + i, xv);
+        }
+    }
+}
+
+// One head (64 columns) of one projection for one row.
+__device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], int row, int n) {
+    add_bias<64>(acc, p.bias, n);
+    const int inner = p.heads * 64;
+    const int pi = n / inner;
+    const int head = (n - pi * inner) >> 6;
+    const QkvProjDev& pr = p.proj[pi];
+    if (pr.ln_w != nullptr) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) s += acc[i];
+        const float mean = s * (1.0f / 64.0f);
+        float ss = 0.f;
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            const float d = acc[i] - mean;
+            ss = fmaf(d, d, ss);
+        }
+        const float rstd = rsqrtf(ss * (1.0f / 64.0f) + p.ln_eps);
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+            float w[8], b[8];
+            load8_bf16(pr.ln_w + i, w);
+            load8_bf16(pr.ln_b + i, b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i + j] = fmaf((acc[i + j] - mean) * rstd, w[j], b[j]);
+        }
+    }
+    if (row >= p.M) return;
+    const RowInfo ri = row_info(p.map, row);
+    if (ri.r >= pr.out_rows) return;
+    const float* cs = nullptr;
+    const float* sn = nullptr;
+    if (ri.seg == 1 && pr.cos_video != nullptr) {
+        cs = pr.cos_video + int64_t(ri.r - p.map.n_text) * 64;
+        sn = pr.sin_video + int64_t(ri.r - p.map.n_text) * 64;
+    } else if (ri.seg == 2 && pr.cos_vip != nullptr) {
+        cs = pr.cos_vip + int64_t(ri.r - p.map.n_text - p.map.n_video) * 64;
+        sn = pr.sin_vip + int64_t(ri.r - p.map.n_text - p.map.n_video) * 64;
+    }
+    if (cs != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+            const float4 c = *reinterpret_cast<const float4*>(cs + i);
+            const float4 s = *reinterpret_cast<const float4*>(sn + i);
+            const float x0 = acc[i], x1 = acc[i + 1], x2 = acc[i + 2], x3 = acc[i + 3];
+            acc[i] = x0 * c.x - x1 * s.x;
+            acc[i + 1] = x1 * c.y + x0 * s.y;
+            acc[i + 2] = x2 * c.z - x3 * s.z;
+            acc[i + 3] = x3 * c.w + x2 * s.w;
+        }
+    }
+    __nv_bfloat16* o = pr.out + (int64_t(ri.b * p.heads + head) * pr.out_rows + ri.r) * 64;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) store8_bf16(o + i, &acc[i]);
+}
+
+template <int BLOCK_N, int EPI>
+__global__ void __launch_bounds__(256, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const __grid_constant__ GemmParams p) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int k_blocks = p.K / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int mt, nt;
+                tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u, 0x101);
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmap_a, full_bar(stage), kb * BLOCK_K, mt * BLOCK_M);
+                    tma_load_2d(sa + Cfg::A_BYTES, &tmap_b, full_bar(stage), kb * BLOCK_K, nt * BLOCK_N);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x102);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x103);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * UMMA_K * 2, 16, 1024);
+                        umma_ss(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));  // smem slot free once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(acc));  // accumulator complete
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ epilogue
+        const int ew = warp & 3;  // TMEM lane quarter this warp may touch
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int mt, nt;
+            tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+            const int row = mt * BLOCK_M + ew * 32 + lane;
+            mbar_wait(tfull_bar(acc), acc_phase, 0x104);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
+            if constexpr (EPI == EPI_QKV) {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 64) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_row + c, r0);
+                    tmem_ld32(t_row + c + 32, r1);
+                    tmem_wait_ld();
+                    float accv[64];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        accv[i] = __uint_as_float(r0[i]);
+                        accv[32 + i] = __uint_as_float(r1[i]);
+                    }
+                    epi_qkv(p, accv, row, nt * BLOCK_N + c);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t r0[32];
+                    tmem_ld32(t_row + c, r0);
+                    tmem_wait_ld();
+                    float accv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) accv[i] = __uint_as_float(r0[i]);
+                    if constexpr (EPI == EPI_BIAS_ACT)
+                        epi_bias_act(p, accv, row, nt * BLOCK_N + c);
+                    else
+                        epi_gate_residual(p, accv, row, nt * BLOCK_N + c);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------- host side
+template <int BLOCK_N, int EPI>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = GemmCfg<BLOCK_N>;
+    auto kern = gemm_kernel<BLOCK_N, EPI>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "gemm: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(ta, tb, p);
+    return check_launch("gemm");
+}
+
+static int check_common(const void* A, int64_t lda, const void* W, int M, int N, int K) {
+    if (A == nullptr || W == nullptr) return fail(-1, "gemm: null operand");
+    if (M <= 0 || N <= 0 || K <= 0) return fail(-2, "gemm: non-positive shape M=%d N=%d K=%d", M, N, K);
+    if (K % BLOCK_K != 0) return fail(-3, "gemm: K=%d must be a multiple of %d", K, BLOCK_K);
+    if (N % 64 != 0) return fail(-4, "gemm: N=%d must be a multiple of 64", N);
+    if (lda % 8 != 0 || lda < K) return fail(-5, "gemm: lda=%lld must be >= K and a multiple of 8", (long long)lda);
+    if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(W) & 15))
+        return fail(-6, "gemm: operands must be 16-byte aligned");
+    return 0;
+}
+
+template <int EPI>
+static int dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, GemmParams& p, cudaStream_t stream) {
+    const int bn = (EPI == EPI_QKV) ? 256 : (p.N % 256 == 0 ? 256 : (p.N % 128 == 0 ? 128 : 64));
+    p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+    p.n_tiles = p.N / bn;
+    CUtensorMap ta, tb;
+    int rc = make_tmap_2d(&ta, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, BLOCK_K, BLOCK_M);
+    if (rc) return rc;
+    rc = make_tmap_2d(&tb, W, uint64_t(p.K), uint64_t(p.N), uint64_t(p.K) * 2, BLOCK_K, uint32_t(bn));
+    if (rc) return rc;
+    if (bn == 256) return launch_gemm<256, EPI>(ta, tb, p, stream);
+    if constexpr (EPI != EPI_QKV) {
+        if (bn == 128) return launch_gemm<128, EPI>(ta, tb, p, stream);
+        return launch_gemm<64, EPI>(ta, tb, p, stream);
+    }
+    return fail(-7, "gemm: unsupported tile");
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" int tg_gemm_bias_act(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, tg_bf16* out,
+                                int64_t ldo, int M, int N, int K, int act, void* stream) {
+    int rc = check_common(A, lda, W, M, N, K);
+    if (rc) return rc;
+    if (out == nullptr || ldo % 8 != 0 || ldo < N || (reinterpret_cast<uintptr_t>(out) & 15))
+        return fail(-8, "gemm_bias_act: bad output (ldo=%lld)", (long long)ldo);
+    if (act < TG_ACT_NONE || act > TG_ACT_SILU) return fail(-9, "gemm_bias_act: unknown activation %d", act);
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.ldo = ldo;
+    p.act = act;
+    return dispatch<EPI_BIAS_ACT>(reinterpret_cast<const __nv_bfloat16*>(A), lda,
+                                  reinterpret_cast<const __nv_bfloat16*>(W), p, static_cast<cudaStream_t>(stream));
+}
+
+static int check_rowmap(const tg_rowmap* map) {
+    if (map == nullptr) return fail(-10, "rowmap is null");
+    if (map->n_text < 0 || map->n_video < 0 || map->n_vip < 0 ||
+        map->rows_per_batch != map->n_text + map->n_video + map->n_vip || map->rows_per_batch <= 0)
+        return fail(-11, "rowmap: rows_per_batch must equal n_text+n_video+n_vip");
+    if (map->n_video > 0 && (map->hw <= 0 || map->frames <= 0 || map->n_video != map->hw * map->frames))
+        return fail(-12, "rowmap: n_video must equal hw*frames");
+    if (map->frames <= 0) return fail(-13, "rowmap: frames must be positive");
+    return 0;
+}
+
+extern "C" int tg_gemm_gate_residual(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, tg_bf16* X,
+                                     int64_t ldx, int B, int N, int K, const tg_rowmap* map, const tg_modvec* gate,
+                                     void* stream) {
+    int rc = check_rowmap(map);
+    if (rc) return rc;
+    if (B <= 0) return fail(-2, "gemm_gate_residual: B=%d", B);
+    const int M = B * map->rows_per_batch;
+    rc = check_common(A, lda, W, M, N, K);
+    if (rc) return rc;
+    if (X == nullptr || ldx % 8 != 0 || ldx < N || (reinterpret_cast<uintptr_t>(X) & 15))
+        return fail(-8, "gemm_gate_residual: bad X (ldx=%lld)", (long long)ldx);
+    if (gate == nullptr) return fail(-14, "gemm_gate_residual: gate is null");
+    if ((map->n_text > 0 && !gate->text) || (map->n_video > 0 && !gate->video) || (map->n_vip > 0 && !gate->vip))
+        return fail(-15, "gemm_gate_residual: a populated segment has no gate vector");
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    p.out = reinterpret_cast<__nv_bfloat16*>(X);
+    p.ldo = ldx;
+    p.map = *map;
+    p.gate = *gate;
+    return dispatch<EPI_GATE_RESIDUAL>(reinterpret_cast<const __nv_bfloat16*>(A), lda,
+                                       reinterpret_cast<const __nv_bfloat16*>(W), p,
+                                       static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H,
+                                int K, const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps,
+                                void* stream) {
+    int rc = check_rowmap(map);
+    if (rc) return rc;
+    if (B <= 0 || H <= 0) return fail(-2, "qkv_rope_gemm: B=%d H=%d", B, H);
+    if (nproj < 1 || nproj > 6 || proj == nullptr) return fail(-16, "qkv_rope_gemm: nproj=%d (1..6)", nproj);
+    if ((H * 64) % 256 != 0) return fail(-17, "qkv_rope_gemm: H*64 must be a multiple of 256");
+    const int M = B * map->rows_per_batch;
+    const int N = nproj * H * 64;
+    rc = check_common(A, lda, W, M, N, K);
+    if (rc) return rc;
+    GemmParams p{};
+    p.M = M; p.N = N; p.K = K;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
+    p.map = *map;
+    p.heads = H;
+    p.ln_eps = ln_eps;
+    for (int i = 0; i < nproj; ++i) {
+        if (proj[i].out == nullptr || proj[i].out_rows <= 0 || proj[i].out_rows > map->rows_per_batch)
+            return fail(-18, "qkv_rope_gemm: projection %d has a bad output", i);
+        if ((proj[i].ln_w == nullptr) != (proj[i].ln_b == nullptr) ||
+            (proj[i].cos_video == nullptr) != (proj[i].sin_video == nullptr) ||
+            (proj[i].cos_vip == nullptr) != (proj[i].sin_vip == nullptr))
+            return fail(-19, "qkv_rope_gemm: projection %d has half of a (weight,bias) or (cos,sin) pair", i);
+        p.proj[i].out = reinterpret_cast<__nv_bfloat16*>(proj[i].out);
+        p.proj[i].out_rows = proj[i].out_rows;
+        p.proj[i].ln_w = reinterpret_cast<const __nv_bfloat16*>(proj[i].ln_w);
+        p.proj[i].ln_b = reinterpret_cast<const __nv_bfloat16*>(proj[i].ln_b);
+        p.proj[i].cos_video = proj[i].cos_video;
+        p.proj[i].sin_video = proj[i].sin_video;
+        p.proj[i].cos_vip = proj[i].cos_vip;
+        p.proj[i].sin_vip = proj[i].sin_vip;
+    }
+    return dispatch<EPI_QKV>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
+                             p, static_cast<cudaStream_t>(stream));
+}

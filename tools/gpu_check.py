@@ -1,0 +1,368 @@
+"""Bring-up checks for the CUDA kernels against plain torch math on the same GPU.
+
+Each group runs in its own subprocess (a trapped kernel kills the CUDA context) under a timeout.
+    python tools/gpu_check.py            # all groups
+    python tools/gpu_check.py gemm attn  # selected groups
+This is a developer tool, not the parity suite (tests/ holds that).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+GROUPS = ["gemm", "gemm_epi", "attn", "elem"]
+
+
+def rel_l2(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def report(name, got, ref, tol):
+    import torch
+    err = rel_l2(got, ref)
+    mx = (got.float() - ref.float()).abs().max().item()
+    bad = not (err < tol) or not torch.isfinite(got.float()).all().item()
+    print(f"  [{'FAIL' if bad else ' ok '}] {name}: rel_l2={err:.3e} max_abs={mx:.3e} (tol {tol:.1e})", flush=True)
+    return not bad
+
+
+def run_gemm():
+    import torch
+    from tokensgen_b200 import _ext as E
+    torch.manual_seed(0)
+    dev = "cuda"
+    ok = True
+    for (M, N, K) in [(128, 256, 64), (128, 256, 256), (128, 128, 128), (128, 64, 64), (300, 512, 256), (26, 512, 512),
+                      (1000, 3072, 3072), (4096, 12288, 3072), (36512, 3072, 3072)]:
+        a = torch.randn(M, K, device=dev).bfloat16()
+        w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+        b = torch.randn(N, device=dev).bfloat16()
+        out = E.gemm_bias_act(a, w, b)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().T + b.float()
+        good = report(f"gemm_bias_act M={M} N={N} K={K}", out, ref, 5e-3)
+        if not good and M <= 300:
+            d = (out.float() - ref).abs()
+            print("     row err profile:", d.max(dim=1).values[:16].tolist())
+            print("     col err profile:", d.max(dim=0).values[:16].tolist())
+            print("     out[0,:8]", out[0, :8].tolist(), "ref", ref[0, :8].tolist())
+        ok &= good
+    # gelu
+    a = torch.randn(500, 256, device=dev).bfloat16()
+    w = (torch.randn(512, 256, device=dev) / 16).bfloat16()
+    b = torch.randn(512, device=dev).bfloat16()
+    out = E.gemm_bias_act(a, w, b, act=E.ACT_GELU_TANH)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().T + b.float(), approximate="tanh")
+    ok &= report("gemm gelu-tanh", out, ref, 5e-3)
+    # timing of the big one
+    M, N, K = 36512, 3072, 3072
+    a = torch.randn(M, K, device=dev).bfloat16()
+    w = (torch.randn(N, K, device=dev) / K ** 0.5).bfloat16()
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        E.gemm_bias_act(a, w, None, out)
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    for _ in range(10):
+        E.gemm_bias_act(a, w, None, out)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f"  gemm {M}x{N}x{K}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    s.record()
+    for _ in range(10):
+        torch.matmul(a, w.T)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 10
+    print(f"  cublas same shape: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s")
+    return ok
+
+
+def run_gemm_epi():
+    import torch
+    from tokensgen_b200 import _ext as E
+    torch.manual_seed(1)
+    dev = "cuda"
+    ok = True
+    B, F, hw, n_text, n_vip, d, H = 2, 3, 50, 26, 40, 512, 8
+    n_video = F * hw
+    rows = n_text + n_video + n_vip
+    rm = E.make_rowmap(n_text, n_video, n_vip, hw, F)
+    # ---- gate residual
+    K = 256
+    a = torch.randn(B * rows, K, device=dev).bfloat16()
+    w = (torch.randn(d, K, device=dev) / K ** 0.5).bfloat16()
+    bias = torch.randn(d, device=dev).bfloat16()
+    x = torch.randn(B * rows, d, device=dev).bfloat16()
+    table = torch.randn(B * F, 3 * d, device=dev).bfloat16()
+    vtable = torch.randn(B * F, d, device=dev).bfloat16()
+    gate = E.make_modvec(table[:, d:2 * d], table[:, 0:d], vtable)
+    x_ref = x.float().view(B, rows, d).clone()
+    y = (a.float() @ w.float().T + bias.float()).view(B, rows, d)
+    t3 = table.float().view(B, F, 3 * d)
+    x_ref[:, :n_text] += t3[:, 0:1, d:2 * d] * y[:, :n_text]
+    gv = t3[:, :, 0:d].repeat_interleave(hw, dim=1)
+    x_ref[:, n_text:n_text + n_video] += gv * y[:, n_text:n_text + n_video]
+    x_ref[:, n_text + n_video:] += vtable.float().view(B, F, d)[:, 0:1] * y[:, n_text + n_video:]
+    E.gemm_gate_residual(a, w, bias, x, B, rm, gate)
+    torch.cuda.synchronize()
+    ok &= report("gemm_gate_residual", x.view(B, rows, d), x_ref, 5e-3)
+
+    # ---- qkv + head LN + rope
+    K = d
+    a = torch.randn(B * rows, K, device=dev).bfloat16()
+    nproj = 6
+    w = (torch.randn(nproj * H * 64, K, device=dev) / K ** 0.5).bfloat16()
+    bias = torch.randn(nproj * H * 64, device=dev).bfloat16()
+    lnw = [torch.randn(64, device=dev).bfloat16() for _ in range(4)]
+    lnb = [torch.randn(64, device=dev).bfloat16() for _ in range(4)]
+    cos_v, sin_v = torch.randn(n_video, 64, device=dev), torch.randn(n_video, 64, device=dev)
+    cos_i, sin_i = torch.randn(n_video, 64, device=dev), torch.randn(n_video, 64, device=dev)
+    cos_c, sin_c = torch.randn(n_vip, 64, device=dev), torch.randn(n_vip, 64, device=dev)
+    base_rows = n_text + n_video
+    outs = [torch.zeros(B, H, base_rows if i < 3 else rows, 64, device=dev, dtype=torch.bfloat16) for i in range(nproj)]
+    projs = []
+    for i in range(nproj):
+        pr = E.QkvProj()
+        pr.out = outs[i].data_ptr()
+        pr.out_rows = outs[i].shape[2]
+        if i in (0, 1):
+            pr.ln_w, pr.ln_b = lnw[i].data_ptr(), lnb[i].data_ptr()
+            pr.cos_video, pr.sin_video = cos_v.data_ptr(), sin_v.data_ptr()
+        elif i in (3, 4):
+            pr.ln_w, pr.ln_b = lnw[i - 1].data_ptr(), lnb[i - 1].data_ptr()
+            pr.cos_video, pr.sin_video = cos_i.data_ptr(), sin_i.data_ptr()
+            pr.cos_vip, pr.sin_vip = cos_c.data_ptr(), sin_c.data_ptr()
+        projs.append(pr)
+    E.qkv_rope_gemm(a, w, bias, B, H, rm, projs, 1e-6)
+    torch.cuda.synchronize()
+    y = (a.float() @ w.float().T + bias.float()).view(B, rows, nproj, H, 64).permute(2, 0, 3, 1, 4)  # p,B,H,rows,64
+
+    def rope(t, cos, sin):
+        x0, x1 = t[..., 0::2], t[..., 1::2]
+        rot = torch.stack([-x1, x0], dim=-1).flatten(-2)
+        return t * cos + rot * sin
+
+    for i in range(nproj):
+        t = y[i].clone()
+        if i in (0, 1, 3, 4):
+            j = i if i < 2 else i - 1
+            t = torch.nn.functional.layer_norm(t, (64,), lnw[j].float(), lnb[j].float(), 1e-6)
+            cv, sv = (cos_v, sin_v) if i < 2 else (cos_i, sin_i)
+            t[:, :, n_text:n_text + n_video] = rope(t[:, :, n_text:n_text + n_video], cv, sv)
+            if i >= 3:
+                t[:, :, n_text + n_video:] = rope(t[:, :, n_text + n_video:], cos_c, sin_c)
+        t = t[:, :, :outs[i].shape[2]]
+        ok &= report(f"qkv proj {i}", outs[i], t, 6e-3)
+    return ok
+
+
+def attn_ref(q, k, v, scale):
+    import torch
+    s = torch.einsum("bhqd,bhkd->bhqk", q.float(), k.float()) * scale
+    p = torch.softmax(s, dim=-1)
+    o = torch.einsum("bhqk,bhkd->bhqd", p, v.float())
+    return o.permute(0, 2, 1, 3).flatten(2)  # [B, Nq, H*64]
+
+
+def run_attn():
+    import torch
+    from tokensgen_b200 import _ext as E
+    torch.manual_seed(2)
+    dev = "cuda"
+    ok = True
+    for (B, H, Nq, Nkv, boost) in [(1, 1, 256, 128, 0), (1, 1, 128, 128, 0), (1, 2, 300, 200, 0), (2, 3, 520, 1000, 0),
+                                   (1, 2, 256, 1024, 1), (1, 4, 1000, 2341, 1), (2, 48, 2048, 2048, 0)]:
+        q = torch.randn(B, H, Nq, 64, device=dev).bfloat16()
+        k = torch.randn(B, H, Nkv, 64, device=dev).bfloat16()
+        v = torch.randn(B, H, Nkv, 64, device=dev).bfloat16()
+        if boost:  # growing score magnitude along kv -> exercises the lazy O rescale
+            ramp = torch.linspace(0.2, 3.0, Nkv, device=dev).view(1, 1, Nkv, 1)
+            k = (k.float() * ramp).bfloat16()
+        out = torch.zeros(B, Nq, H * 64, device=dev, dtype=torch.bfloat16)
+        E.attn_fwd(q, k, v, out)
+        torch.cuda.synchronize()
+        ref = attn_ref(q, k, v, 0.125)
+        good = report(f"attn B={B} H={H} Nq={Nq} Nkv={Nkv} boost={boost}", out, ref, 1e-2)
+        if not good and Nq <= 300:
+            d = (out.float() - ref).abs()
+            print("     per-row max err[:8]", d[0].max(dim=1).values[:8].tolist())
+            print("     per-col max err[:16]", d[0].max(dim=0).values[:16].tolist())
+            print("     out[0,0,:8]", out[0, 0, :8].tolist())
+            print("     ref[0,0,:8]", ref[0, 0, :8].tolist())
+        ok &= good
+    # windows + accumulate: q rows [100, 100+300) of 500, kv rows [50, 50+333) of 400, out rows offset 7
+    B, H = 1, 2
+    q = torch.randn(B, H, 500, 64, device=dev).bfloat16()
+    k = torch.randn(B, H, 400, 64, device=dev).bfloat16()
+    v = torch.randn(B, H, 400, 64, device=dev).bfloat16()
+    out = torch.randn(B, 320, H * 64, device=dev).bfloat16()
+    base = out.clone()
+    E.attn_fwd(q, k, v, out, q_row0=100, q_rows=300, kv_row0=50, kv_rows=333, out_row0=7, accumulate=True, out_scale=0.6015625)
+    torch.cuda.synchronize()
+    ref = base.float()
+    ref[:, 7:307] += 0.6015625 * attn_ref(q[:, :, 100:400], k[:, :, 50:383], v[:, :, 50:383], 0.125)
+    ok &= report("attn windows+accumulate", out, ref, 1e-2)
+    # full-size timing
+    B, H, N = 2, 48, 17776
+    q = torch.randn(B, H, N, 64, device=dev).bfloat16()
+    k = torch.randn(B, H, N, 64, device=dev).bfloat16()
+    v = torch.randn(B, H, N, 64, device=dev).bfloat16()
+    out = torch.empty(B, N, H * 64, device=dev, dtype=torch.bfloat16)
+    for _ in range(2):
+        E.attn_fwd(q, k, v, out)
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    for _ in range(5):
+        E.attn_fwd(q, k, v, out)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 5
+    fl = 4 * B * H * N * N * 64
+    print(f"  attn full {B}x{H}x{N}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).flatten(2)
+    ok &= report("attn full vs torch sdpa(bf16)", out, ref, 1e-2)
+    s.record()
+    for _ in range(5):
+        torch.nn.functional.scaled_dot_product_attention(q, k, v)
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / 5
+    print(f"  torch sdpa same shape: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    return ok
+
+
+def run_elem():
+    import torch
+    from tokensgen_b200 import _ext as E
+    torch.manual_seed(3)
+    dev = "cuda"
+    ok = True
+    # ---- ln_modulate
+    B, F, hw, n_text, n_vip, d = 2, 3, 50, 26, 40, 3072
+    n_video = F * hw
+    rows = n_text + n_video + n_vip
+    rm = E.make_rowmap(n_text, n_video, n_vip, hw, F)
+    x = (torch.randn(B * rows, d, device=dev) * 2 + 0.5).bfloat16()
+    w, b = torch.randn(d, device=dev).bfloat16(), torch.randn(d, device=dev).bfloat16()
+    vw, vb = torch.randn(d, device=dev).bfloat16(), torch.randn(d, device=dev).bfloat16()
+    table = (torch.randn(B * F, 6 * d, device=dev) * 0.3).bfloat16()
+    vtable = (torch.randn(B * F, 3 * d, device=dev) * 0.3).bfloat16()
+    shift = E.make_modvec(table[:, 3 * d:4 * d], table[:, 0:d], vtable[:, 0:d])
+    scale = E.make_modvec(table[:, 4 * d:5 * d], table[:, d:2 * d], vtable[:, d:2 * d])
+    out = torch.empty_like(x)
+    E.ln_modulate(x, out, B, rm, w, b, vw, vb, 1e-5, shift, scale)
+    torch.cuda.synchronize()
+    xf = x.float().view(B, rows, d)
+    t = table.float().view(B, F, 6 * d)
+    vt = vtable.float().view(B, F, 3 * d)
+    ln = torch.nn.functional.layer_norm(xf, (d,), w.float(), b.float(), 1e-5)
+    lnv = torch.nn.functional.layer_norm(xf, (d,), vw.float(), vb.float(), 1e-5)
+    ref = torch.empty_like(xf)
+    ref[:, :n_text] = ln[:, :n_text] * (1 + t[:, 0:1, 4 * d:5 * d]) + t[:, 0:1, 3 * d:4 * d]
+    ref[:, n_text:n_text + n_video] = ln[:, n_text:n_text + n_video] * (1 + t[:, :, d:2 * d].repeat_interleave(hw, 1)) \
+        + t[:, :, 0:d].repeat_interleave(hw, 1)
+    ref[:, n_text + n_video:] = lnv[:, n_text + n_video:] * (1 + vt[:, 0:1, d:2 * d]) + vt[:, 0:1, 0:d]
+    ok &= report("ln_modulate", out.view(B, rows, d), ref, 4e-3)
+    # ---- time embedding
+    ts = torch.tensor([999., 980., 500., 3., 0., 123.], device=dev)
+    w1 = (torch.randn(512, 3072, device=dev) / 3072 ** 0.5).bfloat16()
+    b1 = torch.randn(512, device=dev).bfloat16()
+    w2 = (torch.randn(512, 512, device=dev) / 512 ** 0.5).bfloat16()
+    b2 = torch.randn(512, device=dev).bfloat16()
+    emb, silu = E.time_embedding(ts, w1, b1, w2, b2, 3072)
+    torch.cuda.synchronize()
+    import math
+    half = 1536
+    ex = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32, device=dev) / half)
+    arg = ts[:, None] * ex[None]
+    te = torch.cat([torch.cos(arg), torch.sin(arg)], -1).bfloat16().float()
+    h = torch.nn.functional.silu((te @ w1.float().T + b1.float()).bfloat16().float()).bfloat16().float()
+    e_ref = (h @ w2.float().T + b2.float())
+    ok &= report("time_embedding emb", emb, e_ref, 5e-3)
+    ok &= report("time_embedding silu", silu, torch.nn.functional.silu(e_ref), 8e-3)
+    # ---- patchify / unpatchify (bit exact)
+    lat = torch.randn(2, 3, 16, 60, 90, device=dev).bfloat16()
+    rowsT = E.patchify(lat, 2)
+    ref_rows = lat.view(2, 3, 16, 30, 2, 45, 2).permute(0, 1, 3, 5, 2, 4, 6).reshape(-1, 64)
+    same = torch.equal(rowsT, ref_rows)
+    back = E.unpatchify(rowsT, 2, 3, 16, 60, 90, 2)
+    same2 = torch.equal(back, lat)
+    print(f"  [{' ok ' if same and same2 else 'FAIL'}] patchify bit-exact={same} unpatchify round-trip={same2}")
+    ok &= same and same2
+    # ---- cfg + dpm step, both chains, against op-by-op torch
+    Fw, chw = 5, 16 * 60 * 90
+    npred = torch.randn(2, Fw, chw, device=dev).bfloat16()
+    sample = torch.randn(Fw, chw, device=dev).bfloat16()
+    old = torch.randn(Fw, chw, device=dev).bfloat16()
+    n1 = torch.randn(Fw, chw, device=dev).bfloat16()
+    n2 = torch.randn(Fw, chw, device=dev).bfloat16()
+    coef64 = torch.rand(Fw, 8, dtype=torch.float64) + 0.1
+    coef64[:, 7] = torch.tensor([0, 1, 1, 0, 1], dtype=torch.float64)
+    coef = coef64.float().to(dev)
+    g = 6.0
+    prev, x0 = E.cfg_dpm_step(npred, sample, old, n1, n2, coef, g, E.DPM_BF16_CHAIN)
+    torch.cuda.synchronize()
+    pr_ref, x0_ref = torch.empty_like(sample), torch.empty_like(sample)
+    for f in range(Fw):
+        c = [coef64[f, i] for i in range(8)]  # 0-dim f64 tensors like the scheduler's
+        u, t_ = npred[0, f], npred[1, f]
+        mo = u + g * (t_ - u)
+        s_ = sample[f]
+        x0f = c[0] * s_ - c[1] * mo
+        if coef64[f, 7] == 0:
+            p_ = c[2] * s_ - c[3] * x0f + c[6] * n1[f]
+        else:
+            dd = c[4] * x0f - c[5] * old[f]
+            p_ = c[2] * s_ - c[3] * dd + c[6] * n2[f]
+        pr_ref[f], x0_ref[f] = p_, x0f
+    e1, e2 = torch.equal(prev, pr_ref), torch.equal(x0, x0_ref)
+    print(f"  [{' ok ' if e1 and e2 else 'FAIL'}] cfg_dpm_step bf16 chain bit-exact prev={e1} x0={e2} "
+          f"(mismatch {(prev != pr_ref).float().mean().item():.2e})")
+    ok &= e1 and e2
+    oldf = old.float() * 1.37
+    prev, x0 = E.cfg_dpm_step(npred, sample, oldf, n1, n2, coef, g, E.DPM_BASE_CHAIN)
+    torch.cuda.synchronize()
+    pr_ref, x0_ref = torch.empty_like(sample), torch.empty(Fw, chw, device=dev)
+    for f in range(Fw):
+        c = [coef64[f, i] for i in range(8)]
+        u, t_ = npred[0, f].float(), npred[1, f].float()
+        mo = u + g * (t_ - u)
+        s_ = sample[f]
+        x0f = c[0] * s_ - c[1] * mo
+        if coef64[f, 7] == 0:
+            p_ = c[2] * s_ - c[3] * x0f + c[6] * n1[f]
+        else:
+            dd = c[4] * x0f - c[5] * oldf[f]
+            p_ = c[2] * s_ - c[3] * dd + c[6] * n2[f]
+        pr_ref[f], x0_ref[f] = p_.to(torch.bfloat16), x0f
+    e1, e2 = torch.equal(prev, pr_ref), torch.equal(x0, x0_ref)
+    print(f"  [{' ok ' if e1 and e2 else 'FAIL'}] cfg_dpm_step base chain bit-exact prev={e1} x0={e2} "
+          f"(mismatch {(prev != pr_ref).float().mean().item():.2e}, {(x0 != x0_ref).float().mean().item():.2e})")
+    ok &= e1 and e2
+    return ok
+
+
+if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "--one":
+        fn = {"gemm": run_gemm, "gemm_epi": run_gemm_epi, "attn": run_attn, "elem": run_elem}[sys.argv[2]]
+        sys.exit(0 if fn() else 1)
+    groups = sys.argv[1:] or GROUPS
+    rc = 0
+    for g in groups:
+        print(f"== {g}", flush=True)
+        t0 = time.time()
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--one", g], timeout=300)
+            code = r.returncode
+        except subprocess.TimeoutExpired:
+            code = 124
+        print(f"== {g}: exit {code} in {time.time() - t0:.1f}s", flush=True)
+        rc |= code != 0
+    sys.exit(rc)
