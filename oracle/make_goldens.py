@@ -1,0 +1,252 @@
+"""Generates tests/golden/* by running the UNMODIFIED reference (/root/reference via oracle/stubs) on seeded inputs.
+
+Run in the build container only:  python -m oracle.make_goldens
+Outputs are small (.pt / .json) and committed; the GPU box never needs /root/reference.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import queue
+import sys
+import threading
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from oracle import ref_import
+from oracle.synth import dit_shapes, state_dict_digest, synth_state_dict
+
+GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+TINY = dict(heads=4, head_dim=64, layers=2, time_dim=128, text_dim=128, in_ch=16, out_ch=16, patch=2, vip_dim=128)
+TINY_VIP = dict(length=12, func_type="1", scale=[0.6],
+                resampler_params=dict(output_dim=128, num_height_queries=2, num_width_queries=3, num_temporal_queries=1))
+TINY_GEOM = dict(B=2, F=3, H=8, W=12, n_text=10)
+
+
+def _sha(t: torch.Tensor) -> str:
+    return hashlib.sha256(t.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes()).hexdigest()
+
+
+def build_ref_tiny(use_vip: bool):
+    from longvgen.models.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    c = TINY
+    m = CogVideoXTransformer3DModel(
+        num_attention_heads=c["heads"], attention_head_dim=c["head_dim"], in_channels=c["in_ch"], out_channels=c["out_ch"],
+        time_embed_dim=c["time_dim"], text_embed_dim=c["text_dim"], num_layers=c["layers"], patch_size=c["patch"],
+        sample_width=TINY_GEOM["W"], sample_height=TINY_GEOM["H"], sample_frames=9, max_text_seq_length=TINY_GEOM["n_text"],
+        use_rotary_positional_embeddings=True, attention_bias=True)
+    if use_vip:
+        m.set_vip_layers(None, **TINY_VIP)
+    return m.eval()
+
+
+def tiny_inputs(seed: int, per_frame_t: bool):
+    g = torch.Generator().manual_seed(seed)
+    G = TINY_GEOM
+    lat = torch.randn(G["B"], G["F"], TINY["in_ch"], G["H"], G["W"], generator=g).bfloat16()
+    text = torch.randn(G["B"], G["n_text"], TINY["text_dim"], generator=g).bfloat16()
+    vip = torch.randn(G["B"], 2, TINY["vip_dim"], 2, 3, generator=g).bfloat16()
+    if per_frame_t:
+        ts = torch.tensor([[999, 640, 21], [999, 640, 21]])
+    else:
+        ts = torch.tensor([731, 731])
+    return lat, text, vip, ts
+
+
+def gen_rope():
+    from longvgen.models.embeddings import get_3d_rotary_pos_embed, get_3d_rotary_pos_embed_v2
+    out = {}
+    cos, sin = get_3d_rotary_pos_embed(64, [[0, 0, 0], [3, 4, 6]], (3, 4, 6))
+    out["small_cos"], out["small_sin"] = cos, sin
+    cos, sin = get_3d_rotary_pos_embed(64, [[0, 0, 0], [13, 30, 45]], (13, 30, 45))
+    idx = torch.arange(0, 17550, 397)
+    out["full_rows"], out["full_cos_rows"], out["full_sin_rows"] = idx, cos[idx], sin[idx]
+    out["full_cos_sha"], out["full_sin_sha"] = _sha(cos), _sha(sin)
+    gt = np.array([1000, 1003.25, 1006.5, 1009.75, 1013], dtype=np.float32)
+    gh = np.linspace(0, 30, 8, endpoint=False, dtype=np.float32)
+    gw = np.linspace(0, 45, 12, endpoint=False, dtype=np.float32)
+    cos, sin = get_3d_rotary_pos_embed_v2(64, gt, gh, gw)
+    out["cond_cos"], out["cond_sin"] = cos, sin
+    gt = np.array([0, 0, 0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9], dtype=np.float32) + 37
+    cos, sin = get_3d_rotary_pos_embed_v2(64, gt, np.arange(30, dtype=np.float32), np.arange(45, dtype=np.float32))
+    out["img_cos_sha"], out["img_sin_sha"] = _sha(cos), _sha(sin)
+    out["img_grid_t"] = torch.from_numpy(gt)
+    torch.save(out, GOLDEN / "rope.pt")
+
+
+def gen_dit_tiny():
+    from longvgen.models.embeddings import get_3d_rotary_pos_embed, get_3d_rotary_pos_embed_v2
+    G = TINY_GEOM
+    gh, gw = G["H"] // 2, G["W"] // 2
+    rope = get_3d_rotary_pos_embed(64, [[0, 0, 0], [G["F"], gh, gw]], (G["F"], gh, gw))
+    img_rope = get_3d_rotary_pos_embed_v2(64, np.array([5, 6, 7], dtype=np.float32), np.arange(gh, dtype=np.float32),
+                                          np.arange(gw, dtype=np.float32))
+    cond_rope = get_3d_rotary_pos_embed_v2(64, np.array([1000, 1001.5], dtype=np.float32),
+                                           np.linspace(0, gh, 2, endpoint=False, dtype=np.float32),
+                                           np.linspace(0, gw, 3, endpoint=False, dtype=np.float32))
+    meta = {}
+    blob = {"rope": rope, "img_rope": img_rope, "cond_rope": cond_rope}
+    for use_vip in (True, False):
+        tag = "vip" if use_vip else "plain"
+        model = build_ref_tiny(use_vip)
+        shapes = {k: list(v.shape) for k, v in model.state_dict().items() if "pos_embedding" not in k}
+        mine = dit_shapes(use_vip=use_vip, **TINY)
+        assert shapes == mine, (set(shapes) ^ set(mine), [k for k in shapes if k in mine and shapes[k] != mine[k]])
+        sd = synth_state_dict(shapes, seed=1234)
+        meta[tag] = {"shapes": shapes, "digest": state_dict_digest(sd)}
+        for per_frame in (True, False):
+            lat, text, vip, ts = tiny_inputs(7 + int(per_frame), per_frame)
+            for dt in (torch.float32, torch.bfloat16):
+                model.load_state_dict({k: v.to(dt) for k, v in sd.items()}, strict=False)
+                model.to(dt)
+                with torch.no_grad():
+                    y = model(hidden_states=lat.to(dt), encoder_hidden_states=text.to(dt), timestep=ts,
+                              vip_encoder_hidden_states=vip.to(dt) if use_vip else None,
+                              image_rotary_emb=rope, vip_image_rotary_emb=img_rope if use_vip else None,
+                              vip_condition_rotary_emb=cond_rope if use_vip else None, return_dict=False)[0]
+                key = f"{tag}_{'pf' if per_frame else 'ps'}_{'f32' if dt == torch.float32 else 'bf16'}"
+                blob[key] = y.clone()
+            blob[f"{tag}_{'pf' if per_frame else 'ps'}_inputs"] = (lat, text, vip, ts)
+        # one block in isolation (fp32), exercising CogVideoXBlock.forward directly
+        blk = model.float().transformer_blocks[1]
+        model.load_state_dict({k: v.float() for k, v in sd.items()}, strict=False)
+        g = torch.Generator().manual_seed(99)
+        n_enc = G["n_text"] + (12 if use_vip else 0)
+        hid = torch.randn(2, 72, 256, generator=g).bfloat16().float()
+        enc = torch.randn(2, n_enc, 256, generator=g).bfloat16().float()
+        temb = torch.randn(2, 3, 128, generator=g).bfloat16().float()
+        with torch.no_grad():
+            h2, e2 = blk(hid, enc, temb, rope, img_rope if use_vip else None, cond_rope if use_vip else None)
+        blob[f"{tag}_block"] = (hid, enc, temb, h2.clone(), e2.clone())
+    torch.save(blob, GOLDEN / "dit_tiny.pt")
+    (GOLDEN / "dit_tiny.json").write_text(json.dumps(meta, indent=1))
+
+
+def gen_dpm():
+    import longvgen.schedulers.scheduling_dpm_cogvideox as mod
+    sch = mod.CogVideoXDPMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                                    prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=1.0,
+                                    timestep_spacing="trailing", set_alpha_to_one=True, clip_sample=False)
+    sch.set_timesteps(52)
+    out = {"alphas_cumprod": sch.alphas_cumprod.clone(), "betas": sch.betas.clone(), "timesteps52": sch.timesteps.clone()}
+    sch50 = mod.CogVideoXDPMScheduler(prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=1.0,
+                                      timestep_spacing="trailing")
+    sch50.set_timesteps(50)
+    out["timesteps50"] = sch50.timesteps.clone()
+    g = torch.Generator().manual_seed(5)
+    shape = (1, 1, 16, 6, 8)
+    cases = []
+    ts = sch.timesteps.tolist()
+    for dt in (torch.bfloat16, torch.float32):
+        for (i, has_old) in [(0, False), (1, True), (20, True), (50, True), (51, True), (51, False)]:
+            t, prev_t = ts[i], (ts[i + 1] if i + 1 < len(ts) else -1)
+            back = ts[i - 1] if i > 0 else None
+            mo = torch.randn(shape, generator=g).to(dt)
+            smp = torch.randn(shape, generator=g).bfloat16() if dt == torch.float32 else torch.randn(shape, generator=g).to(dt)
+            old = torch.randn(shape, generator=g).to(dt) if has_old else None
+            n1, n2 = torch.randn(shape, generator=g).to(smp.dtype), torch.randn(shape, generator=g).to(smp.dtype)
+            draws = iter([n1, n2])
+            orig = mod.randn_tensor
+            mod.randn_tensor = lambda *a, **k: next(draws)
+            try:
+                if back is None and has_old:
+                    continue
+                p, x0 = sch.step(mo, old, t, prev_t, back, smp, return_dict=False)
+            finally:
+                mod.randn_tensor = orig
+            cases.append(dict(t=t, prev_t=prev_t, back=back, model_output=mo, sample=smp, old=old, n1=n1, n2=n2,
+                              prev_sample=p.clone(), x0=x0.clone()))
+    out["step_cases"] = cases
+    x = torch.randn(1, 16, 6, 8, generator=g).bfloat16()
+    n = torch.randn(1, 16, 6, 8, generator=g).bfloat16()
+    out["renoise"] = (x, n, sch.add_noise_to_xt(x, n, torch.Tensor([999]).long()).clone())
+    torch.save(out, GOLDEN / "dpm.pt")
+
+
+def gen_fifo_trace():
+    """Runs the reference controller cogvideo_fifo_mp_v2 with threads + a recording worker instead of GPU processes."""
+    import longvgen.fifo_sampling.cogvideo_sampling_mp_fifo as mod
+    import longvgen.schedulers.scheduling_dpm_cogvideox as smod
+
+    records = []
+
+    def fake_worker(pid, in_q, out_q, pipe, *args):
+        while True:
+            item = in_q.get()
+            if item is None:
+                return
+            (i, sub_rank, queue_start_idx, start_idx, midpoint_idx, end_idx, real_end_idx, t, prev_t, next_t, lat, old,
+             g_t, g_h, g_w, c_t, c_h, c_w, emb, cache_idx) = item
+            records.append(dict(iteration=int(i), queue_start=int(queue_start_idx), start=int(start_idx), mid=int(midpoint_idx),
+                                end=int(end_idx), real_end=int(real_end_idx), t=t.tolist(), prev_t=prev_t.tolist(),
+                                next_t=next_t.tolist(), img_t=[float(v) for v in g_t], cond_t=[float(v) for v in c_t],
+                                emb_first=float(emb[0, 0, 0, 0, 0]), has_old=[o is not None for o in old],
+                                lat_tag=[float(v) for v in lat[0, :, 0, 0, 0]]))
+            out_q.put((sub_rank, start_idx, midpoint_idx, end_idx, real_end_idx, lat + 1.0,
+                       [torch.full((1, 1, 1, 1, 1), float(i)) for _ in range(lat.shape[1])], []))
+
+    class FakeProc:
+        def __init__(self, target, args):
+            self.th = threading.Thread(target=fake_worker, args=args, daemon=True)
+
+        def start(self):
+            self.th.start()
+
+        def join(self):
+            self.th.join()
+
+        def close(self):
+            pass
+
+    mod.mp = SimpleNamespace(Queue=queue.Queue, Process=FakeProc)
+    mod.tqdm = lambda *a, **k: SimpleNamespace(update=lambda: None)
+    sch = smod.CogVideoXDPMScheduler(prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=1.0,
+                                     timestep_spacing="trailing")
+    sch.set_timesteps(52)
+    traces = {}
+    for name, num_chunks in (("edit", 12), ("short", 2)):
+        records.clear()
+        nf, T = 13, 52
+        num_frames = num_chunks * nf
+        pipe = SimpleNamespace(scheduler=sch, device="cpu")
+        # queue slot tag = its index; embeddings tagged by temporal slot
+        fifo_latents = torch.arange(T, dtype=torch.float32).view(1, T, 1, 1, 1) * 100.0
+        n_emb = (num_chunks + 1) * 4
+        emb = torch.arange(n_emb, dtype=torch.float32).view(1, n_emb, 1, 1, 1).repeat(2, 1, 1, 1, 1)
+        img_t = np.linspace(0, num_chunks * nf, num_chunks * nf, endpoint=False, dtype=np.float32)
+        cond_t = np.concatenate([np.linspace(1000 + i * nf, 1000 + (i + 1) * nf, 4, endpoint=False, dtype=np.float32)
+                                 for i in range(num_chunks + 1)])
+        base = SimpleNamespace(
+            sampling_params={"num_partitions": 4}, fifo_latents=fifo_latents,
+            fifo_old_pred_original_sample=[None] + [torch.zeros(1, 1, 1, 1, 1) for _ in range(T - 1)],
+            nf_per_chunk=nf, vip_nf_per_chunk=4, num_frames=num_frames, image_embeddings=emb, timesteps=sch.timesteps,
+            num_inference_steps=T, do_classifier_free_guidance=True, use_separate_guidance=False, use_dynamic_cfg=False,
+            prompt_embeds=torch.zeros(2, 1, 1), image_rotary_emb=(torch.zeros(1), torch.zeros(1)),
+            vip_image_rotary_grid=(img_t, np.arange(30, dtype=np.float32), np.arange(45, dtype=np.float32)),
+            vip_condition_rotary_grid=(cond_t, np.zeros(8, dtype=np.float32), np.zeros(12, dtype=np.float32)),
+            attention_kwargs=None, guidance_scale=6.0, guidance_scale_img=1.0, extra_step_kwargs={}, cache_idx=[],
+            condition_frames=None, video_ipadapter_start_frame_idx=1000, output_type="latent", return_dict=False,
+            orig_latents=torch.zeros(1))
+        torch.manual_seed(0)
+        _, video, _ = mod.cogvideo_fifo_mp_v2([pipe], base)
+        traces[name] = dict(num_frames=num_frames, records=list(records), emitted=int(video.shape[1]))
+    (GOLDEN / "fifo_trace.json").write_text(json.dumps(traces))
+
+
+def main():
+    ref_import.enable()
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    torch.set_num_threads(8)
+    for fn in (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace):
+        print("generating", fn.__name__, flush=True)
+        fn()
+    for p in sorted(GOLDEN.iterdir()):
+        print(f"  {p.name}: {p.stat().st_size / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    sys.exit(main())
