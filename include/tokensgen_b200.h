@@ -155,6 +155,7 @@ int tg_unpatchify(const tg_bf16* rows, tg_bf16* latents, int B, int F, int C, in
 enum { TG_DPM_BF16_CHAIN = 1, TG_DPM_BASE_CHAIN = 0 };
 typedef struct {
     const tg_bf16* noise_pred;
+    const float* noise_pred_f32; /* BASE_CHAIN only: an already guided fp32 model output [F, chw] (then noise_pred = NULL) */
     int n_branches;
     float guidance_scale;
     const tg_bf16* sample;     /* [F, chw] */
@@ -171,6 +172,18 @@ typedef struct {
     int mode;
 } tg_dpm_step_args;
 int tg_cfg_dpm_step(const tg_dpm_step_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * K13: advance the FIFO queue by one latent frame and re-noise the new tail slot, in place.
+ * Replaces shift_latents() of cogvideo_sampling_mp_fifo.py:117-131 (clone + slice copy) and
+ * CogVideoXDPMScheduler.add_noise_to_xt (scheduling_dpm_cogvideox.py:497-518).
+ *   queue : bf16 [n_slots, chw]; slot i <- slot i+1 for i < n_slots-1;
+ *           tail <- bf16( sqrt_one_minus_beta * old_tail + sqrt_beta * noise ) evaluated in fp64 like the reference
+ *           (its [1]-shaped fp64 coefficients promote the expression to fp64 before the in-place assignment rounds it).
+ *   x0_queue : optional bf16 [n_slots, chw] history shifted the same way (tail left untouched: the host marks it empty).
+ *   noise : bf16 [chw]. */
+int tg_queue_shift_renoise(tg_bf16* queue, tg_bf16* x0_queue, int n_slots, int64_t chw, const tg_bf16* noise,
+                           double sqrt_one_minus_beta, double sqrt_beta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,127 @@
+"""Host logic of the FIFO sampler: schedule bit-exact vs the oracle and the reference trace; the multi-process boundary
+exchange (gloo, world_size 2 and 4 on CPU) reproduces the single-process result exactly."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import dpm as odpm
+from oracle import fifo as ofifo
+from tokensgen_b200.fifo import FifoQueue, FifoSchedule, VipBook, run_fifo
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _timesteps():
+    return odpm.DpmTables().trailing_timesteps(52)
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 12, 24])
+def test_schedule_equals_oracle(chunks):
+    s = FifoSchedule(chunks * 13, _timesteps())
+    ref = ofifo.window_schedule(chunks * 13)
+    assert s.num_iterations == len(ref)
+    for it in range(s.num_iterations):
+        got = [(w.rank, w.start, w.mid, w.end, w.real_end, w.write_lo, w.write_hi) for w in s.windows(it)]
+        exp = [(w.rank, w.start, w.mid, w.end, w.real_end, w.write_lo, w.write_hi) for w in ref[it]]
+        assert got == exp
+    t, p, n = ofifo.fifo_timestep_tables(_timesteps())
+    assert s.t.tolist() == t.tolist() and s.prev_t.tolist() == p.tolist() and s.next_t.tolist() == n.tolist()
+
+
+def test_schedule_and_vip_lookup_equal_reference_trace():
+    traces = json.load(open(os.path.join(ROOT, "tests", "golden", "fifo_trace.json")))
+    for name, tr in traces.items():
+        nf, T = 13, 52
+        chunks = tr["num_frames"] // nf
+        s = FifoSchedule(tr["num_frames"], _timesteps())
+        img_t = np.linspace(0, chunks * nf, chunks * nf, endpoint=False, dtype=np.float32)
+        cond_t = np.concatenate([np.linspace(1000 + i * nf, 1000 + (i + 1) * nf, 4, endpoint=False, dtype=np.float32)
+                                 for i in range(chunks + 1)])
+        n_emb = (chunks + 1) * 4
+        emb = torch.arange(n_emb, dtype=torch.float32).view(1, n_emb, 1, 1, 1).repeat(2, 1, 1, 1, 1)
+        book = VipBook((img_t, np.arange(30, dtype=np.float32), np.arange(45, dtype=np.float32)),
+                       (cond_t, np.zeros(8, dtype=np.float32), np.zeros(12, dtype=np.float32)), emb, nf, 4, T, 1000)
+        by_iter = {}
+        for r in tr["records"]:
+            by_iter.setdefault(r["iteration"], []).append(r)
+        for it in range(s.num_iterations):
+            recs = sorted(by_iter.get(it, []), key=lambda r: r["start"])
+            wins = s.windows(it)
+            assert len(wins) == len(recs)
+            for w, r in zip(wins, recs):
+                assert (w.start, w.mid, w.end, w.real_end) == (r["start"], r["mid"], r["end"], r["real_end"])
+                (gt, _, _), (ct, _, _), e, _ = book.window(w.start, w.end)
+                assert gt.tolist() == r["img_t"] and ct.tolist() == r["cond_t"]
+                assert float(e[0, 0, 0, 0, 0]) == r["emb_first"]
+            book.shift()
+
+
+# ---- multi-process exchange -------------------------------------------------------------------------------------
+def _toy_step(w, lat, old, t, pt, nt, gen):
+    """Deterministic stand-in for DiT + scheduler: depends on every input frame, its history flag and the window's noise."""
+    noise = torch.randn(lat.shape, generator=gen)
+    ctx = lat.mean(dim=1, keepdim=True)
+    hist = torch.stack([torch.zeros_like(lat[0, 0]) if o is None else o.reshape(lat[0, 0].shape) for o in old]).unsqueeze(0)
+    tt = torch.as_tensor(np.ascontiguousarray(t), dtype=lat.dtype).view(1, -1, 1, 1, 1)
+    out = 0.9 * lat + 0.05 * ctx + 0.01 * hist + 0.001 * tt + 0.01 * noise
+    return out, [out[:, [j]] * 0.5 for j in range(lat.shape[1])]
+
+
+def _toy_shift(queue, gen):
+    noise = torch.randn(queue.x0.shape[1:], generator=gen)
+    queue.latents[:, :-1] = queue.latents[:, 1:].clone()
+    queue.x0[:-1] = queue.x0[1:].clone()
+    queue.latents[:, -1] = 0.99 * queue.latents[:, -1] + 0.1 * noise
+    queue.x0_valid = queue.x0_valid[1:] + [False]
+
+
+def _make_queue():
+    g = torch.Generator().manual_seed(5)
+    lat = torch.randn(1, 52, 2, 3, 4, generator=g)
+    hist = [None] + [torch.randn(1, 1, 2, 3, 4, generator=g) for _ in range(51)]
+    return FifoQueue(lat, hist, 6)
+
+
+def _worker(rank, world, port, num_frames, out_path):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sched = FifoSchedule(num_frames, _timesteps())
+        em = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, rank=rank, world=world)
+        if rank == 0:
+            torch.save(torch.cat(em[52 - 13:], dim=1), out_path)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_boundary_exchange_reproduces_single_process(tmp_path, world):
+    num_frames = 26
+    sched = FifoSchedule(num_frames, _timesteps())
+    ref = torch.cat(run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3)[52 - 13:], dim=1)
+    assert ref.shape[1] == num_frames
+    out = str(tmp_path / "emitted.pt")
+    port = 29500 + (os.getpid() % 2000) + world
+    mp.spawn(_worker, args=(world, port, num_frames, out), nprocs=world, join=True)
+    got = torch.load(out)
+    assert torch.equal(got, ref)
+
+
+def test_transfers_are_neighbour_sized_at_world_8():
+    """At P = 8 a rank receives only the boundary slots: <= 7 from the left neighbour and 1 from the right one."""
+    s = FifoSchedule(24 * 13, _timesteps())
+    it = 100  # steady state: all 8 windows active
+    per_dst = {}
+    for src, dst, lo, hi in s.transfers(it, 8):
+        per_dst.setdefault(dst, []).append((src, hi - lo))
+    for dst, items in per_dst.items():
+        assert sum(n for _, n in items) <= 8
+        assert all(abs(src - dst) == 1 for src, _ in items)
+    # 7 ranks take the 5-6 frames of their left neighbour's write region they will read, 7 ranks take 1 frame from the right
+    assert sum(n for items in per_dst.values() for _, n in items) == 46

@@ -35,7 +35,8 @@ class QkvProj(C.Structure):
 
 
 class DpmStepArgs(C.Structure):
-    _fields_ = [("noise_pred", C.c_void_p), ("n_branches", C.c_int), ("guidance_scale", C.c_float),
+    _fields_ = [("noise_pred", C.c_void_p), ("noise_pred_f32", C.c_void_p), ("n_branches", C.c_int),
+                ("guidance_scale", C.c_float),
                 ("sample", C.c_void_p), ("old_x0", C.c_void_p), ("old_x0_f32", C.c_void_p),
                 ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("coef", C.c_void_p),
                 ("prev_sample", C.c_void_p), ("x0_out", C.c_void_p), ("x0_out_f32", C.c_void_p),
@@ -61,9 +62,35 @@ SYMBOLS = {
     "tg_patchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "tg_unpatchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "tg_cfg_dpm_step": (C.c_int, [C.POINTER(DpmStepArgs), _VP]),
+    "tg_queue_shift_renoise": (C.c_int, [_VP, _VP, _I, _I64, _VP, C.c_double, C.c_double, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None
+
+# Instrumentation used by bench.py: number of kernel launches issued through this binding, and (when `profile` is a
+# dict) CUDA-event pairs recorded around every call on the launching stream, keyed by op tag.
+launch_count = 0
+profile: Optional[dict] = None
+
+
+class _Timed:
+    def __init__(self, tag: str, launches: int = 1):
+        self.tag, self.launches = tag, launches
+
+    def __enter__(self):
+        global launch_count
+        launch_count += self.launches
+        if profile is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if profile is not None:
+            self.e.record()
+            profile.setdefault(self.tag, []).append((self.s, self.e))
+        return False
 
 
 def load() -> C.CDLL:
@@ -129,10 +156,11 @@ def time_embedding(timesteps: torch.Tensor, w1, b1, w2, b2, sincos_dim: int, fli
     emb = torch.empty(R, time_dim, device=w1.device, dtype=torch.bfloat16)
     silu = torch.empty_like(emb)
     scratch = torch.empty_like(emb)
-    _check(lib.tg_time_embedding(ts.data_ptr(), R, sincos_dim, time_dim, int(flip_sin_to_cos), float(freq_shift),
-                                 _bf16_cuda(w1, "w1").data_ptr(), _bf16_cuda(b1, "b1").data_ptr(),
-                                 _bf16_cuda(w2, "w2").data_ptr(), _bf16_cuda(b2, "b2").data_ptr(),
-                                 emb.data_ptr(), silu.data_ptr(), scratch.data_ptr(), _stream()), "tg_time_embedding")
+    with _Timed("time_embedding", 2):
+        _check(lib.tg_time_embedding(ts.data_ptr(), R, sincos_dim, time_dim, int(flip_sin_to_cos), float(freq_shift),
+                                     _bf16_cuda(w1, "w1").data_ptr(), _bf16_cuda(b1, "b1").data_ptr(),
+                                     _bf16_cuda(w2, "w2").data_ptr(), _bf16_cuda(b2, "b2").data_ptr(),
+                                     emb.data_ptr(), silu.data_ptr(), scratch.data_ptr(), _stream()), "tg_time_embedding")
     return emb, silu
 
 
@@ -140,9 +168,10 @@ def ln_modulate(x: torch.Tensor, out: torch.Tensor, B: int, rowmap: RowMap, ln_w
                 shift: ModVec, scale: ModVec, ln2_w=None, ln2_b=None, eps2: float = 1e-5) -> None:
     lib = load()
     d = x.shape[-1]
-    _check(lib.tg_ln_modulate(_bf16_cuda(x, "x").data_ptr(), _bf16_cuda(out, "out").data_ptr(), B, d, C.byref(rowmap),
-                              _ptr(ln_w), _ptr(ln_b), _ptr(vip_ln_w), _ptr(vip_ln_b), float(eps), _ptr(ln2_w), _ptr(ln2_b),
-                              float(eps2), C.byref(shift), C.byref(scale), _stream()), "tg_ln_modulate")
+    with _Timed("ln_modulate", 1):
+        _check(lib.tg_ln_modulate(_bf16_cuda(x, "x").data_ptr(), _bf16_cuda(out, "out").data_ptr(), B, d, C.byref(rowmap),
+                                  _ptr(ln_w), _ptr(ln_b), _ptr(vip_ln_w), _ptr(vip_ln_b), float(eps), _ptr(ln2_w), _ptr(ln2_b),
+                                  float(eps2), C.byref(shift), C.byref(scale), _stream()), "tg_ln_modulate")
 
 
 def gemm_bias_act(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
@@ -157,8 +186,9 @@ def gemm_bias_act(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
         out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16)
     if out.dim() != 2 or out.stride(1) != 1 or out.shape[0] != M or out.shape[1] != N:
         raise TokensGenError("gemm_bias_act: bad out")
-    _check(lib.tg_gemm_bias_act(a.data_ptr(), a.stride(0), _bf16_cuda(w, "w").data_ptr(), _ptr(bias), out.data_ptr(),
-                                out.stride(0), M, N, K, act, _stream()), "tg_gemm_bias_act")
+    with _Timed(f"gemm_bias_act[{M}x{N}x{K}]", 1):
+        _check(lib.tg_gemm_bias_act(a.data_ptr(), a.stride(0), _bf16_cuda(w, "w").data_ptr(), _ptr(bias), out.data_ptr(),
+                                    out.stride(0), M, N, K, act, _stream()), "tg_gemm_bias_act")
     return out
 
 
@@ -167,9 +197,10 @@ def gemm_gate_residual(a: torch.Tensor, w: torch.Tensor, bias, x: torch.Tensor, 
     lib = load()
     M, K = a.shape
     N = w.shape[0]
-    _check(lib.tg_gemm_gate_residual(_bf16_cuda(a, "a").data_ptr(), a.stride(0), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
-                                     _bf16_cuda(x, "x").data_ptr(), x.stride(-2), B, N, K, C.byref(rowmap), C.byref(gate),
-                                     _stream()), "tg_gemm_gate_residual")
+    with _Timed(f"gemm_gate_residual[{M}x{N}x{K}]", 1):
+        _check(lib.tg_gemm_gate_residual(_bf16_cuda(a, "a").data_ptr(), a.stride(0), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
+                                         _bf16_cuda(x, "x").data_ptr(), x.stride(-2), B, N, K, C.byref(rowmap), C.byref(gate),
+                                         _stream()), "tg_gemm_gate_residual")
 
 
 def qkv_rope_gemm(a: torch.Tensor, w: torch.Tensor, bias, B: int, H: int, rowmap: RowMap,
@@ -177,8 +208,9 @@ def qkv_rope_gemm(a: torch.Tensor, w: torch.Tensor, bias, B: int, H: int, rowmap
     lib = load()
     K = a.shape[-1]
     arr = (QkvProj * len(projs))(*projs)
-    _check(lib.tg_qkv_rope_gemm(_bf16_cuda(a, "a").data_ptr(), a.stride(-2), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
-                                B, H, K, C.byref(rowmap), arr, len(projs), float(ln_eps), _stream()), "tg_qkv_rope_gemm")
+    with _Timed(f"qkv_rope_gemm[{a.shape[0]}x{w.shape[0]}x{K}]", 1):
+        _check(lib.tg_qkv_rope_gemm(_bf16_cuda(a, "a").data_ptr(), a.stride(-2), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
+                                    B, H, K, C.byref(rowmap), arr, len(projs), float(ln_eps), _stream()), "tg_qkv_rope_gemm")
 
 
 def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, q_row0: int = 0,
@@ -195,26 +227,29 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
     q_rows = nq_alloc - q_row0 if q_rows is None else q_rows
     kv_rows = nkv_alloc - kv_row0 if kv_rows is None else kv_rows
     scale = D ** -0.5 if softmax_scale is None else softmax_scale
-    _check(lib.tg_attn_fwd(_bf16_cuda(q, "q").data_ptr(), nq_alloc, q_row0, q_rows, _bf16_cuda(k, "k").data_ptr(),
-                           _bf16_cuda(v, "v").data_ptr(), nkv_alloc, kv_row0, kv_rows, _bf16_cuda(out, "out").data_ptr(),
-                           out.shape[1], out_row0, B, H, float(scale), int(accumulate), float(out_scale), _stream()),
-           "tg_attn_fwd")
+    with _Timed(f"attn_fwd[q{q_rows},kv{kv_rows}]", 1):
+        _check(lib.tg_attn_fwd(_bf16_cuda(q, "q").data_ptr(), nq_alloc, q_row0, q_rows, _bf16_cuda(k, "k").data_ptr(),
+                               _bf16_cuda(v, "v").data_ptr(), nkv_alloc, kv_row0, kv_rows, _bf16_cuda(out, "out").data_ptr(),
+                               out.shape[1], out_row0, B, H, float(scale), int(accumulate), float(out_scale), _stream()),
+               "tg_attn_fwd")
 
 
 def patchify(latents: torch.Tensor, p: int) -> torch.Tensor:
     lib = load()
     B, F, Cc, H, W = latents.shape
     rows = torch.empty(B * F * (H // p) * (W // p), Cc * p * p, device=latents.device, dtype=torch.bfloat16)
-    _check(lib.tg_patchify(_bf16_cuda(latents, "latents").data_ptr(), rows.data_ptr(), B, F, Cc, H, W, p, _stream()),
-           "tg_patchify")
+    with _Timed("patchify", 1):
+        _check(lib.tg_patchify(_bf16_cuda(latents, "latents").data_ptr(), rows.data_ptr(), B, F, Cc, H, W, p, _stream()),
+               "tg_patchify")
     return rows
 
 
 def unpatchify(rows: torch.Tensor, B: int, F: int, Cc: int, H: int, W: int, p: int) -> torch.Tensor:
     lib = load()
     out = torch.empty(B, F, Cc, H, W, device=rows.device, dtype=torch.bfloat16)
-    _check(lib.tg_unpatchify(_bf16_cuda(rows, "rows").data_ptr(), out.data_ptr(), B, F, Cc, H, W, p, _stream()),
-           "tg_unpatchify")
+    with _Timed("unpatchify", 1):
+        _check(lib.tg_unpatchify(_bf16_cuda(rows, "rows").data_ptr(), out.data_ptr(), B, F, Cc, H, W, p, _stream()),
+               "tg_unpatchify")
     return out
 
 
@@ -226,7 +261,12 @@ def cfg_dpm_step(noise_pred: torch.Tensor, sample: torch.Tensor, old_x0: Optiona
     chw = sample.numel() // F
     prev = torch.empty_like(sample)
     a = DpmStepArgs()
-    a.noise_pred = _bf16_cuda(noise_pred, "noise_pred").data_ptr()
+    if noise_pred.dtype == torch.float32:
+        if not (noise_pred.is_cuda and noise_pred.is_contiguous()):
+            raise TokensGenError("cfg_dpm_step: fp32 noise_pred must be contiguous CUDA")
+        a.noise_pred_f32 = noise_pred.data_ptr()
+    else:
+        a.noise_pred = _bf16_cuda(noise_pred, "noise_pred").data_ptr()
     a.n_branches = nb
     a.guidance_scale = float(guidance_scale)
     a.sample = _bf16_cuda(sample, "sample").data_ptr()
@@ -245,5 +285,18 @@ def cfg_dpm_step(noise_pred: torch.Tensor, sample: torch.Tensor, old_x0: Optiona
         x0 = torch.empty(sample.shape, device=sample.device, dtype=torch.float32)
         a.x0_out_f32 = x0.data_ptr()
         a.old_x0_f32 = _ptr(old_x0)
-    _check(lib.tg_cfg_dpm_step(C.byref(a), _stream()), "tg_cfg_dpm_step")
+    with _Timed("cfg_dpm_step", 1):
+        _check(lib.tg_cfg_dpm_step(C.byref(a), _stream()), "tg_cfg_dpm_step")
     return prev, x0
+
+
+def queue_shift_renoise(queue: torch.Tensor, x0_queue: Optional[torch.Tensor], noise: torch.Tensor,
+                        sqrt_one_minus_beta: float, sqrt_beta: float) -> None:
+    """queue / x0_queue: bf16 [n_slots, ...] (in place); noise bf16 [...] of one slot."""
+    lib = load()
+    n_slots = queue.shape[0]
+    chw = queue.numel() // n_slots
+    with _Timed("queue_shift_renoise", 1):
+        _check(lib.tg_queue_shift_renoise(_bf16_cuda(queue, "queue").data_ptr(), _ptr(x0_queue), n_slots, chw,
+                                          _bf16_cuda(noise, "noise").data_ptr(), float(sqrt_one_minus_beta), float(sqrt_beta),
+                                          _stream()), "tg_queue_shift_renoise")

@@ -241,7 +241,14 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(const __grid_constant
     for (int64_t vi = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; vi < nvec; vi += int64_t(gridDim.x) * blockDim.x) {
         const int64_t off = frame_off + vi * 8;
         float u[8], c[8], smp[8], nz[8], old[8], mo[8], x0[8], ps[8];
-        unpack8(*reinterpret_cast<const uint4*>(a.noise_pred + off), u);
+        if (a.noise_pred_f32 != nullptr) {
+            const float4 o0 = *reinterpret_cast<const float4*>(a.noise_pred_f32 + off);
+            const float4 o1 = *reinterpret_cast<const float4*>(a.noise_pred_f32 + off + 4);
+            u[0] = o0.x; u[1] = o0.y; u[2] = o0.z; u[3] = o0.w;
+            u[4] = o1.x; u[5] = o1.y; u[6] = o1.z; u[7] = o1.w;
+        } else {
+            unpack8(*reinterpret_cast<const uint4*>(a.noise_pred + off), u);
+        }
         unpack8(*reinterpret_cast<const uint4*>(a.sample + off), smp);
         unpack8(*reinterpret_cast<const uint4*>((second ? a.noise2 : a.noise1) + off), nz);
         if (a.n_branches == 2) unpack8(*reinterpret_cast<const uint4*>(a.noise_pred + branch_stride + off), c);
@@ -295,9 +302,48 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(const __grid_constant
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K13
+// One thread owns one 16-byte column of every slot and walks the slots in order, so the in-place shift has no
+// cross-thread hazard.
+__global__ void __launch_bounds__(256)
+queue_shift_renoise_kernel(__nv_bfloat16* __restrict__ queue, __nv_bfloat16* __restrict__ x0q, int n_slots, int64_t chw,
+                           const __nv_bfloat16* __restrict__ noise, double s1, double s2) {
+    const int64_t nvec = chw / 8;
+    for (int64_t vi = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; vi < nvec; vi += int64_t(gridDim.x) * blockDim.x) {
+        uint4* q = reinterpret_cast<uint4*>(queue) + vi;
+        for (int s = 0; s + 1 < n_slots; ++s) q[int64_t(s) * nvec] = q[int64_t(s + 1) * nvec];
+        if (x0q != nullptr) {
+            uint4* h = reinterpret_cast<uint4*>(x0q) + vi;
+            for (int s = 0; s + 1 < n_slots; ++s) h[int64_t(s) * nvec] = h[int64_t(s + 1) * nvec];
+        }
+        float x[8], n[8], o[8];
+        unpack8(q[int64_t(n_slots - 1) * nvec], x);
+        unpack8(reinterpret_cast<const uint4*>(noise)[vi], n);
+        // fp64 -> bf16 in one rounding (no float intermediate), like the reference's fp64 expression assigned into bf16
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const double dv = __dadd_rn(__dmul_rn(s1, double(x[j])), __dmul_rn(s2, double(n[j])));
+            o[j] = __bfloat162float(__double2bfloat16(dv));
+        }
+        q[int64_t(n_slots - 1) * nvec] = pack8(o);
+    }
+}
+
 }  // namespace tg
 
 using namespace tg;
+
+extern "C" int tg_queue_shift_renoise(tg_bf16* queue, tg_bf16* x0_queue, int n_slots, int64_t chw, const tg_bf16* noise,
+                                      double sqrt_one_minus_beta, double sqrt_beta, void* stream) {
+    if (!queue || !noise) return fail(-1, "queue_shift_renoise: null pointer");
+    if (n_slots < 1 || chw <= 0 || chw % 8 != 0) return fail(-2, "queue_shift_renoise: n_slots=%d chw=%lld", n_slots, (long long)chw);
+    const int64_t nvec = chw / 8;
+    const int grid = int((nvec + 255) / 256);
+    queue_shift_renoise_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<__nv_bfloat16*>(queue), reinterpret_cast<__nv_bfloat16*>(x0_queue), n_slots, chw,
+        reinterpret_cast<const __nv_bfloat16*>(noise), sqrt_one_minus_beta, sqrt_beta);
+    return check_launch("queue_shift_renoise");
+}
 
 extern "C" int tg_ln_modulate(const tg_bf16* x, tg_bf16* out, int B, int d, const tg_rowmap* map, const tg_bf16* ln_w,
                               const tg_bf16* ln_b, const tg_bf16* vip_ln_w, const tg_bf16* vip_ln_b, float eps,
@@ -330,11 +376,13 @@ extern "C" int tg_ln_modulate(const tg_bf16* x, tg_bf16* out, int B, int d, cons
     const int grid = (p.M + 7) / 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     switch (d / 256) {
+        case 1: ln_modulate_kernel<1><<<grid, 256, 0, st>>>(p); break;
+        case 2: ln_modulate_kernel<2><<<grid, 256, 0, st>>>(p); break;
         case 4: ln_modulate_kernel<4><<<grid, 256, 0, st>>>(p); break;
         case 8: ln_modulate_kernel<8><<<grid, 256, 0, st>>>(p); break;
         case 12: ln_modulate_kernel<12><<<grid, 256, 0, st>>>(p); break;
         case 16: ln_modulate_kernel<16><<<grid, 256, 0, st>>>(p); break;
-        default: return fail(-7, "ln_modulate: d=%d not instantiated (1024, 2048, 3072, 4096)", d);
+        default: return fail(-7, "ln_modulate: d=%d not instantiated (256, 512, 1024, 2048, 3072, 4096)", d);
     }
     return check_launch("ln_modulate");
 }
@@ -389,8 +437,10 @@ extern "C" int tg_unpatchify(const tg_bf16* rows, tg_bf16* latents, int B, int F
 
 extern "C" int tg_cfg_dpm_step(const tg_dpm_step_args* a, void* stream) {
     if (!a) return fail(-1, "cfg_dpm_step: null args");
-    if (!a->noise_pred || !a->sample || !a->noise1 || !a->noise2 || !a->coef || !a->prev_sample)
+    if ((!a->noise_pred && !a->noise_pred_f32) || !a->sample || !a->noise1 || !a->noise2 || !a->coef || !a->prev_sample)
         return fail(-1, "cfg_dpm_step: null pointer");
+    if (a->noise_pred_f32 && (a->noise_pred || a->n_branches != 1 || a->mode != TG_DPM_BASE_CHAIN))
+        return fail(-6, "cfg_dpm_step: noise_pred_f32 is for the base chain with n_branches = 1 and no bf16 noise_pred");
     if (a->n_branches != 1 && a->n_branches != 2) return fail(-2, "cfg_dpm_step: n_branches must be 1 or 2");
     if (a->F <= 0 || a->chw <= 0 || a->chw % 8 != 0) return fail(-3, "cfg_dpm_step: F=%d chw=%lld (chw %% 8 == 0)", a->F, (long long)a->chw);
     if (a->mode == TG_DPM_BF16_CHAIN) {

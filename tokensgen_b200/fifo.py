@@ -1,0 +1,240 @@
+"""FIFO diagonal-queue sampler: controller + worker step of the reference's cogvideo_fifo_mp_v2 / fifo_onestep_per_gpu
+(longvgen/fifo_sampling/cogvideo_sampling_mp_fifo.py:27-395, :408-579), re-designed for one persistent process per GPU.
+
+Reference design: a controller process owns the 58-slot queue, ships every window through mp.Queue (CUDA IPC) to one
+spawned worker per GPU and copies results back, per iteration.
+This design:      every rank runs the same deterministic controller on its own replica of the (10 MB) queue; window
+rank w is owned by process w % P (the reference's `rank = base_rank * num_processes + sub_rank` assignment); after each
+iteration only the slots a *different* process will read next are exchanged, as grouped NCCL send/recv
+(`torch.distributed.batch_isend_irecv`) — for P = 8 that is the 6-7 boundary frames from the left neighbour and one from
+the right neighbour.  No queue gather, no pickling of pipelines, no per-video process spawn.
+
+Determinism: the noise a window consumes is drawn from a generator seeded by (seed, iteration, window rank) and the
+tail re-noise from (seed, iteration), so the result does not depend on P — the property the multi-process tests check.
+
+The integer index schedule is bit-identical to the reference controller (tests/golden/fifo_trace.json).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class Window:
+    iteration: int
+    rank: int       # window rank 0..2*num_partitions-1
+    start: int
+    mid: int
+    end: int
+    real_end: int
+    write_lo: int   # queue slots [write_lo, write_hi) take this window's outputs
+    write_hi: int
+
+    @property
+    def out_lo(self) -> int:
+        """Offset of write_lo inside the window's 13 output frames."""
+        return self.write_lo - self.start
+
+
+class FifoSchedule:
+    """Index arithmetic of cogvideo_fifo_mp_v2 (:175-188 tables, :223-259 windows, :322-327 write-back, :358 padding)."""
+
+    def __init__(self, num_frames: int, timesteps: Sequence[int], nf_per_chunk: int = 13, num_partitions: int = 4,
+                 use_adaptive_padding: bool = True):
+        self.nf = nf_per_chunk
+        self.l_nf, self.r_nf = nf_per_chunk - nf_per_chunk // 2, nf_per_chunk // 2
+        self.T = len(timesteps)
+        self.num_frames = num_frames
+        self.num_rank = 2 * num_partitions
+        self.num_iterations = num_frames + self.T - nf_per_chunk
+        self.queue_len = self.T + self.r_nf
+        self.initial_queue_start = self.T - self.l_nf if use_adaptive_padding else 0
+        ts = np.asarray(timesteps, dtype=np.int64)
+        r = self.r_nf
+        self.t = np.concatenate([ts, np.full(r, ts[-1])])[::-1].copy()
+        self.prev_t = np.concatenate([ts[1:], np.full(r + 1, -1)])[::-1].copy()
+        self.next_t = np.concatenate([np.full(1, -1), ts[:-1], np.full(r, ts[-2])])[::-1].copy()
+
+    def queue_start(self, iteration: int) -> int:
+        return max(0, self.initial_queue_start - iteration)
+
+    def windows(self, iteration: int) -> List[Window]:
+        qs = self.queue_start(iteration)
+        out = []
+        for rank in range(self.num_rank):
+            start = self.nf * (rank // 2) + self.r_nf * (rank % 2)
+            nxt = self.nf * ((rank + 1) // 2) + self.r_nf * ((rank + 1) % 2)
+            if nxt <= qs:
+                continue
+            mid = start + (self.l_nf if rank % 2 == 1 else self.r_nf)
+            real_end = start + self.nf
+            if start < qs:
+                start = qs
+            end = start + self.nf
+            lo, hi = (mid, end) if start > qs else (max(self.r_nf, start), real_end)
+            out.append(Window(iteration, rank, start, mid, end, real_end, lo, hi))
+        return out
+
+    def transfers(self, iteration: int, world: int) -> List[Tuple[int, int, int, int]]:
+        """(src_process, dst_process, slot_lo, slot_hi) in PRE-shift slot numbers: what was written in `iteration` by one
+        process and is read in `iteration + 1` by another.  Identical on every rank (pure function of the schedule)."""
+        if iteration + 1 >= self.num_iterations:
+            return []
+        cur, nxt = self.windows(iteration), self.windows(iteration + 1)
+        out = []
+        for w in cur:
+            src = w.rank % world
+            for v in nxt:
+                dst = v.rank % world
+                if dst == src:
+                    continue
+                lo, hi = max(w.write_lo, v.start + 1), min(w.write_hi, v.end + 1)  # v reads pre-shift [start+1, end+1)
+                if lo < hi:
+                    out.append((src, dst, lo, hi))
+        # a slot range may be requested by several windows of the same destination: merge duplicates
+        return sorted(set(out))
+
+
+StepFn = Callable[[Window, torch.Tensor, List[Optional[torch.Tensor]], np.ndarray, np.ndarray, np.ndarray, torch.Generator],
+                  Tuple[torch.Tensor, List[torch.Tensor]]]
+
+
+class FifoQueue:
+    """Device-resident queue state of one rank: latents [1, L, C, H, W], x0 history [L, C, H, W] + validity flags."""
+
+    def __init__(self, fifo_latents: torch.Tensor, fifo_old_x0: Sequence[Optional[torch.Tensor]], r_nf: int):
+        pad = [fifo_latents[:, [0]]] * r_nf
+        self.latents = torch.cat(pad + [fifo_latents], dim=1).contiguous()      # prepare_fifo_latents (:72-82)
+        hist = [fifo_old_x0[0]] * r_nf + list(fifo_old_x0)                       # :145-146
+        self.x0 = torch.zeros_like(self.latents[0])
+        self.x0_valid = []
+        for i, h in enumerate(hist):
+            self.x0_valid.append(h is not None)
+            if h is not None:
+                self.x0[i].copy_(h.reshape(self.x0[i].shape))
+
+    def window_inputs(self, w: Window):
+        lat = self.latents[:, w.start:w.end]
+        old = [self.x0[i].unsqueeze(0).unsqueeze(0) if self.x0_valid[i] else None for i in range(w.start, w.end)]
+        return lat, old
+
+
+def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn, seed: int = 0, rank: int = 0,
+             world: int = 1, group=None, progress: Optional[Callable[[int], None]] = None) -> List[torch.Tensor]:
+    """The controller loop (:230-359).  `step_fn(window, latents[1,13,...], old_x0 list, t, prev_t, next_t, generator)`
+    returns (latents_out [1,13,...], x0 list); `shift_fn(queue, noise_generator)` advances the queue by one slot and
+    re-noises the tail.  Returns the emitted frames (slot r_nf of every iteration) as seen by this rank; rank 0's list is
+    the video (emissions before iteration T - nf are the ramp-up the reference drops, :367)."""
+    import torch.distributed as dist
+    emitted = []
+    dev = queue.latents.device
+    for it in range(schedule.num_iterations):
+        wins = schedule.windows(it)
+        mine = [w for w in wins if w.rank % world == rank]
+        results = []
+        for w in mine:  # all windows read the pre-iteration queue (:232,258) -> compute first, write back after
+            lat, old = queue.window_inputs(w)
+            gen = torch.Generator(device=dev).manual_seed((seed * 1000003 + it) * 64 + w.rank)
+            t, pt, nt = schedule.t[w.start:w.end], schedule.prev_t[w.start:w.end], schedule.next_t[w.start:w.end]
+            results.append(step_fn(w, lat.clone(), old, t, pt, nt, gen))
+        for w, (out_lat, out_x0) in zip(mine, results):
+            n = w.write_hi - w.write_lo
+            queue.latents[:, w.write_lo:w.write_hi] = out_lat[:, w.out_lo:w.out_lo + n]
+            for k in range(n):
+                queue.x0[w.write_lo + k].copy_(out_x0[w.out_lo + k].reshape(queue.x0[0].shape))
+                queue.x0_valid[w.write_lo + k] = True
+        if world > 1:
+            ops, recvs = [], []
+            for (src, dst, lo, hi) in schedule.transfers(it, world):
+                if src == rank:
+                    buf = torch.stack([queue.latents[0, lo:hi], queue.x0[lo:hi]]).contiguous()
+                    ops.append(dist.P2POp(dist.isend, buf, dst, group=group))
+                elif dst == rank:
+                    buf = torch.empty((2, hi - lo) + tuple(queue.x0.shape[1:]), device=dev, dtype=queue.x0.dtype)
+                    ops.append(dist.P2POp(dist.irecv, buf, src, group=group))
+                    recvs.append((lo, hi, buf))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            for lo, hi, buf in recvs:
+                queue.latents[0, lo:hi] = buf[0]
+                queue.x0[lo:hi] = buf[1]
+                for s in range(lo, hi):
+                    queue.x0_valid[s] = True
+        emitted.append(queue.latents[:, [schedule.r_nf]].clone())
+        ngen = torch.Generator(device=dev).manual_seed(seed * 1000003 + it + 7919)
+        shift_fn(queue, ngen)
+        if progress is not None:
+            progress(it)
+    return emitted
+
+
+def make_shift_fn(scheduler):
+    """shift_latents (:117-131) on the GPU: one tg_queue_shift_renoise launch for the latent queue and its x0 history."""
+    from . import _ext as E
+    b = scheduler.betas[999].double()
+    s1, s2 = float((1 - b) ** 0.5), float(b ** 0.5)
+
+    def shift(queue: FifoQueue, gen: torch.Generator):
+        noise = torch.randn(queue.x0.shape[1:], generator=gen, device=queue.x0.device, dtype=torch.bfloat16)
+        E.queue_shift_renoise(queue.latents[0], queue.x0, noise, s1, s2)
+        queue.x0_valid = queue.x0_valid[1:] + [False]
+
+    return shift
+
+
+class VipBook:
+    """Bookkeeping of the condensed-token conditioning along the queue (cogvideo_sampling_mp_fifo.py:84-115,133-139,
+    148-173,261-273,351-357): per-slot temporal positions of the video tokens, the (extended) condition grid and
+    embeddings, and the searchsorted lookup of the 5 condensed-token frames a window attends to."""
+
+    def __init__(self, img_grid, cond_grid, image_embeddings: torch.Tensor, nf: int, vip_nf: int, T: int,
+                 start_frame_idx: float):
+        img_t, self.img_h, self.img_w = [np.asarray(g, dtype=np.float32) for g in img_grid]
+        cond_t, self.cond_h, self.cond_w = [np.asarray(g, dtype=np.float32) for g in cond_grid]
+        r_nf = nf // 2
+        self.nf, self.vip_nf, self.start_frame_idx = nf, vip_nf, start_frame_idx
+        self.slot_t = np.concatenate([img_t[[0]]] * (r_nf + T - nf) + [img_t[:nf]])                      # :84-88
+        self.t_queue = np.concatenate([img_t[nf:], np.linspace(img_t[-1] + 1, img_t[-1] + 1 + T, T, endpoint=False,
+                                                                dtype=np.float32)])                        # :90-91
+        self.cond_t = np.concatenate([cond_t] + [cond_t[-vip_nf:] + (i + 1) * nf for i in range(T // nf + 1)])  # :95-99
+        self.embeddings = torch.cat([image_embeddings] + [image_embeddings[:, -vip_nf:]] * (T // nf + 1), dim=1)  # :101-108
+
+    def window(self, start: int, end: int):
+        idx = int(np.searchsorted(self.cond_t, self.slot_t[start] + self.start_frame_idx, side="right") - 1)  # :110-115
+        n = min(self.vip_nf + 1, self.nf)
+        return (self.slot_t[start:end].copy(), self.img_h, self.img_w), \
+               (self.cond_t[idx:idx + n].copy(), self.cond_h, self.cond_w), self.embeddings[:, idx:idx + n], idx
+
+    def shift(self):
+        self.slot_t[:-1] = self.slot_t[1:].copy()                                                          # :133-139
+        self.slot_t[-1] = self.t_queue[0]
+        self.t_queue = self.t_queue[1:]
+
+
+def make_step_fn(transformer, scheduler, prompt_embeds: torch.Tensor, image_rotary_emb, vip: Optional[VipBook],
+                 guidance_scale: float, head_dim: int = 64, noise_override=None):
+    """fifo_onestep_per_gpu (:408-579) for one window on this rank's GPU: DiT forward (CFG pair, per-frame timesteps)
+    then the fused CFG + per-frame DPM step."""
+    from .rope import get_3d_rotary_pos_embed_v2
+    dev = prompt_embeds.device
+    B = prompt_embeds.shape[0]
+
+    def step(w: Window, latents, old_x0, t, prev_t, next_t, gen):
+        kw = {}
+        if vip is not None:
+            img_grid, cond_grid, emb, _ = vip.window(w.start, w.end)
+            kw = dict(vip_image_rotary_emb=get_3d_rotary_pos_embed_v2(head_dim, *img_grid, device=dev),
+                      vip_condition_rotary_emb=get_3d_rotary_pos_embed_v2(head_dim, *cond_grid, device=dev),
+                      vip_encoder_hidden_states=emb.contiguous())
+        ts = torch.as_tensor(np.ascontiguousarray(t), device=dev).expand(B, -1)
+        noise_pred = transformer(hidden_states=torch.cat([latents] * B), encoder_hidden_states=prompt_embeds, timestep=ts,
+                                 image_rotary_emb=image_rotary_emb, return_dict=False, **kw)[0]
+        return scheduler.window_step(noise_pred, latents, old_x0, t, prev_t, next_t, guidance_scale, generator=gen,
+                                     noise=None if noise_override is None else noise_override(w))
+
+    return step
