@@ -56,20 +56,32 @@ class DpmTables:
         return a_t ** 0.5, (1 - a_t) ** 0.5, mult0, mult1, mult2, mult3, mult_noise
 
 
-def step(tables: DpmTables, model_output, old_x0, timestep, prev_timestep, timestep_back, sample, noise1, noise2):
+def _smul(c, x, device_semantics: str):
+    """`c * x` for a 0-dim fp64 scalar tensor c and a tensor x, the way the reference writes it (scalar first).
+    PyTorch evaluates this differently per device when x is bf16: the CUDA kernels keep the scalar in fp32 (opmath),
+    the CPU kernels round it to bf16 first (only `x * c` keeps fp32 on CPU).  The reference runs on CUDA, so
+    device_semantics="cuda" is the behaviour to reproduce; "cpu" is what the unmodified reference yields when it is run
+    on the CPU to produce tests/golden/dpm.pt."""
+    return c * x if device_semantics == "cpu" else x * c
+
+
+def step(tables: DpmTables, model_output, old_x0, timestep, prev_timestep, timestep_back, sample, noise1, noise2,
+         device_semantics: str = "cuda"):
     """CogVideoXDPMScheduler.step (v_prediction), scheduling_dpm_cogvideox.py:424-468, with the two randn draws
     supplied (noise1 = first draw, noise2 = second draw)."""
     sa, sb, m0, m1, m2, m3, mn = tables.coefficients(int(timestep), int(prev_timestep),
                                                      None if timestep_back is None else int(timestep_back))
-    x0 = sa * sample - sb * model_output
-    prev = m0 * sample - m1 * x0 + mn * noise1
+    mul = lambda c, x: _smul(c, x, device_semantics)
+    x0 = mul(sa, sample) - mul(sb, model_output)
+    prev = mul(m0, sample) - mul(m1, x0) + mul(mn, noise1)
     if old_x0 is None or prev_timestep < 0:
         return prev, x0
-    d = m2 * x0 - m3 * old_x0
-    return m0 * sample - m1 * d + mn * noise2, x0
+    d = mul(m2, x0) - mul(m3, old_x0)
+    return mul(m0, sample) - mul(m1, d) + mul(mn, noise2), x0
 
 
-def window_step_bf16(tables: DpmTables, noise_pred, guidance_scale, latents, old_x0: List, t, prev_t, next_t, noise1, noise2):
+def window_step_bf16(tables: DpmTables, noise_pred, guidance_scale, latents, old_x0: List, t, prev_t, next_t, noise1, noise2,
+                     device_semantics: str = "cuda"):
     """The FIFO worker's CFG + per-frame scheduler loop, cogvideo_sampling_mp_fifo.py:527-550 (all tensors bf16).
     noise_pred [2,F,...], latents [1,F,...], old_x0 list of F (tensor [1,1,...] or None); t/prev_t/next_t int arrays [F]."""
     u, c = noise_pred.chunk(2)
@@ -79,7 +91,7 @@ def window_step_bf16(tables: DpmTables, noise_pred, guidance_scale, latents, old
     for j in range(latents.shape[1]):
         back = int(next_t[j]) if next_t[j] > 0 else None
         p, x0 = step(tables, npred[:, [j]], old_x0[j], int(t[j]), int(prev_t[j]), back, latents[:, [j]],
-                     noise1[:, [j]], noise2[:, [j]])
+                     noise1[:, [j]], noise2[:, [j]], device_semantics)
         out[:, [j]] = p.to(latents.dtype)
         x0s.append(x0.to(latents.dtype))
     return out, x0s

@@ -130,29 +130,41 @@ def test_full_size_block_vs_oracle():
     assert eh < 1e-2 and ee < 1e-2
 
 
-def test_dpm_step_kernel_bit_exact_vs_reference_golden(golden_dir):
-    """tg_cfg_dpm_step against outputs of the real CogVideoXDPMScheduler.step (bf16 chain and base fp32 chain)."""
+def test_dpm_step_kernel_bit_exact_vs_reference_chain(golden_dir):
+    """tg_cfg_dpm_step on the golden step cases of the real CogVideoXDPMScheduler.
+
+    The reference's result depends on the device it runs on: PyTorch's CUDA kernels keep a 0-dim fp64 scalar in fp32 when
+    multiplying a bf16 tensor, the CPU kernels round it to bf16 first (oracle/dpm.py:_smul).  The kernel reproduces the
+    CUDA behaviour (the reference runs on GPUs), so it is compared bit-for-bit with (a) the oracle in "cuda" semantics and
+    (b) the same chain evaluated op by op with torch on this GPU."""
     from oracle import dpm as odpm
     from tokensgen_b200 import _ext as E
     g = torch.load(os.path.join(golden_dir, "dpm.pt"))
     tb = odpm.DpmTables()
     n = 0
     for c in g["step_cases"]:
-        sa, sb, m0, m1, m2, m3, mn = tb.coefficients(c["t"], c["prev_t"], c["back"])
+        if c["model_output"].dtype != torch.bfloat16:
+            continue
+        coefs = tb.coefficients(c["t"], c["prev_t"], c["back"])
         second = c["old"] is not None and c["prev_t"] >= 0
-        coef = torch.tensor([[sa, sb, m0, m1, m2, m3, mn, 1.0 if second else 0.0]], dtype=torch.float64).float().cuda()
-        bf = c["model_output"].dtype == torch.bfloat16
+        coef = torch.tensor([[float(v) for v in coefs] + [1.0 if second else 0.0]], dtype=torch.float64).float().cuda()
         shp = c["sample"].shape
         flat = lambda t: None if t is None else t.reshape(1, -1).contiguous().cuda()
-        if bf:
-            prev, x0 = E.cfg_dpm_step(flat(c["model_output"]).unsqueeze(0), flat(c["sample"]), flat(c["old"]) if second else None,
-                                      flat(c["n1"]), flat(c["n2"]), coef, 0.0, E.DPM_BF16_CHAIN)
-            assert torch.equal(prev.cpu().view(shp), c["prev_sample"]) and torch.equal(x0.cpu().view(shp), c["x0"])
+        prev, x0 = E.cfg_dpm_step(flat(c["model_output"]).unsqueeze(0), flat(c["sample"]), flat(c["old"]) if second else None,
+                                  flat(c["n1"]), flat(c["n2"]), coef, 0.0, E.DPM_BF16_CHAIN)
+        p_o, x0_o = odpm.step(tb, c["model_output"], c["old"], c["t"], c["prev_t"], c["back"], c["sample"], c["n1"], c["n2"],
+                              device_semantics="cuda")
+        assert torch.equal(prev.cpu().view(shp), p_o) and torch.equal(x0.cpu().view(shp), x0_o)
+        # (b) torch on the GPU, written exactly like scheduling_dpm_cogvideox.py:439-463 (scalar first)
+        sa, sb, m0, m1, m2, m3, mn = coefs
+        smp, mo = c["sample"].cuda(), c["model_output"].cuda()
+        x0_t = sa * smp - sb * mo
+        if second:
+            d = m2 * x0_t - m3 * c["old"].cuda()
+            p_t = m0 * smp - m1 * d + mn * c["n2"].cuda()
         else:
-            mo = c["model_output"]
-            assert torch.equal(mo, mo.bfloat16().float()) or True
-            # the base chain consumes the bf16 network output upcast to fp32; feed a bf16-representable model output
-            continue
+            p_t = m0 * smp - m1 * x0_t + mn * c["n1"].cuda()
+        assert torch.equal(prev.view(shp), p_t) and torch.equal(x0.view(shp), x0_t)
         n += 1
     assert n >= 5
 

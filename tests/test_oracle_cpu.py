@@ -98,7 +98,9 @@ def test_dpm_tables_and_steps_bit_exact(golden_dir):
     assert tb.trailing_timesteps(50).tolist() == g["timesteps50"].tolist()
     assert len(g["step_cases"]) >= 10
     for c in g["step_cases"]:
-        p, x0 = odpm.step(tb, c["model_output"], c["old"], c["t"], c["prev_t"], c["back"], c["sample"], c["n1"], c["n2"])
+        # the goldens were produced by the reference ON THE CPU -> PyTorch's CPU scalar semantics (oracle/dpm.py:_smul)
+        p, x0 = odpm.step(tb, c["model_output"], c["old"], c["t"], c["prev_t"], c["back"], c["sample"], c["n1"], c["n2"],
+                          device_semantics="cpu")
         assert p.dtype == c["prev_sample"].dtype and torch.equal(p, c["prev_sample"])
         assert torch.equal(x0, c["x0"])
     x, n, y = g["renoise"]

@@ -190,13 +190,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             tc_fence_after();
             float s[128];
             {
-                uint32_t r[32];
+                // issue all four TMEM loads, then one wait: the loads overlap each other
+                uint32_t r0[32], r1[32], r2[32], r3[32];
+                tmem_ld32(s_addr, r0);
+                tmem_ld32(s_addr + 32, r1);
+                tmem_ld32(s_addr + 64, r2);
+                tmem_ld32(s_addr + 96, r3);
+                tmem_wait_ld();
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    tmem_ld32(s_addr + cc * 32, r);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) s[cc * 32 + i] = __uint_as_float(r[i]);
+                for (int i = 0; i < 32; ++i) {
+                    s[i] = __uint_as_float(r0[i]);
+                    s[32 + i] = __uint_as_float(r1[i]);
+                    s[64 + i] = __uint_as_float(r2[i]);
+                    s[96 + i] = __uint_as_float(r3[i]);
                 }
             }
             const int valid = p.kv_rows - j * AT_BLOCK_KV;
@@ -205,9 +211,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 for (int i = 0; i < 128; ++i)
                     if (i >= valid) s[i] = -INFINITY;
             }
-            float mx = s[0];
+            // row max with 8 independent chains (a single chain of 128 dependent FMNMX costs ~500 cycles of latency)
+            float pm[8];
 #pragma unroll
-            for (int i = 1; i < 128; ++i) mx = fmaxf(mx, s[i]);
+            for (int k = 0; k < 8; ++k) pm[k] = fmaxf(s[2 * k], s[2 * k + 1]);
+#pragma unroll
+            for (int i = 16; i < 128; i += 16)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pm[k] = fmaxf(pm[k], fmaxf(s[i + 2 * k], s[i + 2 * k + 1]));
+            const float mx = fmaxf(fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3])), fmaxf(fmaxf(pm[4], pm[5]), fmaxf(pm[6], pm[7])));
 
             const bool need = (mx - m_ref) * c > 8.0f;  // true on the first block (m_ref = -inf)
             if (j == 0) {
@@ -233,13 +245,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 }
             }
             const float mc = m_ref * c;
-            float sum = 0.f;
+            float ps[8];
 #pragma unroll
-            for (int i = 0; i < 128; ++i) {
-                s[i] = fast_exp2(fmaf(s[i], c, -mc));
-                sum += s[i];
-            }
-            l += sum;
+            for (int k = 0; k < 8; ++k) ps[k] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 128; i += 8)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    s[i + k] = fast_exp2(fmaf(s[i + k], c, -mc));
+                    ps[k] += s[i + k];
+                }
+            l += ((ps[0] + ps[1]) + (ps[2] + ps[3])) + ((ps[4] + ps[5]) + (ps[6] + ps[7]));
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
                 uint32_t r[32];
@@ -261,6 +277,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int b = bh / p.H, h = bh - b * p.H;
         __nv_bfloat16* o_ptr =
             p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D;
+        uint4 prev[8];
+        if (store && p.accumulate) {  // all loads of the read-modify-write first (see gemm.cu: epi_gate_residual)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) prev[i] = reinterpret_cast<const uint4*>(o_ptr)[i];
+        }
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
             uint32_t r[32];
@@ -272,9 +293,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     float f[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(r[i + k]) * inv_l;
-                    uint4* dst = reinterpret_cast<uint4*>(o_ptr + cc * 32 + i);
                     if (p.accumulate) {
-                        const uint4 old = *dst;
+                        const uint4 old = prev[cc * 4 + i / 8];
                         f[0] = fmaf(p.out_scale, f[0], bf16_lo(old.x)); f[1] = fmaf(p.out_scale, f[1], bf16_hi(old.x));
                         f[2] = fmaf(p.out_scale, f[2], bf16_lo(old.y)); f[3] = fmaf(p.out_scale, f[3], bf16_hi(old.y));
                         f[4] = fmaf(p.out_scale, f[4], bf16_lo(old.z)); f[5] = fmaf(p.out_scale, f[5], bf16_hi(old.z));
@@ -283,7 +303,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     uint4 v;
                     v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
                     v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
-                    *dst = v;
+                    reinterpret_cast<uint4*>(o_ptr + cc * 32 + i)[0] = v;
                 }
             }
         }

@@ -105,7 +105,7 @@ __device__ __forceinline__ void tile_coords(int tile, int m_tiles, int n_tiles, 
 }
 
 __device__ __forceinline__ void load8_bf16(const __nv_bfloat16* p, float (&f)[8]) {
-    uint4 v = *reinterpret_cast<const uint4*>(p);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(p));  // read-only operands only (bias, norm weights)
     f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
     f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
 }
@@ -149,17 +149,29 @@ __device__ __forceinline__ void epi_gate_residual(const GemmParams& p, float (&a
     add_bias<32>(acc, p.bias, n);
     if (row < p.M) {
         const RowInfo ri = row_info(p.map, row);
-        const __nv_bfloat16* g = modvec_row(p.gate, p.map, ri);
-        __nv_bfloat16* x = p.out + int64_t(row) * p.ldo + n;
+        const uint4* g = reinterpret_cast<const uint4*>(modvec_row(p.gate, p.map, ri) + n);
+        uint4* x = reinterpret_cast<uint4*>(p.out + int64_t(row) * p.ldo + n);
+        // all loads first, then all stores: a store to X followed by a load of the neighbouring 16 bytes of the same line
+        // would serialise on an L2 round trip per 8 elements
+        uint4 xr[4], gr[4];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < 4; ++i) xr[i] = x[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) gr[i] = __ldg(g + i);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
             float gv[8], xv[8];
-            load8_bf16(g + n + i, gv);
-            load8_bf16(x + i, xv);
+            gv[0] = bf16_lo(gr[i].x); gv[1] = bf16_hi(gr[i].x); gv[2] = bf16_lo(gr[i].y); gv[3] = bf16_hi(gr[i].y);
+            gv[4] = bf16_lo(gr[i].z); gv[5] = bf16_hi(gr[i].z); gv[6] = bf16_lo(gr[i].w); gv[7] = bf16_hi(gr[i].w);
+            xv[0] = bf16_lo(xr[i].x); xv[1] = bf16_hi(xr[i].x); xv[2] = bf16_lo(xr[i].y); xv[3] = bf16_hi(xr[i].y);
+            xv[4] = bf16_lo(xr[i].z); xv[5] = bf16_hi(xr[i].z); xv[6] = bf16_lo(xr[i].w); xv[7] = bf16_hi(xr[i].w);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) xv[j] = fmaf(gv[j], acc[i + j], xv[j]);
-            store8_bf16(x + i, xv);
+            for (int j = 0; j < 8; ++j) xv[j] = fmaf(gv[j], acc[i * 8 + j], xv[j]);
+            xr[i].x = pack_bf16x2(xv[0], xv[1]); xr[i].y = pack_bf16x2(xv[2], xv[3]);
+            xr[i].z = pack_bf16x2(xv[4], xv[5]); xr[i].w = pack_bf16x2(xv[6], xv[7]);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = xr[i];
     }
 }
 

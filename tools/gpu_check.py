@@ -160,6 +160,28 @@ def run_gemm_epi():
                 t[:, :, n_text + n_video:] = rope(t[:, :, n_text + n_video:], cos_c, sin_c)
         t = t[:, :, :outs[i].shape[2]]
         ok &= report(f"qkv proj {i}", outs[i], t, 6e-3)
+    # ---- full-size timings of the fused epilogues
+    B, F, hw, n_text, n_vip, d, H = 2, 13, 1350, 226, 480, 3072, 48
+    n_video = F * hw
+    rows = n_text + n_video + n_vip
+    rm = E.make_rowmap(n_text, n_video, n_vip, hw, F)
+    x = torch.randn(B * rows, d, device=dev).bfloat16()
+    table = torch.randn(B * F, 18 * d, device=dev).bfloat16()
+    gate = E.make_modvec(table[:, 5 * d:6 * d], table[:, 2 * d:3 * d], table[:, 14 * d:15 * d])
+    for K in (3072, 12288):
+        a = torch.randn(B * rows, K, device=dev).bfloat16()
+        w = (torch.randn(d, K, device=dev) / K ** 0.5).bfloat16()
+        bias = torch.randn(d, device=dev).bfloat16()
+        for _ in range(2):
+            E.gemm_gate_residual(a, w, bias, x, B, rm, gate)
+        s_, e_ = torch.cuda.Event(True), torch.cuda.Event(True)
+        s_.record()
+        for _ in range(5):
+            E.gemm_gate_residual(a, w, bias, x, B, rm, gate)
+        e_.record()
+        torch.cuda.synchronize()
+        ms = s_.elapsed_time(e_) / 5
+        print(f"  gemm_gate_residual {B * rows}x{d}x{K}: {ms:.3f} ms  {2 * B * rows * d * K / ms / 1e9:.1f} TFLOP/s")
     return ok
 
 
