@@ -184,7 +184,8 @@ def test_window_step_vs_oracle_loop():
         t, pt, nt = t_tab[start:start + F], prev_tab[start:start + F], next_tab[start:start + F]
         npred = torch.randn(2, F, *shp, generator=gen).bfloat16()
         lat = torch.randn(1, F, *shp, generator=gen).bfloat16()
-        old = [torch.randn(1, 1, *shp, generator=gen).bfloat16() if (j % 5 != 0) else None for j in range(F)]
+        # a slot without a history timestep (next_t <= 0: the freshly re-noised tail) never carries an x0 history
+        old = [torch.randn(1, 1, *shp, generator=gen).bfloat16() if (j % 5 != 0 and nt[j] > 0) else None for j in range(F)]
         n1 = torch.randn(1, F, *shp, generator=gen).bfloat16()
         n2 = torch.randn(1, F, *shp, generator=gen).bfloat16()
         ref_lat, ref_x0 = odpm.window_step_bf16(tb, npred, 6.0, lat, old, t, pt, nt, n1, n2)

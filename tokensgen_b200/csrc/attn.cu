@@ -9,10 +9,11 @@
 //   warps 4..7   softmax for tile 0 (thread = one query row; no cross-thread reductions)
 //   warps 8..11  softmax for tile 1
 // The two tiles ping-pong: while one tile's rows are in softmax (MUFU-bound at hd=64), the tensor core runs the
-// other tile's PV and next QK^T.  S_t lives in TMEM (128 fp32 columns); P_t (bf16) overwrites the first 64
-// columns of S_t and is consumed by the PV MMA straight from TMEM.  O_t accumulates in TMEM (64 columns) and is
-// rescaled lazily (only when the running max grows by > 2^8), which keeps the exact result because P and the row
-// sum always share the same reference max.
+// other tile's MMAs.  TMEM (512 columns): S_t 128 fp32 columns, O_t 64, P_t 64 (bf16 pairs) for t = 0,1.  P_t has its
+// own columns so that S_t can be overwritten by the NEXT block's QK^T as soon as the softmax threads have pulled S_t
+// into registers (s_free barrier) — the QK^T round trip is then off the softmax critical path.  The PV MMA reads P_t
+// straight from TMEM.  O_t is rescaled lazily (only when the running max grows by > 2^8), which keeps the exact result
+// because P and the row sum always share the same reference max.
 #include <cuda_bf16.h>
 
 #include "common.h"
@@ -52,7 +53,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * AT_STAGES + t); };
     auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * AT_STAGES + t); };
     auto o_done = [&](int t) { return bar_base + 8u * (5 + 2 * AT_STAGES + t); };
-    const uint32_t tmem_slot = bar_base + 8u * (7 + 2 * AT_STAGES);
+    auto s_free = [&](int t) { return bar_base + 8u * (7 + 2 * AT_STAGES + t); };
+    const uint32_t tmem_slot = bar_base + 8u * (9 + 2 * AT_STAGES);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -76,6 +78,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int t = 0; t < 2; ++t) {
             mbar_init(s_full(t), 1);
             mbar_init(p_full(t), 4);  // one arrive per softmax warp of the tile
+            mbar_init(s_free(t), 4);
             mbar_init(o_done(t), 1);
         }
         fence_barrier_init();
@@ -85,9 +88,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
-    // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384); P_t aliases S_t[0,64).
+    // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512)
     auto s_col = [&](int t) { return uint32_t(t * 128); };
     auto o_col = [&](int t) { return uint32_t(256 + t * 64); };
+    auto p_col = [&](int t) { return uint32_t(384 + t * 64); };
 
     if (warp < 4) {
         reg_dealloc<80>();
@@ -133,7 +137,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     for (int k = 0; k < AT_BLOCK_KV / 16; ++k) {
                         // 16 kv rows per MMA = two 8-row swizzle groups (SBO 1024 B apart); N = 64 is one MN atom.
                         const uint64_t db = make_smem_desc_sw128(vs + k * 2048, 1024, 1024);
-                        umma_ts(tmem_base + o_col(t), tmem_base + s_col(t) + uint32_t(k * 8), db, idesc_pv,
+                        umma_ts(tmem_base + o_col(t), tmem_base + p_col(t) + uint32_t(k * 8), db, idesc_pv,
                                 (first && k == 0) ? 0u : 1u);
                     }
                 };
@@ -153,18 +157,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                     }
                     const bool has_next = (j + 1 < n_blocks);
                     for (int t = 0; t < 2; ++t) {
+                        if (has_next) {
+                            // S_t(j) has been pulled into registers: overwrite it with the next block's scores now
+                            mbar_wait(s_free(t), uint32_t(j & 1), 0x209);
+                            if (t == 0) mbar_wait(kv_full(nstage), nphase, 0x205);
+                            tc_fence_after();
+                            issue_qk(t, nstage);
+                        }
                         mbar_wait(p_full(t), uint32_t(j & 1), 0x204);
                         tc_fence_after();
                         issue_pv(t, stage, j == 0);
                         if (t == 1) umma_commit(kv_empty(stage));
                         umma_commit(o_done(t));
-                        if (has_next) {
-                            if (t == 0) {
-                                mbar_wait(kv_full(nstage), nphase, 0x205);
-                                tc_fence_after();
-                            }
-                            issue_qk(t, nstage);
-                        }
                     }
                     stage = nstage;
                     phase = nphase;
@@ -181,6 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const uint32_t lane_base = tmem_base + (uint32_t(wq * 32) << 16);
         const uint32_t s_addr = lane_base + s_col(t);
         const uint32_t o_addr = lane_base + o_col(t);
+        const uint32_t p_addr = lane_base + p_col(t);
         const float c = p.scale_log2;
         float m_ref = -INFINITY;  // reference max (raw score units)
         float l = 0.f;            // running sum of exp2((s - m_ref) * c)
@@ -197,6 +202,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 tmem_ld32(s_addr + 64, r2);
                 tmem_ld32(s_addr + 96, r3);
                 tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free(t));
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                     s[i] = __uint_as_float(r0[i]);
@@ -224,24 +232,26 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
             const bool need = (mx - m_ref) * c > 8.0f;  // true on the first block (m_ref = -inf)
             if (j == 0) {
                 m_ref = mx;
-            } else if (__any_sync(0xffffffffu, need)) {
-                float alpha = 1.0f;
-                if (need) {
-                    alpha = fast_exp2((m_ref - mx) * c);
-                    m_ref = mx;
-                    l *= alpha;
-                }
-                // O_t holds PV over blocks < j: its last MMA must have landed before we touch it.
+            } else {
+                // PV_t(j-1) must have landed before P_t is overwritten or O_t rescaled (almost always already true)
                 mbar_wait(o_done(t), uint32_t((j - 1) & 1), 0x207);
                 tc_fence_after();
+                if (__any_sync(0xffffffffu, need)) {
+                    float alpha = 1.0f;
+                    if (need) {
+                        alpha = fast_exp2((m_ref - mx) * c);
+                        m_ref = mx;
+                        l *= alpha;
+                    }
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    uint32_t r[32];
-                    tmem_ld32(o_addr + cc * 32, r);
-                    tmem_wait_ld();
+                    for (int cc = 0; cc < 2; ++cc) {
+                        uint32_t r[32];
+                        tmem_ld32(o_addr + cc * 32, r);
+                        tmem_wait_ld();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    tmem_st32(o_addr + cc * 32, r);
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st32(o_addr + cc * 32, r);
+                    }
                 }
             }
             const float mc = m_ref * c;
@@ -261,7 +271,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 uint32_t r[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) r[i] = pack_bf16x2(s[cc * 64 + 2 * i], s[cc * 64 + 2 * i + 1]);
-                tmem_st32(s_addr + cc * 32, r);
+                tmem_st32(p_addr + cc * 32, r);
             }
             tmem_wait_st();
             tc_fence_before();

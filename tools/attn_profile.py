@@ -1,0 +1,19 @@
+"""Small driver for ncu captures of the attention kernel (one head group of the full 17 776-token problem)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tokensgen_b200 import _ext as E  # noqa: E402
+
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+N = 17776
+torch.manual_seed(0)
+q = torch.randn(1, H, N, 64, device="cuda").bfloat16()
+k = torch.randn(1, H, N, 64, device="cuda").bfloat16()
+v = torch.randn(1, H, N, 64, device="cuda").bfloat16()
+out = torch.empty(1, N, H * 64, device="cuda", dtype=torch.bfloat16)
+for _ in range(3):
+    E.attn_fwd(q, k, v, out)
+torch.cuda.synchronize()
