@@ -33,6 +33,10 @@ typedef uint16_t tg_bf16; /* raw bfloat16 bits */
 
 int tg_version(void);
 const char* tg_last_error(void);
+/* Developer tuning knobs (process-wide, not thread-safe; defaults are the shipped configuration):
+ *   "attn_impl" 1|2 : attention kernel generation;  "attn_emu" 0..4 : exponentials per 8 evaluated by polynomial on the
+ *   FMA pipe instead of MUFU.EX2 (tg_attn_fwd).  Returns 0, or -2 for an unknown key. */
+int tg_set_tuning(const char* key, int value);
 
 /* Row layout of the residual stream, shared by the fused epilogues:
  * row r of a batch is text if r < n_text, video if r < n_text + n_video (frame = (r - n_text) / hw), else vip. */

@@ -51,6 +51,7 @@ _VP, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SYMBOLS = {
     "tg_version": (C.c_int, []),
     "tg_last_error": (C.c_char_p, []),
+    "tg_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "tg_time_embedding": (C.c_int, [_VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tg_ln_modulate": (C.c_int, [_VP, _VP, _I, _I, C.POINTER(RowMap), _VP, _VP, _VP, _VP, _F, _VP, _VP, _F,
                                  C.POINTER(ModVec), C.POINTER(ModVec), _VP]),
@@ -109,6 +110,10 @@ def load() -> C.CDLL:
             raise TokensGenError(f"ABI version mismatch: library reports {lib.tg_version()}")
         _lib = lib
     return _lib
+
+
+def set_tuning(key: str, value: int) -> None:
+    _check(load().tg_set_tuning(key.encode(), int(value)), "tg_set_tuning")
 
 
 def _check(rc: int, what: str) -> None:

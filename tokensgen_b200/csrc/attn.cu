@@ -16,6 +16,8 @@
 // because P and the row sum always share the same reference max.
 #include <cuda_bf16.h>
 
+#include <string>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -37,6 +39,9 @@ struct AttnParams {
     float scale_log2;  // softmax_scale * log2(e)
     int accumulate;
     float out_scale;
+    long long* trace;  // developer timeline (tools/attn_trace.py): [16 softmax warps][n_blocks][6] clock64 stamps of CTA (0,0)
+    int mutex;    // v2: the two tiles take turns on the MUFU pipe (named-barrier hand-off) instead of sharing it
+    int stagger;  // v2: cycles by which tile 1 starts after tile 0 (keeps the two tiles' softmax phases interleaved)
 };
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
@@ -327,6 +332,379 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
 }
 
+
+// =====================================================================================================================
+// v2: same tiling (one CTA = one (batch, head) x two 128-row query tiles, 128-row KV blocks, 4-stage TMA ring) with
+//   * 16 softmax warps (4 per SM sub-partition instead of 2): every query row is shared by two threads, each owning 64
+//     of the block's 128 score columns; they exchange their partial row max through shared memory (one 64-thread named
+//     barrier per block).  The extra warps hide the TMEM-load / barrier / MUFU latencies that left the MUFU pipe at 62 %.
+//   * one MMA-issuing thread PER TILE (warps 1 and 3) so that neither tile's QK^T / PV issue ever queues behind a wait
+//     on the other tile's softmax.
+//   * the wait for the previous PV (o_done) moved from before the exponentials to just before P is overwritten.
+//   * EMU of every 8 exponentials evaluated on the FMA pipe (Cody-Waite split + degree-3 polynomial, max rel. error
+//     8.8e-5, far below the bf16 rounding of P) instead of MUFU.EX2 (16 results/clk/SM is the binding limit at hd = 64).
+constexpr int A2_THREADS = 640;
+constexpr int A2_XCH_BYTES = 2 * 2 * 2 * 128 * 4;  // [parity][tile][half][row] fp32
+constexpr int A2_SMEM_BYTES = 2 * AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + A2_XCH_BYTES + 256 + 1024;
+
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -127.0f);
+    float t;
+    asm("add.rm.ftz.f32 %0, %1, 0f4B400000;" : "=f"(t) : "f"(x));  // x + 1.5*2^23, rounded down: low mantissa bits = floor(x)
+    const float fl = t - 12582912.0f;
+    const float f = x - fl;  // [0, 1)
+    float p = fmaf(f, 0.077119089663028717f, 0.227564394474029541f);
+    p = fmaf(p, f, 0.695146143436431885f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+template <int EMU, bool MUTEX, bool TRACE, bool PACKED>
+__global__ void __launch_bounds__(A2_THREADS, 1)
+attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = smem_base;
+    const uint32_t kv_smem = smem_base + 2 * AT_TILE_BYTES;
+    const uint32_t xch_smem = kv_smem + AT_STAGES * 2 * AT_TILE_BYTES;
+    const uint32_t bar_base = xch_smem + A2_XCH_BYTES;
+    const uint32_t q_full = bar_base;
+    auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + AT_STAGES + s); };
+    auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * AT_STAGES + t); };
+    auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * AT_STAGES + t); };
+    auto o_done = [&](int t) { return bar_base + 8u * (5 + 2 * AT_STAGES + t); };
+    auto s_free = [&](int t) { return bar_base + 8u * (7 + 2 * AT_STAGES + t); };
+    const uint32_t tmem_slot = bar_base + 8u * (9 + 2 * AT_STAGES);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* xch = reinterpret_cast<float*>(smem_raw + (xch_smem - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bh = blockIdx.y;
+    const int q0 = blockIdx.x * (2 * AT_BLOCK_Q);
+    const int n_blocks = (p.kv_rows + AT_BLOCK_KV - 1) / AT_BLOCK_KV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < AT_STAGES; ++s) {
+            mbar_init(kv_full(s), 1);
+            mbar_init(kv_empty(s), 2);  // one commit per tile's MMA thread
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(s_full(t), 1);
+            mbar_init(p_full(t), 8);  // one arrive per softmax warp of the tile
+            mbar_init(s_free(t), 8);
+            mbar_init(o_done(t), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    auto s_col = [&](int t) { return uint32_t(t * 128); };
+    auto o_col = [&](int t) { return uint32_t(256 + t * 64); };
+    auto p_col = [&](int t) { return uint32_t(384 + t * 64); };
+
+    if (warp < 4) {
+        reg_dealloc<40>();
+        if (warp == 0) {
+            // -------------------------------------------------------------- TMA producer
+            if (lane == 0) {
+                mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+                tma_load_3d(q_smem, &tmap_q, q_full, 0, q0, bh);
+                tma_load_3d(q_smem + AT_TILE_BYTES, &tmap_q, q_full, 0, q0 + AT_BLOCK_Q, bh);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_blocks; ++j) {
+                    mbar_wait(kv_empty(stage), phase ^ 1u, 0x301);
+                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+                    mbar_arrive_expect_tx(kv_full(stage), 2 * AT_TILE_BYTES);
+                    tma_load_3d(ks, &tmap_k, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                    tma_load_3d(ks + AT_TILE_BYTES, &tmap_v, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                    if (++stage == AT_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        } else if (warp == 1 || warp == 3) {
+            // -------------------------------------------------------------- MMA issuer of tile t
+            if (lane == 0) {
+                const int t = warp >> 1;
+                constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);  // V is MN-major
+                const uint32_t qs = q_smem + t * AT_TILE_BYTES;
+                auto issue_qk = [&](int stage) {
+                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(qs + k * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc_sw128(ks + k * 32, 16, 1024);
+                        umma_ss(tmem_base + s_col(t), da, db, idesc_qk, k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(s_full(t));
+                };
+                auto issue_pv = [&](int stage, bool first) {
+                    const uint32_t vs = kv_smem + stage * 2 * AT_TILE_BYTES + AT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < AT_BLOCK_KV / 16; ++k) {
+                        const uint64_t db = make_smem_desc_sw128(vs + k * 2048, 1024, 1024);
+                        umma_ts(tmem_base + o_col(t), tmem_base + p_col(t) + uint32_t(k * 8), db, idesc_pv,
+                                (first && k == 0) ? 0u : 1u);
+                    }
+                };
+                mbar_wait(q_full, 0, 0x302);
+                mbar_wait(kv_full(0), 0, 0x303);
+                if (t == 1 && p.stagger > 0) {
+                    // The two tiles only interact through the shared MUFU pipe, which preserves whatever phase offset
+                    // they start with: started together, both sit in their latency-bound phase (TMEM
+                    // load, row max, barriers) at the same time and the MUFU pipe idles for that long every block.
+                    const long long t0 = clock64();
+                    while (clock64() - t0 < p.stagger) {}
+                }
+                tc_fence_after();
+                issue_qk(0);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_blocks; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == AT_STAGES) {
+                        nstage = 0;
+                        nphase ^= 1u;
+                    }
+                    if (j + 1 < n_blocks) {
+                        mbar_wait(s_free(t), uint32_t(j & 1), 0x309);  // S_t(j) is in registers: overwrite it
+                        mbar_wait(kv_full(nstage), nphase, 0x305);
+                        tc_fence_after();
+                        issue_qk(nstage);
+                    }
+                    mbar_wait(p_full(t), uint32_t(j & 1), 0x304);
+                    tc_fence_after();
+                    issue_pv(stage, j == 0);
+                    umma_commit(kv_empty(stage));
+                    umma_commit(o_done(t));
+                    stage = nstage;
+                    phase = nphase;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps
+        reg_alloc<104>();
+        const int sw = warp - 4;
+        const int t = sw >> 3;          // tile
+        const int half = (sw >> 2) & 1;  // which 64 of the block's 128 score columns
+        const int wq = warp & 3;         // TMEM lane quarter
+        const int row_in_tile = wq * 32 + lane;
+        const int q_row = q0 + t * AT_BLOCK_Q + row_in_tile;
+        const uint32_t lane_base = tmem_base + (uint32_t(wq * 32) << 16);
+        const uint32_t s_addr = lane_base + s_col(t) + uint32_t(half * 64);
+        const uint32_t o_addr = lane_base + o_col(t) + uint32_t(half * 32);
+        const uint32_t p_addr = lane_base + p_col(t) + uint32_t(half * 32);
+        const int pair_bar = 1 + t * 4 + wq;
+        const float c = p.scale_log2;
+        float m_ref = -INFINITY;
+        float l = 0.f;
+
+        for (int j = 0; j < n_blocks; ++j) {
+            const bool tr = TRACE && p.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+            long long* trp = p.trace + (int64_t(sw) * n_blocks + j) * 6;
+            if (tr) trp[0] = clock64();
+            mbar_wait(s_full(t), uint32_t(j & 1), 0x306);
+            tc_fence_after();
+            if (tr) trp[1] = clock64();
+            float s[64];
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(s_addr, r0);
+                tmem_ld32(s_addr + 32, r1);
+                tmem_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(s_free(t));
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    s[i] = __uint_as_float(r0[i]);
+                    s[32 + i] = __uint_as_float(r1[i]);
+                }
+            }
+            if (tr) trp[2] = clock64();
+            const int valid = p.kv_rows - j * AT_BLOCK_KV - half * 64;
+            if (valid < 64) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i >= valid) s[i] = -INFINITY;
+            }
+            float pm[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pm[k] = fmaxf(s[2 * k], s[2 * k + 1]);
+#pragma unroll
+            for (int i = 8; i < 64; i += 8)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pm[k] = fmaxf(pm[k], fmaxf(s[i + 2 * k], s[i + 2 * k + 1]));
+            float mx = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+            {
+                float* slot = xch + ((((j & 1) * 2 + t) * 2) * 128) + row_in_tile;
+                slot[half * 128] = mx;
+                named_bar_sync(pair_bar, 64);
+                mx = fmaxf(mx, slot[(half ^ 1) * 128]);
+            }
+            if (tr) trp[3] = clock64();
+            bool waited = false;
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const bool need = (mx - m_ref) * c > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {
+                    mbar_wait(o_done(t), uint32_t((j - 1) & 1), 0x307);
+                    tc_fence_after();
+                    waited = true;
+                    float alpha = 1.0f;
+                    if (need) {
+                        alpha = fast_exp2((m_ref - mx) * c);
+                        m_ref = mx;
+                        l *= alpha;
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(o_addr, r);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st32(o_addr, r);
+                }
+            }
+            const float mc = m_ref * c;
+            float ps[4] = {0.f, 0.f, 0.f, 0.f};
+            // MUFU hand-off: tile t may start its exponentials once tile 1-t has finished its own (ids 9, 10; 256 waiting
+            // + 256 arriving threads).  Shared fairly, both tiles would sit in their latency-bound phases (S load, row max
+            // exchange, P store) at the same time and leave the MUFU pipe idle for that long in every block.
+            if (MUTEX && (j > 0 || t == 1)) asm volatile("bar.sync %0, 512;" ::"r"(10 - t) : "memory");
+            if constexpr (PACKED) {
+                const uint64_t c2 = pack_f32x2(c, c), nmc2 = pack_f32x2(-mc, -mc);
+                uint64_t ps2[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+                for (int i = 0; i < 64; i += 8)
+#pragma unroll
+                    for (int k = 0; k < 8; k += 2) {
+                        const uint64_t x2 = fma_f32x2(pack_f32x2(s[i + k], s[i + k + 1]), c2, nmc2);
+                        s[i + k] = (k < EMU) ? ex2_poly(f32x2_lo(x2)) : fast_exp2(f32x2_lo(x2));
+                        s[i + k + 1] = (k + 1 < EMU) ? ex2_poly(f32x2_hi(x2)) : fast_exp2(f32x2_hi(x2));
+                        ps2[k >> 1] = add_f32x2(ps2[k >> 1], pack_f32x2(s[i + k], s[i + k + 1]));
+                    }
+                const uint64_t a = add_f32x2(add_f32x2(ps2[0], ps2[1]), add_f32x2(ps2[2], ps2[3]));
+                l += f32x2_lo(a) + f32x2_hi(a);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; i += 8)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const float x = fmaf(s[i + k], c, -mc);
+                        s[i + k] = (k < EMU) ? ex2_poly(x) : fast_exp2(x);
+                        ps[k & 3] += s[i + k];
+                    }
+                l += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+            }
+            if (MUTEX) asm volatile("bar.arrive %0, 512;" ::"r"(9 + t) : "memory");
+            uint32_t r[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = pack_bf16x2(s[2 * i], s[2 * i + 1]);
+            if (tr) trp[4] = clock64();
+            if (j > 0 && !waited) {  // PV_t(j-1) must have read P_t before it is overwritten (long done by now)
+                mbar_wait(o_done(t), uint32_t((j - 1) & 1), 0x30a);
+                tc_fence_after();
+            }
+            tmem_st32(p_addr, r);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full(t));
+            if (tr) trp[5] = clock64();
+        }
+
+        if (MUTEX && t == 0) asm volatile("bar.sync 10, 512;" ::: "memory");  // consume tile 1's last hand-off
+        // ---- epilogue: O / l -> global (this thread: 32 of the row's 64 output columns)
+        {
+            float* slot = xch + ((((n_blocks & 1) * 2 + t) * 2) * 128) + row_in_tile;
+            slot[half * 128] = l;
+            named_bar_sync(pair_bar, 64);
+            l += slot[(half ^ 1) * 128];
+        }
+        mbar_wait(o_done(t), uint32_t((n_blocks - 1) & 1), 0x308);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const bool store = q_row < p.q_rows;
+        const int b = bh / p.H, h = bh - b * p.H;
+        __nv_bfloat16* o_ptr =
+            p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D + half * 32;
+        uint4 prev[4];
+        if (store && p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prev[i] = reinterpret_cast<const uint4*>(o_ptr)[i];
+        }
+        uint32_t r[32];
+        tmem_ld32(o_addr, r);
+        tmem_wait_ld();
+        if (store) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(r[i + k]) * inv_l;
+                if (p.accumulate) {
+                    const uint4 old = prev[i / 8];
+                    f[0] = fmaf(p.out_scale, f[0], bf16_lo(old.x)); f[1] = fmaf(p.out_scale, f[1], bf16_hi(old.x));
+                    f[2] = fmaf(p.out_scale, f[2], bf16_lo(old.y)); f[3] = fmaf(p.out_scale, f[3], bf16_hi(old.y));
+                    f[4] = fmaf(p.out_scale, f[4], bf16_lo(old.z)); f[5] = fmaf(p.out_scale, f[5], bf16_hi(old.z));
+                    f[6] = fmaf(p.out_scale, f[6], bf16_lo(old.w)); f[7] = fmaf(p.out_scale, f[7], bf16_hi(old.w));
+                }
+                uint4 v;
+                v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+                v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+                reinterpret_cast<uint4*>(o_ptr + i)[0] = v;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int g_attn_impl = 2;  // 1 = v1 (8 softmax warps), 2 = v2
+static int g_attn_emu = 0;   // exponentials per 8 evaluated on the FMA pipe (v2)
+static int g_attn_stagger = 0;
+static long long* g_attn_trace = nullptr;
+static int g_attn_mutex = 0;
+static int g_attn_packed = 1;
+
+template <int EMU, bool MUTEX, bool TRACE, bool PACKED>
+static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const AttnParams& p) {
+    static bool attr_set = false;
+    auto kern = attn2_fwd_kernel<EMU, MUTEX, TRACE, PACKED>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<grid, A2_THREADS, A2_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    return check_launch("attn_fwd");
+}
+
 }  // namespace tg
 
 using namespace tg;
@@ -365,6 +743,9 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.accumulate = accumulate;
     p.out_scale = out_scale;
+    p.stagger = g_attn_stagger;
+    p.trace = g_attn_trace;
+    p.mutex = g_attn_mutex;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
@@ -372,6 +753,36 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
         attr_set = true;
     }
     dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
-    attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tq, tk, tv, p);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_attn_impl == 2) {
+        if (g_attn_trace != nullptr) return launch_attn2<0, false, true, false>(grid, st, tq, tk, tv, p);
+#define TG_A2(E)                                                                        \
+    case E:                                                                             \
+        return g_attn_packed ? launch_attn2<E, false, false, true>(grid, st, tq, tk, tv, p)   \
+                             : launch_attn2<E, false, false, false>(grid, st, tq, tk, tv, p);
+        if (g_attn_mutex) return launch_attn2<0, true, false, false>(grid, st, tq, tk, tv, p);
+        switch (g_attn_emu) {
+            TG_A2(0) TG_A2(1) TG_A2(2) TG_A2(3)
+            default: return fail(-7, "attn_fwd: attn_emu must be 0..3");
+        }
+#undef TG_A2
+    }
+    attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd");
+}
+
+extern "C" int tg_debug_attn_trace(void* device_buffer) {  // developer hook, not in the public header
+    g_attn_trace = static_cast<long long*>(device_buffer);
+    return 0;
+}
+
+extern "C" int tg_set_tuning(const char* key, int value) {
+    if (key == nullptr) return fail(-1, "set_tuning: null key");
+    const std::string k(key);
+    if (k == "attn_impl") { g_attn_impl = value; return 0; }
+    if (k == "attn_emu") { g_attn_emu = value; return 0; }
+    if (k == "attn_stagger") { g_attn_stagger = value; return 0; }
+    if (k == "attn_mutex") { g_attn_mutex = value; return 0; }
+    if (k == "attn_packed") { g_attn_packed = value; return 0; }
+    return fail(-2, "set_tuning: unknown key %s", key);
 }

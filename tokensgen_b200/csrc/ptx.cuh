@@ -209,6 +209,23 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Packed fp32 pairs (FFMA2 / FADD2): one issue slot for two results.
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+    return (uint64_t(__float_as_uint(hi)) << 32) | __float_as_uint(lo);
+}
+__device__ __forceinline__ float f32x2_lo(uint64_t v) { return __uint_as_float(uint32_t(v)); }
+__device__ __forceinline__ float f32x2_hi(uint64_t v) { return __uint_as_float(uint32_t(v >> 32)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

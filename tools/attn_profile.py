@@ -1,4 +1,5 @@
-"""Small driver for ncu captures of the attention kernel (one head group of the full 17 776-token problem)."""
+"""Small driver for ncu captures of the attention kernel (one batch of the full 17 776-token problem).
+usage: attn_profile.py [heads] [impl] [emu] [stagger]"""
 import os
 import sys
 
@@ -8,6 +9,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tokensgen_b200 import _ext as E  # noqa: E402
 
 H = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+if len(sys.argv) > 2:
+    E.set_tuning("attn_impl", int(sys.argv[2]))
+if len(sys.argv) > 3:
+    E.set_tuning("attn_emu", int(sys.argv[3]))
+if len(sys.argv) > 4:
+    E.set_tuning("attn_stagger", int(sys.argv[4]))
 N = 17776
 torch.manual_seed(0)
 q = torch.randn(1, H, N, 64, device="cuda").bfloat16()

@@ -194,6 +194,21 @@ def attn_ref(q, k, v, scale):
 
 
 def run_attn():
+    from tokensgen_b200 import _ext as E
+    ok = True
+    variants = [(2, 0, 0), (2, 0, 1), (2, 1, 1), (2, 2, 1), (2, 3, 1)]
+    if os.environ.get("TG_ATTN_VARIANTS"):
+        variants = [tuple(int(x) for x in v.split(":")) for v in os.environ["TG_ATTN_VARIANTS"].split(",")]
+    for impl, emu, packed in variants:
+        print(f" -- attention kernel v{impl} emu={emu} packed={packed}", flush=True)
+        E.set_tuning("attn_impl", impl)
+        E.set_tuning("attn_emu", emu)
+        E.set_tuning("attn_packed", packed)
+        ok &= run_attn_variant(full_ref=(impl, emu, packed) == variants[-1])
+    return ok
+
+
+def run_attn_variant(full_ref=True):
     import torch
     from tokensgen_b200 import _ext as E
     torch.manual_seed(2)
@@ -250,6 +265,8 @@ def run_attn():
     print(f"  attn full {B}x{H}x{N}: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
     ref = torch.nn.functional.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).flatten(2)
     ok &= report("attn full vs torch sdpa(bf16)", out, ref, 1e-2)
+    if not full_ref:
+        return ok
     s.record()
     for _ in range(5):
         torch.nn.functional.scaled_dot_product_attention(q, k, v)
