@@ -237,11 +237,86 @@ def gen_fifo_trace():
     (GOLDEN / "fifo_trace.json").write_text(json.dumps(traces))
 
 
+VAE_TINY = dict(block_out_channels=(32, 64, 64, 64), latent_channels=16, layers_per_block=1, norm_num_groups=8,
+                sample_height=96, sample_width=80, scaling_factor=0.7)
+
+
+def gen_vae_tiny():
+    """The in-tree AutoencoderKLCogVideoX (longvgen/models/autoencoder_kl_cogvideox.py) on a small configuration whose tile
+    arithmetic is consistent (overlap * 8 == row limit, like 480x720): untiled encode/decode across several frame batches
+    (conv cache), tiled encode/decode with blending, and the layer classes in isolation."""
+    import longvgen.models.autoencoder_kl_cogvideox as m
+    from oracle.vae import VaeConfig, vae_shapes
+    cfg = VaeConfig(**VAE_TINY)
+    vae = m.AutoencoderKLCogVideoX(in_channels=3, out_channels=3, block_out_channels=cfg.block_out_channels,
+                                   latent_channels=cfg.latent_channels, layers_per_block=cfg.layers_per_block,
+                                   norm_num_groups=cfg.norm_num_groups, sample_height=cfg.sample_height,
+                                   sample_width=cfg.sample_width, scaling_factor=cfg.scaling_factor).eval()
+    shapes = {k: list(v.shape) for k, v in vae.state_dict().items()}
+    mine = vae_shapes(cfg)
+    assert shapes == mine, (set(shapes) ^ set(mine), [k for k in shapes if k in mine and shapes[k] != mine[k]])
+    sd = synth_state_dict(shapes, seed=4321)
+    g = torch.Generator().manual_seed(17)
+    blob = {"digest": state_dict_digest(sd)}
+    x = (torch.rand(1, 3, 17, 32, 40, generator=g) * 2 - 1).bfloat16()
+    z = torch.randn(1, 16, 5, 4, 5, generator=g).bfloat16()
+    zt = torch.randn(1, 16, 13, 12, 10, generator=g).bfloat16()
+    xt = (torch.rand(1, 3, 9, 96, 80, generator=g) * 2 - 1).bfloat16()
+    blob["inputs"] = dict(x=x, z=z, zt=zt, xt=xt)
+    for dt, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        vae.load_state_dict({k: v.to(dt) for k, v in sd.items()})
+        vae.to(dt)
+        with torch.no_grad():
+            vae.disable_tiling()
+            blob["enc_" + tag] = vae.encode(x.to(dt)).latent_dist.parameters.clone()
+            blob["dec_" + tag] = vae.decode(z.to(dt)).sample.clone()
+            if dt == torch.float32:
+                vae.enable_tiling()
+                blob["tiled_dec_f32"] = vae.decode(zt.to(dt)).sample.clone()
+                blob["tiled_enc_f32"] = vae.encode(xt.to(dt)).latent_dist.parameters.clone()
+                vae.disable_tiling()
+    vae.load_state_dict({k: v.float() for k, v in sd.items()})
+    vae.float()
+    # layers in isolation (fp32)
+    with torch.no_grad():
+        conv = vae.decoder.up_blocks[3].resnets[0].conv1  # 64 -> 32
+        a = torch.randn(1, 64, 3, 6, 7, generator=g)
+        b = torch.randn(1, 64, 2, 6, 7, generator=g)
+        conv._clear_fake_context_parallel_cache()
+        blob["conv_two_calls"] = (a, b, conv(a).clone(), conv(b).clone())
+        conv._clear_fake_context_parallel_cache()
+        sn = vae.decoder.mid_block.resnets[0].norm1
+        for T in (3, 2, 1):
+            f = torch.randn(1, 64, T * 2 - 1 if T == 3 else T, 4, 6, generator=g)
+            zq = torch.randn(1, 16, T, 2, 3, generator=g)
+            blob[f"spatial_norm_T{f.shape[2]}"] = (f, zq, sn(f, zq).clone())
+        up_t, up_s = vae.decoder.up_blocks[0].upsamplers[0], vae.decoder.up_blocks[2].upsamplers[0]
+        assert up_t.compress_time and not up_s.compress_time
+        for T in (3, 2, 1):
+            h = torch.randn(1, 64, T, 3, 4, generator=g)
+            blob[f"upsample_time_T{T}"] = (h, up_t(h).clone())
+        h = torch.randn(1, 64, 3, 3, 4, generator=g)
+        blob["upsample_space"] = (h, up_s(h).clone())
+        dn_t, dn_s = vae.encoder.down_blocks[0].downsamplers[0], vae.encoder.down_blocks[2].downsamplers[0]
+        assert dn_t.compress_time and not dn_s.compress_time
+        for T in (9, 8, 1):
+            h = torch.randn(1, 32, T, 6, 8, generator=g)
+            blob[f"downsample_time_T{T}"] = (h, dn_t(h).clone())
+        h = torch.randn(1, 64, 3, 6, 8, generator=g)
+        blob["downsample_space"] = (h, dn_s(h).clone())
+        vae._clear_fake_context_parallel_cache()
+    torch.save(blob, GOLDEN / "vae_tiny.pt")
+
+
 def main():
     ref_import.enable()
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    for fn in (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace):
+    fns = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny)
+    only = set(sys.argv[1:])
+    for fn in fns:
+        if only and fn.__name__ not in only:
+            continue
         print("generating", fn.__name__, flush=True)
         fn()
     for p in sorted(GOLDEN.iterdir()):
