@@ -189,6 +189,82 @@ int tg_cfg_dpm_step(const tg_dpm_step_args* args, void* stream);
 int tg_queue_shift_renoise(tg_bf16* queue, tg_bf16* x0_queue, int n_slots, int64_t chw, const tg_bf16* noise,
                            double sqrt_one_minus_beta, double sqrt_beta, void* stream);
 
+/* ===================================================================================================
+ * 3D causal VAE (CogVideoX AutoencoderKL) — activations are CHANNELS-LAST bf16 [T, H, W, C] inside the coder (batch 1;
+ * the pipeline enables slicing, longvgen infer_cogvideo_mp_fifo.py:181-182).  The host mirror converts at the boundary.
+ * ---------------------------------------------------------------------------------------------------
+ * K15/K17: implicit-GEMM convolution on tcgen05.  Replaces CogVideoXCausalConv3d.forward -> CogVideoXSafeConv3d
+ * (longvgen/models/autoencoder_kl_cogvideox.py:38-64,133-145: torch.cat of the conv cache + F.pad + cuDNN conv3d) and the
+ * per-frame Conv2d of diffusers CogVideoXUpsample3D / CogVideoXDownsample3D (called at :413,:606).
+ *   x : [T_in, H_in, W_in, Cin], Cin % 64 == 0 (zero-pad narrow inputs).  The first kt-1 frames of x ARE the causal
+ *       context (previous call's last frames = the reference's conv_cache, or copies of the first frame, :120-127);
+ *       output frame t reads input frames t .. t+kt-1.  H/W zero padding is implicit: pad_h0/pad_w0 rows/cols before
+ *       the first pixel, whatever the output extent needs after the last.
+ *   w : [Cout_pad, kt*kh*kw*Cin] bf16, tap-major (kt, kh, kw, c) — the nn.Conv3d weight [Cout, Cin, kt, kh, kw] permuted
+ *       once by the host; rows >= Cout are zero.  bias [Cout] or NULL.
+ *   y : layout 0 = channels-last [T_out, H_out, W_out, ldy]; layout 1 = channel planes, element (n, t, h, w) at
+ *       y[n*plane_stride + (t*H_out + h)*W_out + w] (lets conv_out write straight into a [C, T, H, W] video / moments
+ *       tensor).  residual (channels-last, row stride ld_res) is added when not NULL (ResnetBlock3D skip, :308). */
+typedef struct {
+    const tg_bf16* x;
+    int T_in, H_in, W_in, Cin;
+    const tg_bf16* w;
+    const tg_bf16* bias;
+    int Cout, Cout_pad;
+    int kt, kh, kw;
+    int stride_hw;
+    int pad_h0, pad_w0;
+    int T_out, H_out, W_out;
+    const tg_bf16* residual;
+    int64_t ld_res;
+    tg_bf16* y;
+    int64_t ldy;
+    int64_t plane_stride;
+    int layout;
+} tg_conv_args;
+int tg_vae_conv(const tg_conv_args* args, void* stream);
+
+/* K16: GroupNorm statistics and apply.  Replaces nn.GroupNorm (:241-242,700), CogVideoXSpatialNorm3D.forward (:175-188:
+ * F.interpolate of zq + two 1x1x1 convolutions + 3 elementwise ops) and the SiLU that always follows (:290,301,741,879).
+ *   tg_vae_group_stats: sums[0..G) += sum x, sums[G..2G) += sum x^2 per group over [pixels, C] (caller zeroes `sums`).
+ *   tg_vae_norm_act   : y = act( ((x - mean_g) * rstd_g * gamma + beta) [* zy[z(p)] + zb[z(p)]] ); zy / zb are
+ *       conv_y(zq) / conv_b(zq) evaluated at LATENT resolution [Tz, Hz, Wz, C] (a 1x1 conv commutes with nearest
+ *       up-sampling) and z(p) is F.interpolate's nearest source pixel, the first frame handled apart when T is odd (:176-184). */
+int tg_vae_group_stats(const tg_bf16* x, int64_t pixels, int C, int64_t ldx, int groups, double* sums, void* stream);
+typedef struct {
+    const tg_bf16* x;
+    int64_t ldx;
+    int T, H, W, C, groups;
+    float eps;
+    const double* sums;
+    const tg_bf16* gamma;
+    const tg_bf16* beta;
+    const tg_bf16* zy;
+    const tg_bf16* zb;
+    int Tz, Hz, Wz;
+    int silu;
+    tg_bf16* y;
+    int64_t ldy;
+} tg_norm_args;
+int tg_vae_norm_act(const tg_norm_args* args, void* stream);
+
+/* K17: nearest up-sampling of diffusers CogVideoXUpsample3D (mode 0: x2 in H,W per frame; mode 1 = compress_time: x2 in T too,
+ * the first frame only in H,W when T is odd and > 1; T == 1 stays 1) and the temporal average pooling of
+ * CogVideoXDownsample3D (frame pairs; first frame kept when T is odd).  Channels-last in and out. */
+int tg_vae_upsample(const tg_bf16* x, tg_bf16* y, int T, int H, int W, int C, int mode, void* stream);
+int tg_vae_avgpool_time(const tg_bf16* x, tg_bf16* y, int T, int64_t frame_elems, void* stream);
+
+/* [C, T, H, W] planes (plane stride in elements) -> channels-last [T*H*W, Cpad], zero pad channels. */
+int tg_vae_to_channels_last(const tg_bf16* x, tg_bf16* y, int C, int Cpad, int64_t pixels, int64_t plane_stride, void* stream);
+
+/* K19: z = (mean + exp(0.5 * clamp(logvar, -30, 20)) * eps) * scale; moments = [mean | logvar], n elements each.
+ * Replaces DiagonalGaussianDistribution.sample() * scaling_factor (longvgen/pipeline/pipeline_cogvideox_mp_fifo.py:585). */
+int tg_vae_posterior_sample(const tg_bf16* moments, const tg_bf16* eps, tg_bf16* z, int64_t n, float scale, void* stream);
+
+/* K18: blend_v (axis 0) / blend_h (axis 1) of tiled_encode / tiled_decode (:1190-1204), in place on b, bf16 op-by-op
+ * rounding like the reference.  a: [planes, Ha, Wa], b: [planes, Hb, Wb]; extent is clamped to the tile sizes. */
+int tg_vae_blend(const tg_bf16* a, tg_bf16* b, int64_t planes, int Ha, int Wa, int Hb, int Wb, int extent, int axis, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,6 +43,21 @@ class DpmStepArgs(C.Structure):
                 ("F", C.c_int), ("chw", C.c_int64), ("mode", C.c_int)]
 
 
+class ConvArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("T_in", C.c_int), ("H_in", C.c_int), ("W_in", C.c_int), ("Cin", C.c_int),
+                ("w", C.c_void_p), ("bias", C.c_void_p), ("Cout", C.c_int), ("Cout_pad", C.c_int),
+                ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride_hw", C.c_int), ("pad_h0", C.c_int), ("pad_w0", C.c_int),
+                ("T_out", C.c_int), ("H_out", C.c_int), ("W_out", C.c_int), ("residual", C.c_void_p), ("ld_res", C.c_int64),
+                ("y", C.c_void_p), ("ldy", C.c_int64), ("plane_stride", C.c_int64), ("layout", C.c_int)]
+
+
+class NormArgs(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("ldx", C.c_int64), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
+                ("groups", C.c_int), ("eps", C.c_float), ("sums", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("zy", C.c_void_p), ("zb", C.c_void_p), ("Tz", C.c_int), ("Hz", C.c_int), ("Wz", C.c_int), ("silu", C.c_int),
+                ("y", C.c_void_p), ("ldy", C.c_int64)]
+
+
 ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
 DPM_BASE_CHAIN, DPM_BF16_CHAIN = 0, 1
 
@@ -64,6 +79,14 @@ SYMBOLS = {
     "tg_unpatchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "tg_cfg_dpm_step": (C.c_int, [C.POINTER(DpmStepArgs), _VP]),
     "tg_queue_shift_renoise": (C.c_int, [_VP, _VP, _I, _I64, _VP, C.c_double, C.c_double, _VP]),
+    "tg_vae_conv": (C.c_int, [C.POINTER(ConvArgs), _VP]),
+    "tg_vae_group_stats": (C.c_int, [_VP, _I64, _I, _I64, _I, _VP, _VP]),
+    "tg_vae_norm_act": (C.c_int, [C.POINTER(NormArgs), _VP]),
+    "tg_vae_upsample": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "tg_vae_avgpool_time": (C.c_int, [_VP, _VP, _I, _I64, _VP]),
+    "tg_vae_to_channels_last": (C.c_int, [_VP, _VP, _I, _I, _I64, _I64, _VP]),
+    "tg_vae_posterior_sample": (C.c_int, [_VP, _VP, _VP, _I64, _F, _VP]),
+    "tg_vae_blend": (C.c_int, [_VP, _VP, _I64, _I, _I, _I, _I, _I, _I, _VP]),
 }
 
 _lib: Optional[C.CDLL] = None
@@ -305,3 +328,118 @@ def queue_shift_renoise(queue: torch.Tensor, x0_queue: Optional[torch.Tensor], n
         _check(lib.tg_queue_shift_renoise(_bf16_cuda(queue, "queue").data_ptr(), _ptr(x0_queue), n_slots, chw,
                                           _bf16_cuda(noise, "noise").data_ptr(), float(sqrt_one_minus_beta), float(sqrt_beta),
                                           _stream()), "tg_queue_shift_renoise")
+
+
+# ------------------------------------------------------------------------------------------------ VAE ops (channels-last)
+def vae_conv(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor], cout: int, kt: int, kh: int, kw: int,
+             t_out: int, h_out: int, w_out: int, *, stride: int = 1, pad_h0: int = 1, pad_w0: int = 1,
+             residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+             planes_out: Optional[torch.Tensor] = None, plane_stride: int = 0) -> torch.Tensor:
+    """x [T_in,H,W,Cin] (causal frames in front), w2d [Cout_pad, kt*kh*kw*Cin].  Returns channels-last [t_out,h_out,w_out,cout]
+    (or writes channel planes into `planes_out`, a view whose first element is (n=0, t=0, h=0, w=0))."""
+    lib = load()
+    a = ConvArgs()
+    T_in, H_in, W_in, Cin = x.shape
+    a.x, a.T_in, a.H_in, a.W_in, a.Cin = _bf16_cuda(x, "x").data_ptr(), T_in, H_in, W_in, Cin
+    a.w, a.bias, a.Cout, a.Cout_pad = _bf16_cuda(w2d, "w").data_ptr(), _ptr(bias), cout, w2d.shape[0]
+    a.kt, a.kh, a.kw, a.stride_hw, a.pad_h0, a.pad_w0 = kt, kh, kw, stride, pad_h0, pad_w0
+    a.T_out, a.H_out, a.W_out = t_out, h_out, w_out
+    if residual is not None:
+        a.residual, a.ld_res = _bf16_cuda(residual, "residual").data_ptr(), residual.shape[-1]
+    if planes_out is not None:
+        a.y, a.layout, a.plane_stride, a.ldy = planes_out.data_ptr(), 1, plane_stride, 0
+        ret = planes_out
+    else:
+        if out is None:
+            out = torch.empty(t_out, h_out, w_out, cout, device=x.device, dtype=torch.bfloat16)
+        a.y, a.layout, a.ldy = out.data_ptr(), 0, out.stride(2)
+        ret = out
+    with _Timed(f"vae_conv[{t_out}x{h_out}x{w_out},{Cin}->{cout},k{kt}{kh}{kw}s{stride}]", 1):
+        _check(lib.tg_vae_conv(C.byref(a), _stream()), "tg_vae_conv")
+    return ret
+
+
+def vae_group_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
+    lib = load()
+    Cc = x.shape[-1]
+    pixels = x.numel() // Cc
+    sums = torch.zeros(2 * groups, device=x.device, dtype=torch.float64)
+    with _Timed("vae_group_stats", 1):
+        _check(lib.tg_vae_group_stats(_bf16_cuda(x, "x").data_ptr(), pixels, Cc, Cc, groups, sums.data_ptr(), _stream()),
+               "tg_vae_group_stats")
+    return sums
+
+
+def vae_norm_act(x: torch.Tensor, sums: torch.Tensor, groups: int, eps: float, gamma: torch.Tensor, beta: torch.Tensor,
+                 out: torch.Tensor, zy: Optional[torch.Tensor] = None, zb: Optional[torch.Tensor] = None, silu: bool = True) -> None:
+    """x, out: channels-last [T,H,W,C]; zy/zb: [Tz,Hz,Wz,C] or None."""
+    lib = load()
+    a = NormArgs()
+    T, H, W, Cc = x.shape
+    a.x, a.ldx, a.T, a.H, a.W, a.C, a.groups, a.eps = _bf16_cuda(x, "x").data_ptr(), Cc, T, H, W, Cc, groups, float(eps)
+    a.sums, a.gamma, a.beta = sums.data_ptr(), _bf16_cuda(gamma, "gamma").data_ptr(), _bf16_cuda(beta, "beta").data_ptr()
+    if zy is not None:
+        a.zy, a.zb = _bf16_cuda(zy, "zy").data_ptr(), _bf16_cuda(zb, "zb").data_ptr()
+        a.Tz, a.Hz, a.Wz = zy.shape[0], zy.shape[1], zy.shape[2]
+    a.silu = int(silu)
+    if not (out.is_cuda and out.dtype == torch.bfloat16 and out.stride(-1) == 1):
+        raise TokensGenError("vae_norm_act: bad out")
+    a.y, a.ldy = out.data_ptr(), out.stride(2)
+    with _Timed("vae_norm_act", 1):
+        _check(lib.tg_vae_norm_act(C.byref(a), _stream()), "tg_vae_norm_act")
+
+
+def vae_upsample(x: torch.Tensor, compress_time: bool) -> torch.Tensor:
+    lib = load()
+    T, H, W, Cc = x.shape
+    T2 = ((2 * T - 1) if T % 2 == 1 else 2 * T) if (compress_time and T > 1) else T
+    y = torch.empty(T2, 2 * H, 2 * W, Cc, device=x.device, dtype=torch.bfloat16)
+    with _Timed("vae_upsample", 1):
+        _check(lib.tg_vae_upsample(_bf16_cuda(x, "x").data_ptr(), y.data_ptr(), T, H, W, Cc, int(compress_time), _stream()),
+               "tg_vae_upsample")
+    return y
+
+
+def vae_avgpool_time(x: torch.Tensor) -> torch.Tensor:
+    lib = load()
+    T = x.shape[0]
+    T2 = 1 + (T - 1) // 2 if T % 2 == 1 else T // 2
+    y = torch.empty((T2,) + tuple(x.shape[1:]), device=x.device, dtype=torch.bfloat16)
+    with _Timed("vae_avgpool_time", 1):
+        _check(lib.tg_vae_avgpool_time(_bf16_cuda(x, "x").data_ptr(), y.data_ptr(), T, x[0].numel(), _stream()),
+               "tg_vae_avgpool_time")
+    return y
+
+
+def vae_to_channels_last(x: torch.Tensor, cpad: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [C,T,H,W] (a view with contiguous [T,H,W] planes) -> [T,H,W,cpad]."""
+    lib = load()
+    Cc, T, H, W = x.shape
+    if not (x.is_cuda and x.dtype == torch.bfloat16 and x[0].is_contiguous()):
+        raise TokensGenError("vae_to_channels_last: expected CUDA bf16 [C,T,H,W] with contiguous planes")
+    if out is None:
+        out = torch.empty(T, H, W, cpad, device=x.device, dtype=torch.bfloat16)
+    with _Timed("vae_to_channels_last", 1):
+        _check(lib.tg_vae_to_channels_last(x.data_ptr(), _bf16_cuda(out, "out").data_ptr(), Cc, cpad, T * H * W, x.stride(0), _stream()),
+               "tg_vae_to_channels_last")
+    return out
+
+
+def vae_posterior_sample(moments: torch.Tensor, eps: torch.Tensor, scale: float) -> torch.Tensor:
+    """moments [2L, ...] planes (mean | logvar), eps [L, ...] -> z [L, ...] = sample * scale."""
+    lib = load()
+    z = torch.empty_like(eps)
+    with _Timed("vae_posterior_sample", 1):
+        _check(lib.tg_vae_posterior_sample(_bf16_cuda(moments, "moments").data_ptr(), _bf16_cuda(eps, "eps").data_ptr(), z.data_ptr(),
+                                           eps.numel(), float(scale), _stream()), "tg_vae_posterior_sample")
+    return z
+
+
+def vae_blend(a: torch.Tensor, b: torch.Tensor, extent: int, axis: int) -> None:
+    """a, b: [planes..., H, W] contiguous bf16; blends the leading `extent` rows (axis 0) / columns (axis 1) of b in place."""
+    lib = load()
+    Ha, Wa, Hb, Wb = a.shape[-2], a.shape[-1], b.shape[-2], b.shape[-1]
+    planes = b.numel() // (Hb * Wb)
+    with _Timed("vae_blend", 1):
+        _check(lib.tg_vae_blend(_bf16_cuda(a, "a").data_ptr(), _bf16_cuda(b, "b").data_ptr(), planes, Ha, Wa, Hb, Wb, extent, axis,
+                                _stream()), "tg_vae_blend")

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtokensgen_b200.so"
-SOURCES = ["common.cu", "gemm.cu", "attn.cu", "elementwise.cu"]
+SOURCES = ["common.cu", "gemm.cu", "attn.cu", "elementwise.cu", "conv.cu", "vae.cu"]
 HEADERS = ["common.h", "ptx.cuh", "../../include/tokensgen_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

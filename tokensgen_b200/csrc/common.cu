@@ -68,6 +68,30 @@ static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t
     return 0;
 }
 
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, const uint32_t* elem_strides) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return fail(999, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t d[5];
+    cuuint64_t st[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        d[i] = dims[i];
+        b[i] = box[i];
+        es[i] = elem_strides[i];
+        if (i + 1 < rank) st[i] = strides_bytes[i];
+    }
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), d, st, b, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(int(r), "cuTensorMapEncodeTiled failed (CUresult %d): base=%p rank=%d dims=(%llu,%llu,%llu,%llu) box=(%u,%u,%u,%u)",
+                    int(r), base, rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                    (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1],
+                    rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0);
+    return 0;
+}
+
 int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                  uint32_t box_inner, uint32_t box_rows) {
     cuuint64_t dims[3] = {inner, rows, 1};

@@ -27,4 +27,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ro
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
                  uint64_t row_stride_bytes, uint64_t batch_stride_bytes, uint32_t box_inner, uint32_t box_rows);
 
+// General form (rank <= 5): dims / box / element strides innermost first, strides_bytes for dims 1..rank-1.
+int make_tmap_nd(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                 const uint32_t* box, const uint32_t* elem_strides);
+
 }  // namespace tg

@@ -1,0 +1,320 @@
+// tcgen05 implicit-GEMM convolution for the 3D causal VAE: CogVideoXCausalConv3d (3x3x3), the per-frame
+// 3x3 convolutions of the up/down-samplers (stride 1 or 2) and 1x1x1 projections, on channels-last activations.
+//
+//   Y[t, h, w, n] = bias[n] + sum_{kt,kh,kw,c} X[t + kt, h*s + kh - ph, w*s + kw - pw, c] * W[n, (kt,kh,kw,c)]  (+ R[t,h,w,n])
+//
+// X already carries the kt-1 causal frames in front (conv cache or first-frame copies, written by the caller), so the time
+// axis needs no padding; the zero padding in H and W is the TMA's out-of-bounds fill — no im2col buffer, no F.pad, no cat.
+//
+// One persistent CTA per SM, 256 threads, same warp roles as gemm.cu:
+//   warp 0  TMA producer : per k-block (one tap x 64 input channels) ONE 4-D box {64 c, 32 w, 8 h, 1 t} of X (32 KB, the
+//                          256 output pixels of the tile shifted by the tap) + a {64 k, BLOCK_N} box of W
+//   warp 1  MMA issuer   : the 256-pixel tile is two 128-row UMMA operands (h rows 0-3 / 4-7): 2 x 4 tcgen05.mma per stage
+//   warp 2  TMEM alloc   : 2 accumulator buffers x 2 halves x BLOCK_N columns
+//   warps 4..7 epilogue  : thread = pixel; bias, optional residual, bf16 store channels-last (or fp32/bf16 planes)
+// Tile = 256 pixels x BLOCK_N channels: 48 KB of operands per 256x128x64 MACs, the same operand traffic per flop as the
+// 128x256 GEMM tile that runs at 96 % of the cuBLAS peak.
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tg {
+
+constexpr int CV_TW = 32, CV_TH = 8;           // output patch of one tile
+constexpr int CV_A_BYTES = CV_TW * CV_TH * 64 * 2;  // 32 KB
+
+struct ConvParams {
+    int T_out, H_out, W_out, Cout;
+    int kt, kh, kw, stride, pad_h, pad_w;
+    int c_chunks;             // Cin / 64
+    int h_tiles, w_tiles, n_tiles;
+    const __nv_bfloat16* bias;
+    const __nv_bfloat16* residual;  // channels-last [T_out, H_out, W_out, ld_res] or null
+    int64_t ld_res;
+    __nv_bfloat16* y;
+    int64_t ldy;              // layout 0: channel stride between pixels
+    int64_t plane_stride;     // layout 1: elements between channel planes; pixel (t,h,w) at (t*H_out + h)*W_out + w
+    int layout;               // 0 channels-last, 1 channel planes
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+    static constexpr int B_BYTES = BLOCK_N * 64 * 2;
+    static constexpr int STAGE_BYTES = CV_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BLOCK_N == 128) ? 4 : 5;
+    static constexpr int TMEM_COLS = 4 * BLOCK_N;  // 512 / 256
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst), "l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+
+__device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int tile, int& nt, int& wt, int& ht, int& t) {
+    nt = tile % p.n_tiles;  // channel tiles of one pixel tile run side by side: they share the activation boxes in L2
+    int r = tile / p.n_tiles;
+    wt = r % p.w_tiles;
+    r /= p.w_tiles;
+    ht = r % p.h_tiles;
+    t = r / p.h_tiles;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1)
+conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+            const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_tiles = p.T_out * p.h_tiles * p.w_tiles * p.n_tiles;
+    const int taps = p.kt * p.kh * p.kw;
+    const int k_blocks = taps * p.c_chunks;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int nt, wt, ht, t;
+                conv_tile_coords(p, tile, nt, wt, ht, t);
+                const int w_in0 = wt * CV_TW * p.stride - p.pad_w;
+                const int h_in0 = ht * CV_TH * p.stride - p.pad_h;
+                int kb = 0;
+                for (int it = 0; it < p.kt; ++it)
+                    for (int ih = 0; ih < p.kh; ++ih)
+                        for (int iw = 0; iw < p.kw; ++iw)
+                            for (int cc = 0; cc < p.c_chunks; ++cc, ++kb) {
+                                mbar_wait(empty_bar(stage), phase ^ 1u, 0x401);
+                                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                                mbar_arrive_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+                                tma_load_4d(sa, &tmap_x, full_bar(stage), cc * 64, w_in0 + iw, h_in0 + ih, t + it);
+                                tma_load_2d(sa + CV_A_BYTES, &tmap_w, full_bar(stage), kb * 64, nt * BLOCK_N);
+                                if (++stage == STAGES) {
+                                    stage = 0;
+                                    phase ^= 1u;
+                                }
+                            }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x402);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * 2 * BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x403);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + CV_A_BYTES;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = make_smem_desc_sw128(sa + half * (CV_A_BYTES / 2) + k * 32, 16, 1024);
+                            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                            umma_ss(d_tmem + uint32_t(half * BLOCK_N), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(tfull_bar(acc));
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int nt, wt, ht, t;
+            conv_tile_coords(p, tile, nt, wt, ht, t);
+            mbar_wait(tfull_bar(acc), acc_phase, 0x404);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int R = half * 128 + ew * 32 + lane;  // row of the 256-pixel tile = th * 32 + tw
+                const int h = ht * CV_TH + (R >> 5), w = wt * CV_TW + (R & 31);
+                const bool ok = h < p.H_out && w < p.W_out;
+                const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
+                const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + half * BLOCK_N);
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(t_row + c, r);
+                    tmem_wait_ld();
+                    const int n0 = nt * BLOCK_N + c;
+                    if (!ok || n0 >= p.Cout) continue;
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    if (p.layout == 0 && n0 + 32 <= p.Cout) {
+                        if (p.bias != nullptr) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 8) {
+                                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + i));
+                                v[i] += bf16_lo(bv.x); v[i + 1] += bf16_hi(bv.x); v[i + 2] += bf16_lo(bv.y); v[i + 3] += bf16_hi(bv.y);
+                                v[i + 4] += bf16_lo(bv.z); v[i + 5] += bf16_hi(bv.z); v[i + 6] += bf16_lo(bv.w); v[i + 7] += bf16_hi(bv.w);
+                            }
+                        }
+                        if (p.residual != nullptr) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + n0);
+                            uint4 rv[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) rv[i] = rp[i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                v[i * 8] += bf16_lo(rv[i].x); v[i * 8 + 1] += bf16_hi(rv[i].x);
+                                v[i * 8 + 2] += bf16_lo(rv[i].y); v[i * 8 + 3] += bf16_hi(rv[i].y);
+                                v[i * 8 + 4] += bf16_lo(rv[i].z); v[i * 8 + 5] += bf16_hi(rv[i].z);
+                                v[i * 8 + 6] += bf16_lo(rv[i].w); v[i * 8 + 7] += bf16_hi(rv[i].w);
+                            }
+                        }
+                        uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.ldy + n0);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            uint4 o;
+                            o.x = pack_bf16x2(v[i * 8], v[i * 8 + 1]); o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+                            o.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); o.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+                            yp[i] = o;
+                        }
+                    } else {
+                        // narrow outputs (conv_out: 3 image channels / 32 moment channels) and channel-plane layout
+                        for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
+                            float o = v[i] + (p.bias != nullptr ? __bfloat162float(p.bias[n0 + i]) : 0.f);
+                            if (p.residual != nullptr) o += __bfloat162float(p.residual[pix * p.ld_res + n0 + i]);
+                            if (p.layout == 0) p.y[pix * p.ldy + n0 + i] = __float2bfloat16_rn(o);
+                            else p.y[int64_t(n0 + i) * p.plane_stride + pix] = __float2bfloat16_rn(o);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int BLOCK_N>
+static int launch_conv(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    auto kern = conv_kernel<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "vae_conv: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = p.T_out * p.h_tiles * p.w_tiles * p.n_tiles;
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    kern<<<grid, 256, Cfg::SMEM_BYTES, stream>>>(tx, tw, p);
+    return check_launch("vae_conv");
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
+    if (a == nullptr || a->x == nullptr || a->w == nullptr || a->y == nullptr) return fail(-1, "vae_conv: null pointer");
+    if (a->Cin <= 0 || a->Cin % 64 != 0) return fail(-2, "vae_conv: Cin=%d must be a positive multiple of 64 (pad the channels)", a->Cin);
+    if (a->Cout <= 0 || a->Cout_pad < a->Cout || a->Cout_pad % 64 != 0)
+        return fail(-3, "vae_conv: Cout=%d Cout_pad=%d (Cout_pad: multiple of 64, >= Cout)", a->Cout, a->Cout_pad);
+    if (a->kt < 1 || a->kt > 3 || a->kh < 1 || a->kh > 3 || a->kw < 1 || a->kw > 3) return fail(-4, "vae_conv: kernel extents must be 1..3");
+    if (a->stride_hw != 1 && a->stride_hw != 2) return fail(-5, "vae_conv: stride_hw must be 1 or 2");
+    if (a->T_out <= 0 || a->H_out <= 0 || a->W_out <= 0 || a->T_in < a->T_out + a->kt - 1)
+        return fail(-6, "vae_conv: T_in=%d must hold T_out=%d + kt-1 causal frames", a->T_in, a->T_out);
+    if (a->layout != 0 && a->layout != 1) return fail(-7, "vae_conv: layout must be 0 (channels-last) or 1 (planes)");
+    if (a->layout == 0 && (a->ldy < a->Cout || (a->Cout % 32 == 0 && a->ldy % 8 != 0))) return fail(-8, "vae_conv: bad ldy=%lld", (long long)a->ldy);
+    if (a->residual != nullptr && a->ld_res < a->Cout) return fail(-9, "vae_conv: bad ld_res");
+    if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w) | reinterpret_cast<uintptr_t>(a->y)) & 15)
+        return fail(-10, "vae_conv: pointers must be 16-byte aligned");
+    const int s = a->stride_hw;
+    CUtensorMap tx, tw;
+    const uint64_t dims[4] = {uint64_t(a->Cin), uint64_t(a->W_in), uint64_t(a->H_in), uint64_t(a->T_in)};
+    const uint64_t strides[3] = {uint64_t(a->Cin) * 2, uint64_t(a->W_in) * a->Cin * 2, uint64_t(a->H_in) * a->W_in * a->Cin * 2};
+    const uint32_t box[4] = {64, uint32_t(CV_TW * s), uint32_t(CV_TH * s), 1};
+    const uint32_t estr[4] = {1, uint32_t(s), uint32_t(s), 1};
+    int rc = make_tmap_nd(&tx, a->x, 4, dims, strides, box, estr);
+    if (rc) return rc;
+    const int K = a->kt * a->kh * a->kw * a->Cin;
+    const int bn = (a->Cout_pad % 128 == 0) ? 128 : 64;
+    rc = make_tmap_2d(&tw, a->w, uint64_t(K), uint64_t(a->Cout_pad), uint64_t(K) * 2, 64, uint32_t(bn));
+    if (rc) return rc;
+    ConvParams p{};
+    p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out; p.Cout = a->Cout;
+    p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.stride = s; p.pad_h = a->pad_h0; p.pad_w = a->pad_w0;
+    p.c_chunks = a->Cin / 64;
+    p.h_tiles = (a->H_out + CV_TH - 1) / CV_TH;
+    p.w_tiles = (a->W_out + CV_TW - 1) / CV_TW;
+    p.n_tiles = a->Cout_pad / bn;
+    p.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
+    p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+    p.ld_res = a->ld_res;
+    p.y = reinterpret_cast<__nv_bfloat16*>(a->y);
+    p.ldy = a->ldy;
+    p.plane_stride = a->plane_stride;
+    p.layout = a->layout;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return bn == 128 ? launch_conv<128>(tx, tw, p, st) : launch_conv<64>(tx, tw, p, st);
+}

@@ -1,0 +1,327 @@
+// HBM-bound kernels of the 3D causal VAE on channels-last activations [T, H, W, C]: GroupNorm statistics,
+// normalise + spatial conditioning + SiLU in one pass, nearest up-sampling, temporal average pooling, layout changes,
+// posterior sampling, tile blending.  All are 16-byte-vector, coalesced, grid-stride kernels; no tensor cores (none of this
+// is a contraction: the two 16->C 1x1 convolutions of SpatialNorm run once at LATENT resolution through the GEMM kernel and
+// are gathered here, which is exact because a 1x1 convolution commutes with nearest-neighbour up-sampling).
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace tg {
+
+__device__ __forceinline__ void unpack8v(const uint4& v, float (&f)[8]) {
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+    f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8v(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    return v;
+}
+__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+static inline int grid_for(int64_t work_items, int threads = 256) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = int64_t(sm_count()) * 16;
+    return int(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------ K16a statistics
+// sums[g] += sum x, sums[G + g] += sum x^2 over every pixel and the C/G channels of group g.  A thread keeps one 8-channel
+// vector position for its whole life (fp32 partials), the block folds them into shared memory, one double atomic per
+// group per block reaches HBM.
+__global__ void __launch_bounds__(256)
+group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t pixels, int C, int64_t ldx, int groups, double* __restrict__ sums) {
+    __shared__ float sh[2 * 64];
+    const int V = C / 8;             // vectors per pixel
+    const int ppb = 256 / V;         // pixels per block iteration (V <= 256 checked by the host)
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    for (int i = threadIdx.x; i < 2 * groups; i += 256) sh[i] = 0.f;
+    __syncthreads();
+    float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (pl < ppb) {
+        for (int64_t p = int64_t(blockIdx.x) * ppb + pl; p < pixels; p += int64_t(gridDim.x) * ppb) {
+            float f[8];
+            unpack8v(__ldg(reinterpret_cast<const uint4*>(x + p * ldx) + v), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s[j] += f[j];
+                q[j] = fmaf(f[j], f[j], q[j]);
+            }
+        }
+    }
+    const int cg = C / groups;
+    if (cg >= 8) {
+        float ss = 0.f, qq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ss += s[j]; qq += q[j]; }
+        const int g = (v * 8) / cg;
+        atomicAdd(&sh[g], ss);
+        atomicAdd(&sh[groups + g], qq);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (v * 8 + j) / cg;
+            atomicAdd(&sh[g], s[j]);
+            atomicAdd(&sh[groups + g], q[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * groups; i += 256) atomicAdd(&sums[i], double(sh[i]));
+}
+
+// ------------------------------------------------------------------------------------------------ K16b apply
+struct NormParams {
+    tg_norm_args a;
+};
+
+__global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ tg_norm_args a) {
+    __shared__ float sh_mean[64], sh_rstd[64];
+    const int C = a.C, V = C / 8, cg = C / a.groups;
+    const int64_t pixels = int64_t(a.T) * a.H * a.W;
+    const double cnt = double(pixels) * cg;
+    for (int g = threadIdx.x; g < a.groups; g += 256) {
+        const double m = a.sums[g] / cnt;
+        double var = a.sums[a.groups + g] / cnt - m * m;
+        if (var < 0) var = 0;
+        sh_mean[g] = float(m);
+        sh_rstd[g] = float(1.0 / sqrt(var + double(a.eps)));
+    }
+    __syncthreads();
+    const int ppb = 256 / V;
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    if (pl >= ppb) return;
+    // per-thread constants: this thread always handles channels [8v, 8v+8)
+    float sc[8], of[8];
+    {
+        float gm[8], bt[8];
+        unpack8v(__ldg(reinterpret_cast<const uint4*>(a.gamma) + v), gm);
+        unpack8v(__ldg(reinterpret_cast<const uint4*>(a.beta) + v), bt);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (v * 8 + j) / cg;
+            sc[j] = sh_rstd[g] * gm[j];
+            of[j] = fmaf(-sh_mean[g], sc[j], bt[j]);
+        }
+    }
+    const bool spatial = a.zy != nullptr;
+    const int HW = a.H * a.W;
+    const bool odd_t = a.T > 1 && (a.T & 1);
+    for (int64_t p = int64_t(blockIdx.x) * ppb + pl; p < pixels; p += int64_t(gridDim.x) * ppb) {
+        float f[8];
+        unpack8v(__ldg(reinterpret_cast<const uint4*>(a.x + p * a.ldx) + v), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], of[j]);
+        if (spatial) {
+            const int t = int(p / HW);
+            const int r = int(p - int64_t(t) * HW);
+            const int h = r / a.W, w = r - h * a.W;
+            // nearest source index of F.interpolate; first frame apart when T is odd and > 1 (autoencoder_kl_cogvideox.py:176-186)
+            const int tz = odd_t ? (t == 0 ? 0 : 1 + ((t - 1) * (a.Tz - 1)) / (a.T - 1)) : (t * a.Tz) / a.T;
+            const int hz = (h * a.Hz) / a.H, wz = (w * a.Wz) / a.W;
+            const int64_t zi = (int64_t(tz) * a.Hz + hz) * a.Wz + wz;
+            float y[8], b[8];
+            unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zy + zi * C) + v), y);
+            unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zb + zi * C) + v), b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], y[j], b[j]);
+        }
+        if (a.silu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+        }
+        reinterpret_cast<uint4*>(a.y + p * a.ldy)[v] = pack8v(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K17 resampling
+// mode 0: nearest x2 in H, W per frame.  mode 1 (compress_time): also x2 in T; when T is odd and > 1 the first frame is
+// only up-sampled in H, W (T -> 2T-1); T == 1 stays one frame.  (diffusers CogVideoXUpsample3D)
+__global__ void __launch_bounds__(256)
+upsample_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int H, int W, int V, int T2, int mode) {
+    const int H2 = 2 * H, W2 = 2 * W;
+    const int64_t total = int64_t(T2) * H2 * W2 * V;
+    const bool odd = mode == 1 && T > 1 && (T & 1);
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int v = int(i % V);
+        int64_t r = i / V;
+        const int w2 = int(r % W2);
+        r /= W2;
+        const int h2 = int(r % H2);
+        const int t2 = int(r / H2);
+        int t = t2;
+        if (mode == 1 && T > 1) t = odd ? (t2 == 0 ? 0 : 1 + (t2 - 1) / 2) : t2 / 2;
+        y[i] = __ldg(x + ((int64_t(t) * H + (h2 >> 1)) * W + (w2 >> 1)) * V + v);
+    }
+}
+
+// avg_pool1d(kernel 2, stride 2) over frame pairs; T odd keeps the first frame (diffusers CogVideoXDownsample3D).
+__global__ void __launch_bounds__(256)
+avgpool_time_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int64_t frame_vecs, int T2) {
+    const int64_t total = int64_t(T2) * frame_vecs;
+    const int odd = T & 1;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int t2 = int(i / frame_vecs);
+        const int64_t r = i - int64_t(t2) * frame_vecs;
+        if (odd && t2 == 0) {
+            y[i] = __ldg(x + r);
+            continue;
+        }
+        const int t = odd ? 1 + 2 * (t2 - 1) : 2 * t2;
+        float a[8], b[8];
+        unpack8v(__ldg(x + int64_t(t) * frame_vecs + r), a);
+        unpack8v(__ldg(x + int64_t(t + 1) * frame_vecs + r), b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = (a[j] + b[j]) * 0.5f;
+        y[i] = pack8v(a);
+    }
+}
+
+// [C, T, H*W] planes -> channels-last [T*H*W, Cpad], zero in the pad channels (Cpad % 8 == 0).
+__global__ void __launch_bounds__(256)
+to_channels_last_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int C, int Cpad, int64_t pixels,
+                        int64_t plane_stride) {
+    const int V = Cpad / 8;
+    const int64_t total = pixels * V;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int v = int(i % V);
+        const int64_t p = i / V;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = v * 8 + j;
+            f[j] = c < C ? __bfloat162float(x[int64_t(c) * plane_stride + p]) : 0.f;
+        }
+        reinterpret_cast<uint4*>(y)[i] = pack8v(f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K19
+__global__ void __launch_bounds__(256)
+posterior_sample_kernel(const __nv_bfloat16* __restrict__ moments, const __nv_bfloat16* __restrict__ eps,
+                        __nv_bfloat16* __restrict__ z, int64_t n, float scale) {
+    // moments: [2, n] = (mean, logvar) flattened; diffusers DiagonalGaussianDistribution.sample then * scaling_factor
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+        const float mean = __bfloat162float(moments[i]);
+        float lv = __bfloat162float(moments[n + i]);
+        lv = fminf(fmaxf(lv, -30.f), 20.f);
+        const float smp = rbf(fmaf(rbf(expf(0.5f * lv)), __bfloat162float(eps[i]), mean));
+        z[i] = __float2bfloat16_rn(smp * scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K18
+// b[.., k, ..] = a[.., -extent + k, ..] * (1 - k/extent) + b[.., k, ..] * (k/extent) along H (axis 0) or W (axis 1),
+// in place on b, every op rounded to bf16 like the reference's bf16 tensor expression (autoencoder_kl_cogvideox.py:1190-1204).
+// a: [planes, Ha, Wa], b: [planes, Hb, Wb] (planes = C*T).
+__global__ void __launch_bounds__(256)
+blend_kernel(const __nv_bfloat16* __restrict__ a, __nv_bfloat16* __restrict__ b, int64_t planes, int Ha, int Wa, int Hb, int Wb,
+             int extent, int axis) {
+    const int64_t line = axis == 0 ? Wb : Hb;  // elements per blended row/column
+    const int64_t total = planes * extent * line;
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        int64_t r = i;
+        const int u = int(r % line);
+        r /= line;
+        const int k = int(r % extent);
+        const int64_t pl = r / extent;
+        const float wb = float(double(k) / double(extent)), wa = float(1.0 - double(k) / double(extent));
+        int64_t ia, ib;
+        if (axis == 0) {
+            ia = (pl * Ha + (Ha - extent + k)) * Wa + u;
+            ib = (pl * Hb + k) * Wb + u;
+        } else {
+            ia = (pl * Ha + u) * Wa + (Wa - extent + k);
+            ib = (pl * Hb + u) * Wb + k;
+        }
+        const float va = __bfloat162float(a[ia]), vb = __bfloat162float(b[ib]);
+        b[ib] = __float2bfloat16_rn(rbf(va * wa) + rbf(vb * wb));
+    }
+}
+
+}  // namespace tg
+
+using namespace tg;
+
+extern "C" int tg_vae_group_stats(const tg_bf16* x, int64_t pixels, int C, int64_t ldx, int groups, double* sums, void* stream) {
+    if (!x || !sums) return fail(-1, "vae_group_stats: null pointer");
+    if (pixels <= 0 || C <= 0 || C % 8 != 0 || C > 2048 || groups <= 0 || groups > 64 || C % groups != 0 || ldx < C || ldx % 8 != 0)
+        return fail(-2, "vae_group_stats: pixels=%lld C=%d groups=%d ldx=%lld", (long long)pixels, C, groups, (long long)ldx);
+    const int ppb = 256 / (C / 8);
+    if (ppb < 1) return fail(-3, "vae_group_stats: C too large");
+    int64_t blocks = (pixels + ppb - 1) / ppb;
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    group_stats_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), pixels, C, ldx, groups, sums);
+    return check_launch("vae_group_stats");
+}
+
+extern "C" int tg_vae_norm_act(const tg_norm_args* a, void* stream) {
+    if (!a || !a->x || !a->y || !a->sums || !a->gamma || !a->beta) return fail(-1, "vae_norm_act: null pointer");
+    if (a->T <= 0 || a->H <= 0 || a->W <= 0 || a->C <= 0 || a->C % 8 != 0 || a->C > 2048 || a->groups <= 0 || a->groups > 64 ||
+        a->C % a->groups != 0 || a->ldx < a->C || a->ldy < a->C || a->ldx % 8 != 0 || a->ldy % 8 != 0)
+        return fail(-2, "vae_norm_act: bad shape T=%d H=%d W=%d C=%d groups=%d", a->T, a->H, a->W, a->C, a->groups);
+    if ((a->zy == nullptr) != (a->zb == nullptr)) return fail(-3, "vae_norm_act: zy and zb come together");
+    if (a->zy != nullptr && (a->Tz <= 0 || a->Hz <= 0 || a->Wz <= 0 || a->Tz > a->T)) return fail(-4, "vae_norm_act: bad latent grid");
+    const int ppb = 256 / (a->C / 8);
+    const int64_t pixels = int64_t(a->T) * a->H * a->W;
+    int64_t blocks = (pixels + ppb - 1) / ppb;
+    const int64_t cap = int64_t(sm_count()) * 8;
+    if (blocks > cap) blocks = cap;
+    norm_act_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
+    return check_launch("vae_norm_act");
+}
+
+extern "C" int tg_vae_upsample(const tg_bf16* x, tg_bf16* y, int T, int H, int W, int C, int mode, void* stream) {
+    if (!x || !y) return fail(-1, "vae_upsample: null pointer");
+    if (T <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0 || (mode != 0 && mode != 1)) return fail(-2, "vae_upsample: bad arguments");
+    const int T2 = (mode == 1 && T > 1) ? ((T & 1) ? 2 * T - 1 : 2 * T) : T;
+    const int64_t total = int64_t(T2) * 4 * H * W * (C / 8);
+    upsample_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), T, H, W, C / 8, T2, mode);
+    return check_launch("vae_upsample");
+}
+
+extern "C" int tg_vae_avgpool_time(const tg_bf16* x, tg_bf16* y, int T, int64_t frame_elems, void* stream) {
+    if (!x || !y) return fail(-1, "vae_avgpool_time: null pointer");
+    if (T <= 0 || frame_elems <= 0 || frame_elems % 8 != 0) return fail(-2, "vae_avgpool_time: bad arguments");
+    const int T2 = (T & 1) ? 1 + (T - 1) / 2 : T / 2;
+    const int64_t total = int64_t(T2) * (frame_elems / 8);
+    avgpool_time_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(y), T, frame_elems / 8, T2);
+    return check_launch("vae_avgpool_time");
+}
+
+extern "C" int tg_vae_to_channels_last(const tg_bf16* x, tg_bf16* y, int C, int Cpad, int64_t pixels, int64_t plane_stride, void* stream) {
+    if (!x || !y) return fail(-1, "vae_to_channels_last: null pointer");
+    if (C <= 0 || Cpad < C || Cpad % 8 != 0 || pixels <= 0 || plane_stride < pixels) return fail(-2, "vae_to_channels_last: bad arguments");
+    to_channels_last_kernel<<<grid_for(pixels * (Cpad / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<__nv_bfloat16*>(y), C, Cpad, pixels, plane_stride);
+    return check_launch("vae_to_channels_last");
+}
+
+extern "C" int tg_vae_posterior_sample(const tg_bf16* moments, const tg_bf16* eps, tg_bf16* z, int64_t n, float scale, void* stream) {
+    if (!moments || !eps || !z) return fail(-1, "vae_posterior_sample: null pointer");
+    if (n <= 0) return fail(-2, "vae_posterior_sample: n=%lld", (long long)n);
+    posterior_sample_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(moments), reinterpret_cast<const __nv_bfloat16*>(eps),
+        reinterpret_cast<__nv_bfloat16*>(z), n, scale);
+    return check_launch("vae_posterior_sample");
+}
+
+extern "C" int tg_vae_blend(const tg_bf16* a, tg_bf16* b, int64_t planes, int Ha, int Wa, int Hb, int Wb, int extent, int axis, void* stream) {
+    if (!a || !b) return fail(-1, "vae_blend: null pointer");
+    if (planes <= 0 || Ha <= 0 || Wa <= 0 || Hb <= 0 || Wb <= 0 || (axis != 0 && axis != 1)) return fail(-2, "vae_blend: bad arguments");
+    // extent is clamped like the reference: min(a.shape, b.shape, blend_extent)
+    const int lim = axis == 0 ? (Ha < Hb ? Ha : Hb) : (Wa < Wb ? Wa : Wb);
+    if (extent > lim) extent = lim;
+    if (extent <= 0) return 0;
+    if (axis == 0 ? (Wa != Wb) : (Ha != Hb)) return fail(-3, "vae_blend: tiles must agree on the non-blended axis");
+    const int64_t total = planes * extent * (axis == 0 ? Wb : Hb);
+    blend_kernel<<<grid_for(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a), reinterpret_cast<__nv_bfloat16*>(b), planes, Ha, Wa, Hb, Wb, extent, axis);
+    return check_launch("vae_blend");
+}
