@@ -287,8 +287,12 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     if (a->layout != 0 && a->layout != 1) return fail(-7, "vae_conv: layout must be 0 (channels-last) or 1 (planes)");
     if (a->layout == 0 && (a->ldy < a->Cout || (a->Cout % 32 == 0 && a->ldy % 8 != 0))) return fail(-8, "vae_conv: bad ldy=%lld", (long long)a->ldy);
     if (a->residual != nullptr && a->ld_res < a->Cout) return fail(-9, "vae_conv: bad ld_res");
-    if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w) | reinterpret_cast<uintptr_t>(a->y)) & 15)
-        return fail(-10, "vae_conv: pointers must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(a->x) | reinterpret_cast<uintptr_t>(a->w)) & 15)
+        return fail(-10, "vae_conv: x and w must be 16-byte aligned");
+    if (a->layout == 0 && a->Cout % 32 == 0 && (reinterpret_cast<uintptr_t>(a->y) & 15))
+        return fail(-10, "vae_conv: y must be 16-byte aligned");
+    if (a->residual != nullptr && a->Cout % 32 == 0 && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || a->ld_res % 8 != 0))
+        return fail(-10, "vae_conv: residual must be 16-byte aligned with ld_res %% 8 == 0");
     const int s = a->stride_hw;
     CUtensorMap tx, tw;
     const uint64_t dims[4] = {uint64_t(a->Cin), uint64_t(a->W_in), uint64_t(a->H_in), uint64_t(a->T_in)};
