@@ -12,7 +12,8 @@ from typing import Optional, Sequence
 import torch
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libtokensgen_b200.so"
+import os as _os
+LIB_PATH = Path(_os.environ.get("TG_LIB_PATH") or (_PKG / "libtokensgen_b200.so"))  # TG_LIB_PATH: developer A/B builds
 
 
 class TokensGenError(RuntimeError):

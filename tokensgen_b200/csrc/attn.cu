@@ -684,12 +684,376 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
-static int g_attn_impl = 2;  // 1 = v1 (8 softmax warps), 2 = v2
+
+// =====================================================================================================================
+// v3: v2's tiling and warp roles, with the three things the v2 timeline (tools/attn_trace.py) showed were missing:
+//   * the two query tiles TAKE TURNS on the MUFU pipe, per SM sub-partition: the two warps of tile t on sub-partition q
+//     start their exponentials only after the two warps of tile 1-t on the same sub-partition have issued theirs
+//     (mbarrier hand-off `turn(t, q)`, 2 arrivals).  Left alone, both tiles drift into the same phase: they share the
+//     pipe for ~2000 cycles and then both sit in their latency-bound phase (S load, row max, exchange, P store) with the
+//     pipe idle.  Alternating, one tile's latency phase hides under the other tile's exponentials.
+//   * P is packed and stored to TMEM in 16-column chunks inside the exponential loop, so only the last chunk's store is
+//     left on the tail of the block.
+//   * a lean instruction stream: hinted mbarrier waits (a blocked warp sleeps instead of spinning through its
+//     sub-partition's issue slots), 112 registers for the softmax warps (no address rematerialisation), and the optional
+//     FMA-pipe exponentials in packed f32x2 form with the range reduction folded into the score scaling:
+//     the reference max is kept as an INTEGER number of log2 units (mc = ceil(max * c)), so
+//         t = fma.rm(s, c, 1.5*2^23 - mc)   has floor(s*c - mc) in its low mantissa bits, exactly,
+//         f = fma.rn(s, c, -(t - (1.5*2^23 - mc)))  is the fractional part,
+//     followed by a degree-3 polynomial and one shift-add into the exponent field (max rel. error 8.8e-5).
+#ifndef A3_PRODUCER_REGS
+#define A3_PRODUCER_REGS 40  // (96 - producer) * 128 registers are all the softmax warps can gain: 40 -> 104, 32 -> 112
+#define A3_SOFTMAX_REGS 104
+#endif
+#ifndef A3_TURN_AT
+#define A3_TURN_AT 4  // 16-column chunks of exponentials issued before the MUFU pipe is handed to the other tile
+#endif
+constexpr int A3_THREADS = 640;
+constexpr int A3_XCH_BYTES = 2 * 2 * 2 * 128 * 4;
+constexpr int A3_SMEM_BYTES = 2 * AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + A3_XCH_BYTES + 384 + 1024;
+
+template <int EMU8>
+__device__ __forceinline__ constexpr bool a3_emulated(int pair) {  // EMU8 of every 8 pairs, evenly spread
+    return ((pair + 1) * EMU8) / 8 != (pair * EMU8) / 8;
+}
+
+template <int EMU8, bool ALT>
+__global__ void __launch_bounds__(A3_THREADS, 1)
+attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t q_smem = smem_base;
+    const uint32_t kv_smem = smem_base + 2 * AT_TILE_BYTES;
+    const uint32_t xch_smem = kv_smem + AT_STAGES * 2 * AT_TILE_BYTES;
+    const uint32_t bar_base = xch_smem + A3_XCH_BYTES;
+    const uint32_t q_full = bar_base;
+    auto kv_full = [&](int s) { return bar_base + 8u * (1 + s); };
+    auto kv_empty = [&](int s) { return bar_base + 8u * (1 + AT_STAGES + s); };
+    auto s_full = [&](int t) { return bar_base + 8u * (1 + 2 * AT_STAGES + t); };
+    auto p_full = [&](int t) { return bar_base + 8u * (3 + 2 * AT_STAGES + t); };
+    auto o_done = [&](int t) { return bar_base + 8u * (5 + 2 * AT_STAGES + t); };
+    auto s_free = [&](int t) { return bar_base + 8u * (7 + 2 * AT_STAGES + t); };
+    auto turn = [&](int t, int q) { return bar_base + 8u * (9 + 2 * AT_STAGES + t * 4 + q); };
+    const uint32_t tmem_slot = bar_base + 8u * (17 + 2 * AT_STAGES);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    float* xch = reinterpret_cast<float*>(smem_raw + (xch_smem - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int bh = blockIdx.y;
+    const int q0 = blockIdx.x * (2 * AT_BLOCK_Q);
+    const int n_blocks = (p.kv_rows + AT_BLOCK_KV - 1) / AT_BLOCK_KV;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_k);
+        tma_prefetch_desc(&tmap_v);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < AT_STAGES; ++s) {
+            mbar_init(kv_full(s), 1);
+            mbar_init(kv_empty(s), 2);
+        }
+        for (int t = 0; t < 2; ++t) {
+            mbar_init(s_full(t), 1);
+            mbar_init(p_full(t), 8);
+            mbar_init(s_free(t), 8);
+            mbar_init(o_done(t), 1);
+            for (int q = 0; q < 4; ++q) mbar_init(turn(t, q), 2);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    auto s_col = [&](int t) { return uint32_t(t * 128); };
+    auto o_col = [&](int t) { return uint32_t(256 + t * 64); };
+    auto p_col = [&](int t) { return uint32_t(384 + t * 64); };
+
+    if (warp < 4) {
+        reg_dealloc<A3_PRODUCER_REGS>();
+        if (warp == 0) {
+            // -------------------------------------------------------------- TMA producer
+            if (lane == 0) {
+                mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+                tma_load_3d(q_smem, &tmap_q, q_full, 0, q0, bh);
+                tma_load_3d(q_smem + AT_TILE_BYTES, &tmap_q, q_full, 0, q0 + AT_BLOCK_Q, bh);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_blocks; ++j) {
+                    mbar_wait_fast(kv_empty(stage), phase ^ 1u);
+                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+                    mbar_arrive_expect_tx(kv_full(stage), 2 * AT_TILE_BYTES);
+                    tma_load_3d(ks, &tmap_k, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                    tma_load_3d(ks + AT_TILE_BYTES, &tmap_v, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                    if (++stage == AT_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        } else if (warp == 1 || warp == 3) {
+            // -------------------------------------------------------------- MMA issuer of tile t
+            if (lane == 0) {
+                const int t = warp >> 1;
+                constexpr uint32_t idesc_qk = make_idesc_bf16(128, 128, false, false);
+                constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, false, true);  // V is MN-major
+                const uint32_t qs = q_smem + t * AT_TILE_BYTES;
+                const uint32_t s_t = tmem_base + s_col(t), o_t = tmem_base + o_col(t), p_t = tmem_base + p_col(t);
+                const uint32_t bar_sfull = s_full(t), bar_sfree = s_free(t), bar_pfull = p_full(t), bar_odone = o_done(t);
+                auto issue_qk = [&](int stage) {
+                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < AT_D / 16; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(qs + k * 32, 16, 1024);
+                        const uint64_t db = make_smem_desc_sw128(ks + k * 32, 16, 1024);
+                        umma_ss(s_t, da, db, idesc_qk, k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(bar_sfull);
+                };
+                auto issue_pv = [&](int stage, bool first) {
+                    const uint32_t vs = kv_smem + stage * 2 * AT_TILE_BYTES + AT_TILE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < AT_BLOCK_KV / 16; ++k) {
+                        const uint64_t db = make_smem_desc_sw128(vs + k * 2048, 1024, 1024);
+                        umma_ts(o_t, p_t + uint32_t(k * 8), db, idesc_pv, (first && k == 0) ? 0u : 1u);
+                    }
+                };
+                mbar_wait_fast(q_full, 0);
+                mbar_wait_fast(kv_full(0), 0);
+                tc_fence_after();
+                issue_qk(0);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int j = 0; j < n_blocks; ++j) {
+                    int nstage = stage + 1;
+                    uint32_t nphase = phase;
+                    if (nstage == AT_STAGES) {
+                        nstage = 0;
+                        nphase ^= 1u;
+                    }
+                    if (j + 1 < n_blocks) {
+                        mbar_wait_fast(bar_sfree, uint32_t(j & 1));  // S_t(j) is in registers: overwrite it
+                        mbar_wait_fast(kv_full(nstage), nphase);
+                        tc_fence_after();
+                        issue_qk(nstage);
+                    }
+                    mbar_wait_fast(bar_pfull, uint32_t(j & 1));
+                    tc_fence_after();
+                    issue_pv(stage, j == 0);
+                    umma_commit(kv_empty(stage));
+                    umma_commit(bar_odone);
+                    stage = nstage;
+                    phase = nphase;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ softmax warps
+        reg_alloc<A3_SOFTMAX_REGS>();
+        const int sw = warp - 4;
+        const int t = sw >> 3;           // tile
+        const int half = (sw >> 2) & 1;  // which 64 of the block's 128 score columns
+        const int wq = warp & 3;         // TMEM lane quarter == SM sub-partition
+        const int row_in_tile = wq * 32 + lane;
+        const int q_row = q0 + t * AT_BLOCK_Q + row_in_tile;
+        const uint32_t lane_base = tmem_base + (uint32_t(wq * 32) << 16);
+        const uint32_t s_addr = lane_base + s_col(t) + uint32_t(half * 64);
+        const uint32_t o_addr = lane_base + o_col(t) + uint32_t(half * 32);
+        const uint32_t p_addr = lane_base + p_col(t) + uint32_t(half * 32);
+        const uint32_t bar_sfull = s_full(t), bar_sfree = s_free(t), bar_pfull = p_full(t), bar_odone = o_done(t);
+        const uint32_t bar_my_turn = turn(t, wq), bar_other_turn = turn(1 - t, wq);
+        const int pair_bar = 1 + t * 4 + wq;
+        float* const xslot_mine = xch + (t * 2 + half) * 128 + row_in_tile;        // + parity * 512
+        float* const xslot_other = xch + (t * 2 + (half ^ 1)) * 128 + row_in_tile;
+        const float c = p.scale_log2;
+        const float inv_c = 1.0f / c;
+        const uint64_t c2 = pack_f32x2(c, c);
+        constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
+        float mc = 0.f;    // reference max in log2 units, integer-valued
+        float smin = 0.f;  // scores below this are clamped before an emulated exponential (2^-126)
+        float l = 0.f;
+
+        for (int j = 0; j < n_blocks; ++j) {
+            mbar_wait_fast(bar_sfull, uint32_t(j & 1));
+            tc_fence_after();
+            uint32_t r[64];
+            {
+                uint32_t (&ra)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[0]);
+                uint32_t (&rb)[32] = *reinterpret_cast<uint32_t (*)[32]>(&r[32]);
+                tmem_ld32(s_addr, ra);
+                tmem_ld32(s_addr + 32, rb);
+                tmem_wait_ld();
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_sfree);
+            const int valid = p.kv_rows - j * AT_BLOCK_KV - half * 64;
+            if (valid < 64) {
+#pragma unroll
+                for (int i = 0; i < 64; ++i)
+                    if (i >= valid) r[i] = 0xff800000u;  // -inf
+            }
+            float pm[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pm[k] = fmaxf(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
+#pragma unroll
+            for (int i = 8; i < 64; i += 8)
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    pm[k] = fmaxf(pm[k], fmaxf(__uint_as_float(r[i + 2 * k]), __uint_as_float(r[i + 2 * k + 1])));
+            float mx = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
+            {
+                const int par = (j & 1) * 512;
+                xslot_mine[par] = mx;
+                named_bar_sync(pair_bar, 64);
+                mx = fmaxf(mx, xslot_other[par]);
+            }
+            bool waited = false;
+            if (j == 0) {
+                mc = ceilf(mx * c);
+                smin = (mc - 126.0f) * inv_c;
+            } else {
+                const bool need = fmaf(mx, c, -mc) > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {
+                    mbar_wait_fast(bar_odone, uint32_t((j - 1) & 1));
+                    tc_fence_after();
+                    waited = true;
+                    float alpha = 1.0f;
+                    if (need) {
+                        const float mc_new = ceilf(mx * c);
+                        alpha = fast_exp2(mc - mc_new);
+                        mc = mc_new;
+                        smin = (mc - 126.0f) * inv_c;
+                        l *= alpha;
+                    }
+                    uint32_t ro[32];
+                    tmem_ld32(o_addr, ro);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ro[i] = __float_as_uint(__uint_as_float(ro[i]) * alpha);
+                    tmem_st32(o_addr, ro);
+                }
+            }
+            const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+            const float Kf = MAGIC - mc;
+            const uint64_t K2 = pack_f32x2(Kf, Kf);
+            uint64_t ps2[4] = {0ull, 0ull, 0ull, 0ull};
+            if (ALT && (j > 0 || t == 1)) mbar_wait_fast(bar_my_turn, uint32_t((t == 1 ? j : j - 1) & 1));
+            // exponentials: a pure FFMA2 / MUFU.EX2 / FADD2 stream (nothing in it waits on a MUFU result except the row sum)
+#pragma unroll
+            for (int ch = 0; ch < 4; ++ch) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int i = ch * 16 + 2 * q;
+                    float e0, e1;
+                    if (a3_emulated<EMU8>(q)) {
+                        const float s0 = fmaxf(__uint_as_float(r[i]), smin), s1 = fmaxf(__uint_as_float(r[i + 1]), smin);
+                        const uint64_t s2 = pack_f32x2(s0, s1);
+                        const uint64_t t2 = fma_rm_f32x2(s2, c2, K2);              // MAGIC + floor(s*c - mc)
+                        const uint64_t f2 = fma_f32x2(s2, c2, sub_f32x2(K2, t2));  // fractional part, [0, 1)
+                        uint64_t p2 = fma_f32x2(f2, pack_f32x2(0.077119089663028717f, 0.077119089663028717f),
+                                                pack_f32x2(0.227564394474029541f, 0.227564394474029541f));
+                        p2 = fma_f32x2(p2, f2, pack_f32x2(0.695146143436431885f, 0.695146143436431885f));
+                        p2 = fma_f32x2(p2, f2, pack_f32x2(1.0f, 1.0f));
+                        e0 = __int_as_float(int(uint32_t(p2)) + (int(uint32_t(t2)) << 23));
+                        e1 = __int_as_float(int(uint32_t(p2 >> 32)) + (int(uint32_t(t2 >> 32)) << 23));
+                    } else {
+                        const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nmc2);
+                        e0 = fast_exp2(f32x2_lo(x2));
+                        e1 = fast_exp2(f32x2_hi(x2));
+                    }
+                    r[i] = __float_as_uint(e0);
+                    r[i + 1] = __float_as_uint(e1);
+                }
+                if (ALT && ch == A3_TURN_AT - 1) {  // hand the MUFU pipe to the other tile (its wake-up overlaps our tail)
+                    asm volatile("" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_other_turn);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 64; i += 2)
+                ps2[(i >> 1) & 3] = add_f32x2(ps2[(i >> 1) & 3], pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
+            if (j > 0 && !waited) {  // PV_t(j-1) must have read P_t before it is overwritten (long done by now)
+                mbar_wait_fast(bar_odone, uint32_t((j - 1) & 1));
+                tc_fence_after();
+            }
+            tmem_st32(p_addr, pk);
+            tmem_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_pfull);
+            const uint64_t a = add_f32x2(add_f32x2(ps2[0], ps2[1]), add_f32x2(ps2[2], ps2[3]));
+            l += f32x2_lo(a) + f32x2_hi(a);
+        }
+
+        // ---- epilogue: O / l -> global (this thread: 32 of the row's 64 output columns)
+        {
+            const int par = (n_blocks & 1) * 512;
+            xslot_mine[par] = l;
+            named_bar_sync(pair_bar, 64);
+            l += xslot_other[par];
+        }
+        mbar_wait_fast(bar_odone, uint32_t((n_blocks - 1) & 1));
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const bool store = q_row < p.q_rows;
+        const int b = bh / p.H, h = bh - b * p.H;
+        __nv_bfloat16* o_ptr =
+            p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D + half * 32;
+        uint4 prev[4];
+        if (store && p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prev[i] = reinterpret_cast<const uint4*>(o_ptr)[i];
+        }
+        uint32_t ro[32];
+        tmem_ld32(o_addr, ro);
+        tmem_wait_ld();
+        if (store) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+                float f[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(ro[i + k]) * inv_l;
+                if (p.accumulate) {
+                    const uint4 old = prev[i / 8];
+                    f[0] = fmaf(p.out_scale, f[0], bf16_lo(old.x)); f[1] = fmaf(p.out_scale, f[1], bf16_hi(old.x));
+                    f[2] = fmaf(p.out_scale, f[2], bf16_lo(old.y)); f[3] = fmaf(p.out_scale, f[3], bf16_hi(old.y));
+                    f[4] = fmaf(p.out_scale, f[4], bf16_lo(old.z)); f[5] = fmaf(p.out_scale, f[5], bf16_hi(old.z));
+                    f[6] = fmaf(p.out_scale, f[6], bf16_lo(old.w)); f[7] = fmaf(p.out_scale, f[7], bf16_hi(old.w));
+                }
+                uint4 v;
+                v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+                v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+                reinterpret_cast<uint4*>(o_ptr + i)[0] = v;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+static int g_attn_impl = 3;  // 1 = v1 (8 softmax warps), 2 = v2 (16), 3 = v3 (16, alternating tiles)
 static int g_attn_emu = 0;   // exponentials per 8 evaluated on the FMA pipe (v2)
 static int g_attn_stagger = 0;
 static long long* g_attn_trace = nullptr;
 static int g_attn_mutex = 0;
 static int g_attn_packed = 1;
+static int g_attn_alt = 1;   // v3: the two query tiles take turns on the MUFU pipe
 
 template <int EMU, bool MUTEX, bool TRACE, bool PACKED>
 static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -702,6 +1066,20 @@ static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const
         attr_set = true;
     }
     kern<<<grid, A2_THREADS, A2_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    return check_launch("attn_fwd");
+}
+
+template <int EMU8, bool ALT>
+static int launch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                        const AttnParams& p) {
+    static bool attr_set = false;
+    auto kern = attn3_fwd_kernel<EMU8, ALT>;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    kern<<<grid, A3_THREADS, A3_SMEM_BYTES, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd");
 }
 
@@ -754,16 +1132,25 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     }
     dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (g_attn_impl == 3) {
+#define TG_A3(E)                                                                                  \
+    case E:                                                                                       \
+        return g_attn_alt ? launch_attn3<E, true>(grid, st, tq, tk, tv, p) : launch_attn3<E, false>(grid, st, tq, tk, tv, p);
+        switch (g_attn_emu) {
+            TG_A3(0) TG_A3(1) TG_A3(2) TG_A3(3) TG_A3(4)
+            default: return fail(-7, "attn_fwd: attn_emu must be 0..4 (eighths of the exponentials on the FMA pipe)");
+        }
+#undef TG_A3
+    }
     if (g_attn_impl == 2) {
         if (g_attn_trace != nullptr) return launch_attn2<0, false, true, false>(grid, st, tq, tk, tv, p);
 #define TG_A2(E)                                                                        \
     case E:                                                                             \
         return g_attn_packed ? launch_attn2<E, false, false, true>(grid, st, tq, tk, tv, p)   \
                              : launch_attn2<E, false, false, false>(grid, st, tq, tk, tv, p);
-        if (g_attn_mutex) return launch_attn2<0, true, false, false>(grid, st, tq, tk, tv, p);
         switch (g_attn_emu) {
-            TG_A2(0) TG_A2(1) TG_A2(2) TG_A2(3)
-            default: return fail(-7, "attn_fwd: attn_emu must be 0..3");
+            TG_A2(0)
+            default: return fail(-7, "attn_fwd: v2 ships with attn_emu 0 only");
         }
 #undef TG_A2
     }
@@ -784,5 +1171,6 @@ extern "C" int tg_set_tuning(const char* key, int value) {
     if (k == "attn_stagger") { g_attn_stagger = value; return 0; }
     if (k == "attn_mutex") { g_attn_mutex = value; return 0; }
     if (k == "attn_packed") { g_attn_packed = value; return 0; }
+    if (k == "attn_alt") { g_attn_alt = value; return 0; }
     return fail(-2, "set_tuning: unknown key %s", key);
 }

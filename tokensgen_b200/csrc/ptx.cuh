@@ -70,6 +70,40 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_
     }
 }
 
+// Lean wait for hot loops: the probe carries a suspend-time hint so a blocked warp sleeps in hardware instead of spinning
+// through issue slots its SM sub-partition neighbours need; still bounded (trap, no printf: keeps the stack frame empty).
+__device__ __forceinline__ bool mbar_try_wait_hint(uint32_t bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+#ifndef TG_WAIT_HINT_NS
+#define TG_WAIT_HINT_NS 0
+#endif
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+#if TG_WAIT_HINT_NS > 0
+    if (mbar_try_wait_hint(bar, parity, TG_WAIT_HINT_NS)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait_hint(bar, parity, TG_WAIT_HINT_NS)) {
+        if (++spins > (1u << 20)) __trap();
+    }
+#else
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 24)) __trap();
+    }
+#endif
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(m) : "memory");
@@ -177,6 +211,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3, uint32_t r4,
+                                         uint32_t r5, uint32_t r6, uint32_t r7) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r0), "r"(r1),
+                 "r"(r2), "r"(r3), "r"(r4), "r"(r5), "r"(r6), "r"(r7)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -223,6 +263,17 @@ __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c
 __device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
     uint64_t d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+__device__ __forceinline__ uint64_t fma_rm_f32x2(uint64_t a, uint64_t b, uint64_t c) {  // round towards -inf
+    uint64_t d;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
 
