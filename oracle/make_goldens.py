@@ -308,11 +308,47 @@ def gen_vae_tiny():
     torch.save(blob, GOLDEN / "vae_tiny.pt")
 
 
+RESAMPLER_TINY = dict(dim=128, depth=2, dim_head=64, heads=2, num_height_queries=2, num_width_queries=3,
+                      num_temporal_queries=2, embedding_dim=128, output_dim=128, max_height_seq_len=4, max_width_seq_len=6,
+                      max_temporal_seq_len=3)
+
+
+def gen_resampler_tiny():
+    """The reference Resampler (longvgen/video_ipadapter/resampler.py) on a small configuration, fp32 and bf16, with the
+    RoPE tables built the way the pipeline builds them (pipeline_cogvideox_mp_fifo.py:1104-1149)."""
+    from longvgen.models.embeddings import get_3d_rotary_pos_embed_v2
+    from longvgen.video_ipadapter.resampler import Resampler
+    from oracle.resampler import ResamplerConfig, resampler_shapes
+    c = RESAMPLER_TINY
+    m = Resampler(**c).eval()
+    shapes = {k: list(v.shape) for k, v in m.state_dict().items()}
+    mine = resampler_shapes(ResamplerConfig(**c))
+    assert shapes == mine, (set(shapes) ^ set(mine), [k for k in shapes if k in mine and shapes[k] != mine[k]])
+    sd = synth_state_dict(shapes, seed=2468)
+    lin = lambda a, b, n: np.linspace(a, b, n, endpoint=False, dtype=np.float32)
+    image_rope = get_3d_rotary_pos_embed_v2(64, lin(0, c["max_temporal_seq_len"], c["max_temporal_seq_len"]),
+                                            lin(0, c["max_height_seq_len"], c["max_height_seq_len"]),
+                                            lin(0, c["max_width_seq_len"], c["max_width_seq_len"]))
+    sampling_rope = get_3d_rotary_pos_embed_v2(64, lin(1000, 1000 + c["max_temporal_seq_len"], c["num_temporal_queries"]),
+                                               lin(0, c["max_height_seq_len"], c["num_height_queries"]),
+                                               lin(0, c["max_width_seq_len"], c["num_width_queries"]))
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, c["max_temporal_seq_len"], c["max_height_seq_len"] * c["max_width_seq_len"], c["embedding_dim"],
+                    generator=g).bfloat16()
+    blob = {"digest": state_dict_digest(sd), "x": x, "image_rope": image_rope, "sampling_rope": sampling_rope}
+    for dt, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        m.load_state_dict({k: v.to(dt) for k, v in sd.items()})
+        m.to(dt)
+        with torch.no_grad():
+            blob["out_" + tag] = m(x.to(dt), image_rotary_emb=image_rope, sampling_rotary_emb=sampling_rope).clone()
+    torch.save(blob, GOLDEN / "resampler_tiny.pt")
+
+
 def main():
     ref_import.enable()
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    fns = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny)
+    fns = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny, gen_resampler_tiny)
     only = set(sys.argv[1:])
     for fn in fns:
         if only and fn.__name__ not in only:

@@ -702,8 +702,11 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 //         f = fma.rn(s, c, -(t - (1.5*2^23 - mc)))  is the fractional part,
 //     followed by a degree-3 polynomial and one shift-add into the exponent field (max rel. error 8.8e-5).
 #ifndef A3_PRODUCER_REGS
-#define A3_PRODUCER_REGS 40  // (96 - producer) * 128 registers are all the softmax warps can gain: 40 -> 104, 32 -> 112
-#define A3_SOFTMAX_REGS 104
+#define A3_PRODUCER_REGS 32  // (96 - producer) * 128 registers are all the softmax warps can gain: 40 -> 104, 32 -> 112
+#define A3_SOFTMAX_REGS 112
+#endif
+#ifndef A3_OPAQUE
+#define A3_OPAQUE 1
 #endif
 #ifndef A3_TURN_AT
 #define A3_TURN_AT 4  // 16-column chunks of exponentials issued before the MUFU pipe is handed to the other tile
@@ -738,7 +741,6 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t tmem_slot = bar_base + 8u * (17 + 2 * AT_STAGES);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
-    float* xch = reinterpret_cast<float*>(smem_raw + (xch_smem - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -863,14 +865,24 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const int row_in_tile = wq * 32 + lane;
         const int q_row = q0 + t * AT_BLOCK_Q + row_in_tile;
         const uint32_t lane_base = tmem_base + (uint32_t(wq * 32) << 16);
-        const uint32_t s_addr = lane_base + s_col(t) + uint32_t(half * 64);
-        const uint32_t o_addr = lane_base + o_col(t) + uint32_t(half * 32);
-        const uint32_t p_addr = lane_base + p_col(t) + uint32_t(half * 32);
-        const uint32_t bar_sfull = s_full(t), bar_sfree = s_free(t), bar_pfull = p_full(t), bar_odone = o_done(t);
-        const uint32_t bar_my_turn = turn(t, wq), bar_other_turn = turn(1 - t, wq);
-        const int pair_bar = 1 + t * 4 + wq;
-        float* const xslot_mine = xch + (t * 2 + half) * 128 + row_in_tile;        // + parity * 512
-        float* const xslot_other = xch + (t * 2 + (half ^ 1)) * 128 + row_in_tile;
+#if A3_OPAQUE
+        // loop-invariant addresses pinned in registers (ptxas otherwise re-derives them from %tid every block)
+#define A3_PIN(x) asm volatile("mov.b32 %0, %0;" : "+r"(x))
+#else
+#define A3_PIN(x)
+#endif
+        uint32_t s_addr = lane_base + s_col(t) + uint32_t(half * 64);
+        uint32_t o_addr = lane_base + o_col(t) + uint32_t(half * 32);
+        uint32_t p_addr = lane_base + p_col(t) + uint32_t(half * 32);
+        uint32_t bar_sfull = s_full(t), bar_sfree = s_free(t), bar_pfull = p_full(t), bar_odone = o_done(t);
+        uint32_t bar_my_turn = turn(t, wq), bar_other_turn = turn(1 - t, wq);
+        int pair_bar = 1 + t * 4 + wq;
+        uint32_t xs_mine = xch_smem + uint32_t(((t * 2 + half) * 128 + row_in_tile) * 4);        // + parity * 2048
+        uint32_t xs_other = xch_smem + uint32_t(((t * 2 + (half ^ 1)) * 128 + row_in_tile) * 4);
+        A3_PIN(s_addr); A3_PIN(o_addr); A3_PIN(p_addr); A3_PIN(bar_sfull); A3_PIN(bar_sfree); A3_PIN(bar_pfull);
+        A3_PIN(bar_odone); A3_PIN(pair_bar); A3_PIN(xs_mine); A3_PIN(xs_other);
+        auto sts_f32 = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
+        auto lds_f32 = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; };
         const float c = p.scale_log2;
         const float inv_c = 1.0f / c;
         const uint64_t c2 = pack_f32x2(c, c);
@@ -909,10 +921,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     pm[k] = fmaxf(pm[k], fmaxf(__uint_as_float(r[i + 2 * k]), __uint_as_float(r[i + 2 * k + 1])));
             float mx = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
             {
-                const int par = (j & 1) * 512;
-                xslot_mine[par] = mx;
+                const uint32_t par = uint32_t(j & 1) * 2048u;
+                sts_f32(xs_mine + par, mx);
                 named_bar_sync(pair_bar, 64);
-                mx = fmaxf(mx, xslot_other[par]);
+                mx = fmaxf(mx, lds_f32(xs_other + par));
             }
             bool waited = false;
             if (j == 0) {
@@ -998,10 +1010,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
         // ---- epilogue: O / l -> global (this thread: 32 of the row's 64 output columns)
         {
-            const int par = (n_blocks & 1) * 512;
-            xslot_mine[par] = l;
+            const uint32_t par = uint32_t(n_blocks & 1) * 2048u;
+            sts_f32(xs_mine + par, l);
             named_bar_sync(pair_bar, 64);
-            l += xslot_other[par];
+            l += lds_f32(xs_other + par);
         }
         mbar_wait_fast(bar_odone, uint32_t((n_blocks - 1) & 1));
         tc_fence_after();
@@ -1048,12 +1060,12 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 static int g_attn_impl = 3;  // 1 = v1 (8 softmax warps), 2 = v2 (16), 3 = v3 (16, alternating tiles)
-static int g_attn_emu = 0;   // exponentials per 8 evaluated on the FMA pipe (v2)
+static int g_attn_emu = 1;   // v3: eighths of the exponentials evaluated on the FMA pipe
 static int g_attn_stagger = 0;
 static long long* g_attn_trace = nullptr;
 static int g_attn_mutex = 0;
 static int g_attn_packed = 1;
-static int g_attn_alt = 1;   // v3: the two query tiles take turns on the MUFU pipe
+static int g_attn_alt = 0;   // v3: the two query tiles take turns on the MUFU pipe
 
 template <int EMU, bool MUTEX, bool TRACE, bool PACKED>
 static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -1144,15 +1156,8 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     }
     if (g_attn_impl == 2) {
         if (g_attn_trace != nullptr) return launch_attn2<0, false, true, false>(grid, st, tq, tk, tv, p);
-#define TG_A2(E)                                                                        \
-    case E:                                                                             \
-        return g_attn_packed ? launch_attn2<E, false, false, true>(grid, st, tq, tk, tv, p)   \
-                             : launch_attn2<E, false, false, false>(grid, st, tq, tk, tv, p);
-        switch (g_attn_emu) {
-            TG_A2(0)
-            default: return fail(-7, "attn_fwd: v2 ships with attn_emu 0 only");
-        }
-#undef TG_A2
+        return g_attn_packed ? launch_attn2<0, false, false, true>(grid, st, tq, tk, tv, p)
+                             : launch_attn2<0, false, false, false>(grid, st, tq, tk, tv, p);
     }
     attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd");
