@@ -1,0 +1,152 @@
+#!/usr/bin/env python
+"""TokensGen long-video inference on B200 — the reference's entry point (infer_cogvideo_mp_fifo.py:186-389) on the
+tokensgen_b200 mirrors.  Same flag (`--config <yaml>`), same yaml schema (config/infer/{edit,gen}.yaml), same outputs
+(`<name>_{source,embeds,orig,fifo}_<prompt[:20]>` under `<output_dir>/<prefix>_<timestamp>/`).
+
+    python infer_cogvideo_mp_fifo.py --config config/infer/edit.yaml                              # one GPU
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 infer_cogvideo_mp_fifo.py --config ...     # one process per GPU
+
+Process model: the reference builds one pipeline per visible GPU inside one process and spawns a worker per GPU for every
+video; here every GPU runs this script as a persistent rank (torchrun), loads its own copy of the weights in parallel,
+rank 0 runs the serial stages (T2To, conditioning, the 52-step base clip) and broadcasts the FIFO priming state, and all
+ranks run the FIFO stage with NCCL boundary-frame exchange, then decode clip-parallel.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import datetime
+import json
+import os
+
+import torch
+import torch.distributed as dist
+
+from tokensgen_b200 import config as cfgmod
+from tokensgen_b200.fifo import broadcast_base_output, cogvideo_fifo_mp_v2
+from tokensgen_b200.pipeline import MPFIFOVideoIPAdapterCogVideoXPipeline
+from tokensgen_b200.pipeline_t2to import LongVGenCogVideoXPipeline
+from tokensgen_b200.resampler import Resampler
+from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+from tokensgen_b200.transformer import CogVideoXTransformer3DModel
+from tokensgen_b200.video_io import export_to_video, load_video
+
+
+def create_output_folders(output_dir, config, prefix="longvgen"):
+    now = datetime.datetime.now().strftime("%Y-%m-%dT%H-%M-%S")
+    out_dir = os.path.join(output_dir, f"{prefix}_{now}")
+    os.makedirs(out_dir, exist_ok=True)
+    cfgmod.save(config, os.path.join(out_dir, "config.yaml"))
+    return out_dir
+
+
+def init_pipeline(gpu_id, args, dtype):
+    """infer_cogvideo_mp_fifo.py:138-183."""
+    device = torch.device(f"cuda:{gpu_id}")
+    transformer = CogVideoXTransformer3DModel.from_pretrained(args.pretrained_model_name_or_path, subfolder="transformer",
+                                                              torch_dtype=torch.bfloat16).to(device)
+    resampler = None
+    if args.use_vip:
+        vip_params = args.video_ipadapter_params
+        vip_path = args.pretrained_resampler_name_or_path
+        transformer.set_vip_layers(vip_path, **vip_params)
+        transformer = transformer.to(dtype)
+        resampler = Resampler.from_pretrained(vip_path, subfolder="resampler", torch_dtype=dtype).to(device)
+        resampler.set_pca(args.get("longvgen_pca", None), device=device)
+    pipe = MPFIFOVideoIPAdapterCogVideoXPipeline.from_pretrained(args.pretrained_model_name_or_path, transformer=transformer,
+                                                                 resampler=resampler, torch_dtype=dtype)
+    pipe.scheduler = CogVideoXDPMScheduler.from_config(pipe.scheduler.config, timestep_spacing="trailing")
+    pipe.to(device)
+    pipe.vae.enable_slicing()
+    pipe.vae.enable_tiling()
+    return pipe
+
+
+def main(args):
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if args.dtype != "bf16":
+        raise SystemExit("tokensgen_b200 computes in bf16 (dtype: 'bf16' in both shipped configs)")
+    dtype = torch.bfloat16
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    if rank == 0:
+        args.output_dir = create_output_folders(args.output_dir, args, args.name_prefix)
+    pipe = init_pipeline(local, args, dtype)              # every rank loads its own weights, in parallel
+    pipe_list = [pipe]
+    vip_params = args.video_ipadapter_params if args.use_vip else None
+
+    pipe_2nd = None
+    if args.use_2nd_stage and rank == 0:
+        tokens_transformer = CogVideoXTransformer3DModel.from_pretrained(args.pretrained_2nd_stage_model_name_or_path,
+                                                                         subfolder="transformer", torch_dtype=dtype)
+        pipe_2nd = LongVGenCogVideoXPipeline.from_pretrained(args.pretrained_model_name_or_path, transformer=tokens_transformer,
+                                                             torch_dtype=dtype, vae=pipe.vae, text_encoder=pipe.text_encoder,
+                                                             tokenizer=pipe.tokenizer)
+        pipe_2nd.scheduler = CogVideoXDPMScheduler.from_config(pipe_2nd.scheduler.config, timestep_spacing="trailing")
+        pipe_2nd.to(device)
+
+    inputs = args.input_config
+    public_dps = inputs.pop("public")
+    items_json = inputs.pop("input_json") if inputs.get("input_json") is not None else None
+    if items_json is not None:
+        with open(items_json) as f:
+            inputs.update(json.load(f).get("input_config"))
+    if rank == 0:
+        print(f"***** Running inference *****\n  Num items = {len(inputs)}  ranks = {world}")
+
+    for name, item in inputs.items():
+        prompt = item["prompt"]
+        dps = copy.deepcopy(public_dps)
+        dps.update(item.get("params", {}))
+        call = dict(
+            prompt=prompt, num_videos_per_prompt=dps.num_videos_per_prompt, num_inference_steps=args.num_inference_steps,
+            num_frames_per_chunk=args.num_frames_per_chunk, max_num_chunks=dps.max_num_chunks,
+            max_num_chunks_wo_fifo=dps.max_num_chunks_wo_fifo, max_num_chunks_w_fifo=dps.max_num_chunks_w_fifo,
+            use_dynamic_cfg=False, use_separate_guidance=dps.get("use_separate_guidance", args.get("use_separate_guidance", False)),
+            guidance_scale=args.guidance_scale, guidance_scale_img=args.get("guidance_scale_img", args.guidance_scale),
+            vip_scale=vip_params.scale if args.use_vip else 1.0, sampling_mode=args.get("sampling_mode"),
+            sampling_params=args.get("sampling_params"), cache_idx=args.get("cache_idx"),
+            video_ipadapter_start_frame_idx=vip_params.video_ipadapter_start_frame_idx if args.use_vip else 1000,
+            return_dict=False, output_type="np")
+        video = image_embeddings = base_outputs = None
+        if rank == 0:
+            print(f"Processing {name}: [{prompt}]")
+            if args.use_vip:
+                if args.use_2nd_stage:
+                    rp = vip_params.resampler_params
+                    image_embeddings = pipe_2nd(
+                        prompt=prompt, height=rp.num_height_queries, width=rp.num_width_queries,
+                        num_frames_per_chunk=rp.num_temporal_queries, num_chunks=dps.max_num_chunks, use_dynamic_cfg=True,
+                        guidance_scale=args.get("guidance_scale_2nd", args.guidance_scale),
+                        generator=torch.Generator().manual_seed(args.seed_2nd), longvgen_mean=args.longvgen_mean,
+                        longvgen_std=args.longvgen_std, longvgen_pca=args.longvgen_pca).frames
+                else:
+                    assert item.get("video") is not None
+                    video = load_video(item["video"], dps.output_res, args.num_frames_per_chunk, dps.pad_to_fit, dps.sample_fps,
+                                       dps.start_t, dps.end_t, dps.max_num_chunks, dps.crop_to_fit)
+            base_outputs = pipe(frames=video, image_embeddings=image_embeddings,
+                                generator=torch.Generator().manual_seed(args.seed), **call)
+            base_outputs.condition_frames = None      # not needed by the FIFO stage; keeps the broadcast small
+        else:
+            pipe.preprare_for_fifo(**call)
+        base_outputs = broadcast_base_output(base_outputs, src=0, device=device)
+        orig_video_frames, video_frames, _ = cogvideo_fifo_mp_v2(pipe_list, base_outputs, seed=args.seed)
+        if rank == 0:
+            tag = prompt[:20]
+            if video is not None:
+                export_to_video((video.clamp(-1, 1) / 2 + 0.5).squeeze(0).permute(0, 2, 3, 1).cpu().numpy(),
+                                os.path.join(args.output_dir, f"{name}_source_{tag}.mp4"), fps=dps.output_fps)
+            if image_embeddings is not None:
+                torch.save(image_embeddings[0].cpu(), os.path.join(args.output_dir, f"{name}_embeds_{tag}.pt"))
+            export_to_video(orig_video_frames[0], os.path.join(args.output_dir, f"{name}_orig_{tag}.mp4"), fps=dps.output_fps)
+            export_to_video(video_frames[0], os.path.join(args.output_dir, f"{name}_fifo_{tag}.mp4"), fps=dps.output_fps)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--config", type=str, default="./config/infer/edit.yaml")
+    main(cfgmod.load(parser.parse_args().config))

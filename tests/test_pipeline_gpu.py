@@ -1,0 +1,89 @@
+"""End-to-end plumbing of the pipeline mirrors on the GPU with tiny random-init models: conditioning video -> VAE encode ->
+patch projection -> Resampler -> 12-step base clip with the diagonal FIFO capture -> FIFO stage -> clip-parallel decode,
+and the T2To pipeline tail.  (Arithmetic parity of each stage has its own test file; here: shapes, bit-exact priming
+capture, determinism, finiteness.)"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_pipe():
+    from tokensgen_b200.pipeline import MPFIFOVideoIPAdapterCogVideoXPipeline
+    from tokensgen_b200.resampler import Resampler
+    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+    from tokensgen_b200.transformer import CogVideoXTransformer3DModel
+    from tokensgen_b200.vae import AutoencoderKLCogVideoX
+    torch.manual_seed(0)
+    dit = CogVideoXTransformer3DModel(num_attention_heads=4, attention_head_dim=64, time_embed_dim=128, text_embed_dim=128,
+                                      num_layers=2, use_rotary_positional_embeddings=True, attention_bias=True)
+    rp = dict(dim=256, depth=1, dim_head=64, heads=4, num_height_queries=2, num_width_queries=3, num_temporal_queries=2,
+              embedding_dim=256, output_dim=256, max_height_seq_len=4, max_width_seq_len=6, max_temporal_seq_len=3)
+    dit.set_vip_layers(None, length=18, func_type="1", scale=[0.6], resampler_params=rp)
+    for p in dit.parameters():
+        torch.nn.init.normal_(p, std=0.02)
+    res = Resampler(**rp)
+    vae = AutoencoderKLCogVideoX(block_out_channels=(64, 64, 64, 64), layers_per_block=1, norm_num_groups=8, sample_height=64,
+                                 sample_width=96, scaling_factor=0.7)
+    dev = torch.device("cuda")
+    pipe = MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae.to(dev, torch.bfloat16).eval(), dit.to(dev, torch.bfloat16).eval(),
+                                                 CogVideoXDPMScheduler(), resampler=res.to(dev, torch.bfloat16).eval())
+    return pipe.to(dev)
+
+
+def _run(pipe, seed):
+    from tokensgen_b200.fifo import cogvideo_fifo_mp_v2
+    g = torch.Generator().manual_seed(3)
+    frames = torch.rand(1, 18, 3, 64, 96, generator=g) * 2 - 1
+    pe = torch.randn(1, 10, 128, generator=g)
+    ne = torch.randn(1, 10, 128, generator=g)
+    base = pipe(frames=frames, prompt_embeds=pe, negative_prompt_embeds=ne, height=64, width=96, num_frames_per_chunk=9,
+                max_num_chunks=2, max_num_chunks_w_fifo=25, max_num_chunks_wo_fifo=1, num_inference_steps=12, guidance_scale=6.0,
+                generator=torch.Generator().manual_seed(seed), vip_scale=[0.6], sampling_mode="fifo",
+                sampling_params={"num_partitions": 4, "use_adaptive_padding": True}, cache_idx=None, output_type="np",
+                return_dict=False)
+    orig, video, cache = cogvideo_fifo_mp_v2([pipe], base, seed=seed)
+    return base, orig, video
+
+
+def test_base_stage_fifo_stage_and_decode():
+    from tokensgen_b200 import _ext as E
+    pipe = _tiny_pipe()
+    base, orig, video = _run(pipe, 42)
+    assert base.nf_per_chunk == 3 and base.vip_nf_per_chunk == 2 and base.num_frames == 6
+    assert tuple(base.fifo_latents.shape) == (1, 12, 16, 8, 12) and len(base.fifo_old_pred_original_sample) == 12
+    assert base.fifo_old_pred_original_sample[-1] is None and base.fifo_old_pred_original_sample[0] is not None
+    # priming capture (pipeline_cogvideox_mp_fifo.py:1190): step 0 contributes the PRE-step latent of frame 2, stored last
+    init = E.randn_tensor((1, 3, 16, 8, 12), torch.Generator().manual_seed(42), "cuda", torch.bfloat16)
+    assert torch.equal(base.fifo_latents[:, -1], init[:, 2])
+    assert tuple(base.image_embeddings.shape) == (2, 6, 256, 2, 3)   # CFG pair x (2 chunks + 1 pad) x 2 temporal queries
+    assert video.shape == (1, 18, 64, 96, 3) and orig.shape == (1, 9, 64, 96, 3)
+    assert np.isfinite(video).all() and np.isfinite(orig).all() and 0.0 <= video.min() and video.max() <= 1.0
+    assert video.std() > 0
+    # determinism: same seeds -> identical video
+    _, _, video2 = _run(pipe, 42)
+    assert np.array_equal(video, video2)
+    _, _, video3 = _run(pipe, 43)
+    assert not np.array_equal(video, video3)
+
+
+def test_t2to_pipeline_tail():
+    from pca import PCA
+    from tokensgen_b200.pipeline_t2to import LongVGenCogVideoXPipeline
+    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+    from tokensgen_b200.transformer import CogVideoXTransformer3DModel
+    torch.manual_seed(1)
+    dit = CogVideoXTransformer3DModel(num_attention_heads=4, attention_head_dim=64, time_embed_dim=128, text_embed_dim=128,
+                                      num_layers=2, patch_size=1, use_rotary_positional_embeddings=True, attention_bias=True)
+    for p in dit.parameters():
+        torch.nn.init.normal_(p, std=0.02)
+    pipe = LongVGenCogVideoXPipeline(None, None, None, dit.to("cuda", torch.bfloat16).eval(), CogVideoXDPMScheduler()).to("cuda")
+    g = torch.Generator().manual_seed(2)
+    pca = PCA(None).fit(torch.randn(64, 32, generator=g))
+    mean, std = torch.randn(1, 32, generator=g), torch.rand(1, 32, generator=g) + 0.5
+    out = pipe(prompt_embeds=torch.randn(1, 10, 128, generator=g), negative_prompt_embeds=torch.randn(1, 10, 128, generator=g),
+               height=2, width=3, num_frames_per_chunk=2, num_chunks=4, num_inference_steps=4, guidance_scale=6.0,
+               use_dynamic_cfg=True, generator=torch.Generator().manual_seed(5), longvgen_mean=mean, longvgen_std=std,
+               longvgen_pca=pca).frames
+    assert tuple(out.shape) == (1, 8, 32, 2, 3) and out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()

@@ -161,6 +161,15 @@ def _bf16_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
     return t
 
 
+def randn_tensor(shape, generator, device, dtype) -> torch.Tensor:
+    """diffusers.utils.torch_utils.randn_tensor as the reference uses it: a CPU generator draws on the CPU and the
+    result is moved (so seeds reproduce across devices); a device generator draws in place."""
+    gdev = generator.device if generator is not None else torch.device(device)
+    if gdev.type != torch.device(device).type:
+        return torch.randn(tuple(shape), generator=generator, device=gdev, dtype=dtype).to(device)
+    return torch.randn(tuple(shape), generator=generator, device=device, dtype=dtype)
+
+
 def make_rowmap(n_text: int, n_video: int, n_vip: int, hw: int, frames: int) -> RowMap:
     return RowMap(n_text + n_video + n_vip, n_text, n_video, n_vip, hw, frames)
 

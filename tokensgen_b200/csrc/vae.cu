@@ -34,11 +34,11 @@ static inline int grid_for(int64_t work_items, int threads = 256) {
 // group per block reaches HBM.
 __global__ void __launch_bounds__(256)
 group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t pixels, int C, int64_t ldx, int groups, double* __restrict__ sums) {
-    __shared__ float sh[2 * 64];
+    __shared__ double sh[2 * 64];    // fp64 so that the order of the atomics cannot change a rounded statistic run to run
     const int V = C / 8;             // vectors per pixel
     const int ppb = 256 / V;         // pixels per block iteration (V <= 256 checked by the host)
     const int v = threadIdx.x % V, pl = threadIdx.x / V;
-    for (int i = threadIdx.x; i < 2 * groups; i += 256) sh[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * groups; i += 256) sh[i] = 0.0;
     __syncthreads();
     float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (pl < ppb) {
@@ -58,18 +58,18 @@ group_stats_kernel(const __nv_bfloat16* __restrict__ x, int64_t pixels, int C, i
 #pragma unroll
         for (int j = 0; j < 8; ++j) { ss += s[j]; qq += q[j]; }
         const int g = (v * 8) / cg;
-        atomicAdd(&sh[g], ss);
-        atomicAdd(&sh[groups + g], qq);
+        atomicAdd(&sh[g], double(ss));
+        atomicAdd(&sh[groups + g], double(qq));
     } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int g = (v * 8 + j) / cg;
-            atomicAdd(&sh[g], s[j]);
-            atomicAdd(&sh[groups + g], q[j]);
+            atomicAdd(&sh[g], double(s[j]));
+            atomicAdd(&sh[groups + g], double(q[j]));
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * groups; i += 256) atomicAdd(&sums[i], double(sh[i]));
+    for (int i = threadIdx.x; i < 2 * groups; i += 256) atomicAdd(&sums[i], sh[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ K16b apply

@@ -238,3 +238,102 @@ def make_step_fn(transformer, scheduler, prompt_embeds: torch.Tensor, image_rota
                                      noise=None if noise_override is None else noise_override(w))
 
     return step
+
+
+def broadcast_base_output(base_output, src: int = 0, device=None, group=None):
+    """Ships the FIFO priming state of the base stage from rank `src` to every rank (one object broadcast of ~0.2 GB for
+    gen.yaml: 52 + 52 latent frames, prompt and condensed-token embeddings, grids).  The reference hands the same bundle
+    to its worker processes through mp.Queue on every window (cogvideo_sampling_mp_fifo.py:284-305); here it crosses
+    NVLink once per video."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return base_output
+    box = [base_output if dist.get_rank(group) == src else None]
+    dist.broadcast_object_list(box, src=src, group=group, device=device)
+    out = box[0]
+    if device is not None:
+        for name, v in list(vars(out).items()):
+            if torch.is_tensor(v):
+                setattr(out, name, v.to(device))
+            elif isinstance(v, (list, tuple)) and v and all(torch.is_tensor(x) or x is None for x in v):
+                setattr(out, name, type(v)(None if x is None else x.to(device) for x in v))
+    return out
+
+
+def decode_latents_parallel(pipe, latents: torch.Tensor, nf: int, rank: int = 0, world: int = 1):
+    """pipe.decode_latents (pipeline_cogvideox_mp_fifo.py:676-684) with its 13-frame chunks dealt round-robin to the
+    processes; process 0 returns the assembled [B, 3, F, H, W] video, the others None."""
+    import torch.distributed as dist
+    chunks = latents.shape[1] // nf
+    outs = {c: pipe.decode_latents(latents[:, c * nf:(c + 1) * nf], nf) for c in range(rank, chunks, world)}
+    if world == 1:
+        return torch.cat([outs[c] for c in range(chunks)], dim=2)
+    if rank != 0:
+        for c in sorted(outs):
+            dist.send(outs[c].contiguous(), dst=0)
+        return None
+    like = outs[0]
+    for c in range(chunks):
+        if c % world:
+            buf = torch.empty_like(like)
+            dist.recv(buf, src=c % world)
+            outs[c] = buf
+    return torch.cat([outs[c] for c in range(chunks)], dim=2)
+
+
+def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **kwargs):
+    """Drop-in for the reference sampler entry point (cogvideo_sampling_mp_fifo.py:27-395): same arguments
+    (`pipe_list`, `base_output`) and the same return value — `(orig_video, video, cache_video)` or a
+    `CogVideoXPipelineOutput` when `base_output.return_dict`; `output_type == "latent"` returns latents (:387-390).
+
+    Process model: the reference spawns one worker per entry of `pipe_list` and feeds them through queues; here every
+    GPU already runs this same function in its own persistent process (torchrun), `pipe_list` holds that process's
+    pipeline, and the window rank -> process assignment, lookahead write-back and boundary exchange are `run_fifo`'s."""
+    import torch.distributed as dist
+    from .pipeline import CogVideoXPipelineOutput
+    pipe = pipe_list[0]
+    world, rank = (dist.get_world_size(), dist.get_rank()) if dist.is_available() and dist.is_initialized() else (1, 0)
+    sp = dict(base_output.sampling_params or {})
+    if sp.get("use_sliding_window_embedding"):
+        raise NotImplementedError("use_sliding_window_embedding calls an undefined function in the reference (:150)")
+    if base_output.use_separate_guidance or base_output.use_dynamic_cfg:
+        raise NotImplementedError("the FIFO worker of the shipped configs runs plain two-branch CFG")
+    if base_output.cache_idx:
+        raise NotImplementedError("cache_idx (debug dumps of intermediate queue slots) is empty in the shipped configs")
+    nf, T = base_output.nf_per_chunk, base_output.num_inference_steps
+    dev = base_output.fifo_latents.device
+    schedule = FifoSchedule(base_output.num_frames, [int(t) for t in base_output.timesteps], nf,
+                            sp.get("num_partitions", 4), sp.get("use_adaptive_padding", True))
+    queue = FifoQueue(base_output.fifo_latents.to(torch.bfloat16), base_output.fifo_old_pred_original_sample, schedule.r_nf)
+    vip = None
+    if base_output.image_embeddings is not None:
+        vip = VipBook(base_output.vip_image_rotary_grid, base_output.vip_condition_rotary_grid, base_output.image_embeddings,
+                      nf, base_output.vip_nf_per_chunk, T, base_output.video_ipadapter_start_frame_idx)
+    step_fn = make_step_fn(pipe.transformer, pipe.scheduler, base_output.prompt_embeds, base_output.image_rotary_emb, vip,
+                           base_output.guidance_scale if base_output.do_classifier_free_guidance else 1.0)
+    shift_latents = make_shift_fn(pipe.scheduler)
+
+    def shift(q, gen):
+        shift_latents(q, gen)
+        if vip is not None:
+            vip.shift()                                                   # :351-357
+
+    emitted = run_fifo(schedule, queue, step_fn, shift, seed=seed, rank=rank, world=world, progress=progress)
+    latents = torch.cat(emitted[(T - nf):], dim=1).contiguous()           # :367 (slot r_nf belongs to window rank 0 -> process 0)
+    if world > 1:
+        dist.broadcast(latents, src=0)
+    orig_latents = base_output.orig_latents
+    if base_output.output_type == "latent":
+        video, orig_video = latents, orig_latents
+    else:
+        # decode is clip-parallel with no communication inside a clip (the conv cache is cleared per 13-frame chunk,
+        # autoencoder_kl_cogvideox.py:1157): chunk c is decoded by process c % P and collected on process 0.
+        decoded = decode_latents_parallel(pipe, latents, nf, rank, world)
+        video = None if decoded is None else pipe.video_processor.postprocess_video(video=decoded, output_type=base_output.output_type)
+        orig_video = None
+        if rank == 0:
+            orig_video = pipe.video_processor.postprocess_video(video=pipe.decode_latents(orig_latents, nf),
+                                                                output_type=base_output.output_type)
+    if not base_output.return_dict:
+        return (orig_video, video, [])
+    return CogVideoXPipelineOutput(frames=video, orig_frames=orig_video, cache_frames=[])

@@ -89,6 +89,12 @@ class Resampler(nn.Module):
     def device(self):
         return self.proj_in.weight.device
 
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kwargs):
+        """diffusers-style loader (infer_cogvideo_mp_fifo.py:162-166): <path>/<subfolder>/config.json + weights."""
+        from .loading import build_from_pretrained
+        return build_from_pretrained(cls, pretrained_model_name_or_path, subfolder, torch_dtype, **kwargs)
+
     def set_pca(self, pca_path=None, device="cuda"):
         """resampler.py:199-207 (the PCA object is a pickled top-level `pca.PCA` module)."""
         if pca_path is None:

@@ -53,6 +53,16 @@ class CogVideoXDPMScheduler:
         self.num_inference_steps = None
         self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
 
+    @classmethod
+    def from_config(cls, config=None, **overrides):
+        """`CogVideoXDPMScheduler.from_config(pipe.scheduler.config, timestep_spacing="trailing")`
+        (infer_cogvideo_mp_fifo.py:177-178): a dict / namespace of constructor arguments, unknown keys dropped."""
+        import inspect
+        cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
+        cfg.update(overrides)
+        names = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        return cls(**{k: v for k, v in cfg.items() if k in names})
+
     # ------------------------------------------------------------------ reference API
     def scale_model_input(self, sample: torch.Tensor, timestep=None) -> torch.Tensor:
         return sample
@@ -110,8 +120,8 @@ class CogVideoXDPMScheduler:
         row = self._coef_row(timestep, prev_timestep, timestep_back, has_old)
         coef = torch.tensor([row], dtype=torch.float64).float().to(sample.device)
         # RNG consumption follows the reference: one draw always, a second one on the 2M branch (:450,:461)
-        n1 = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
-        n2 = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype) if row[7] else n1
+        n1 = E.randn_tensor(sample.shape, generator, sample.device, sample.dtype)
+        n2 = E.randn_tensor(sample.shape, generator, sample.device, sample.dtype) if row[7] else n1
         smp = sample.to(torch.bfloat16).reshape(1, -1).contiguous()
         flat = lambda t: t.reshape(1, -1).contiguous()
         if model_output.dtype == torch.bfloat16:
@@ -141,8 +151,8 @@ class CogVideoXDPMScheduler:
             rows.append(self._coef_row(int(t[j]), int(prev_t[j]), back, old_x0[j] is not None))
         coef = torch.tensor(rows, dtype=torch.float64).float().to(dev)
         if noise is None:
-            n1 = torch.randn(latents.shape, generator=generator, device=dev, dtype=latents.dtype)
-            n2 = torch.randn(latents.shape, generator=generator, device=dev, dtype=latents.dtype)
+            n1 = E.randn_tensor(latents.shape, generator, dev, latents.dtype)
+            n2 = E.randn_tensor(latents.shape, generator, dev, latents.dtype)
         else:
             n1, n2 = noise
         frame_shape = latents.shape[2:]

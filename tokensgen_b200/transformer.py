@@ -494,6 +494,21 @@ class CogVideoXTransformer3DModel(nn.Module):
         torch.save(out, os.path.join(vip_ckpt_dir, "vip.pt"))
 
     # ---- forward
+    def _padded(self, name: str, param: torch.Tensor, fn):
+        """Zero-padded copy of a narrow weight, rebuilt when the parameter is re-assigned or modified in place."""
+        cache = self.__dict__.setdefault("_tg_padded", {})
+        key = (param.data_ptr(), param._version)
+        if name not in cache or cache[name][0] != key:
+            cache[name] = (key, fn(param.detach()).contiguous())
+        return cache[name][1]
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kwargs):
+        """diffusers-style loader (infer_cogvideo_mp_fifo.py:150-156): <path>/<subfolder>/config.json + weights."""
+        from .loading import build_from_pretrained
+        kwargs.pop("revision", None), kwargs.pop("variant", None)
+        return build_from_pretrained(cls, pretrained_model_name_or_path, subfolder, torch_dtype, **kwargs)
+
     def _ada_table(self, silu_emb: torch.Tensor) -> torch.Tensor:
         """K1: every AdaLN linear of every block (and norm_out) in ONE GEMM — temb does not depend on the layer."""
         linears = [l for blk in self.transformer_blocks for l in blk._ada_linears()] + [self.norm_out.linear]
@@ -543,6 +558,9 @@ class CogVideoXTransformer3DModel(nn.Module):
         patches = E.patchify(hidden_states.to(torch.bfloat16).contiguous(), p)
         text = encoder_hidden_states.to(torch.bfloat16)
         pw = pe.proj.weight.reshape(d, -1)
+        if pw.shape[1] % 64:  # patch_size 1 (the T2To model, train_cogvideo_t2to.py:1277): K = 16 -> zero-pad to the GEMM's 64
+            pw = self._padded("patch_w", pe.proj.weight, lambda w: torch.nn.functional.pad(w.reshape(d, -1), (0, -w[0].numel() % 64)))
+            patches = torch.nn.functional.pad(patches, (0, pw.shape[1] - patches.shape[1]))
         if use_vip:
             vip_rows = vip_encoder_hidden_states.to(torch.bfloat16).permute(0, 1, 3, 4, 2).reshape(B, n_vip, -1).contiguous()
         for b in range(B):
@@ -566,10 +584,16 @@ class CogVideoXTransformer3DModel(nn.Module):
         X2, Y2 = bufs.X.view(B * rowmap.rows_per_batch, d), bufs.Y.view(B * rowmap.rows_per_batch, d)
         E.ln_modulate(X2, Y2, B, rowmap, self.norm_final.weight, self.norm_final.bias, None, None, cfg.norm_eps, shift, scale,
                       ln2_w=self.norm_out.norm.weight, ln2_b=self.norm_out.norm.bias, eps2=cfg.norm_eps)
-        out_rows = torch.empty(B * n_video, self.proj_out.out_features, device=dev, dtype=torch.bfloat16)
+        n_out = self.proj_out.out_features
+        ow, ob = self.proj_out.weight, self.proj_out.bias
+        if n_out % 64:  # patch_size 1: N = 16 -> zero rows up to 64, sliced away below
+            ow = self._padded("out_w", self.proj_out.weight, lambda w: torch.nn.functional.pad(w, (0, 0, 0, -w.shape[0] % 64)))
+            ob = self._padded("out_b", self.proj_out.bias, lambda b_: torch.nn.functional.pad(b_, (0, -b_.shape[0] % 64)))
+        out_rows = torch.empty(B * n_video, ow.shape[0], device=dev, dtype=torch.bfloat16)
         for b in range(B):
-            E.gemm_bias_act(bufs.Y[b, n_text:n_text + n_video], self.proj_out.weight, self.proj_out.bias,
-                            out_rows[b * n_video:(b + 1) * n_video])
+            E.gemm_bias_act(bufs.Y[b, n_text:n_text + n_video], ow, ob, out_rows[b * n_video:(b + 1) * n_video])
+        if ow.shape[0] != n_out:
+            out_rows = out_rows[:, :n_out].contiguous()
         output = E.unpatchify(out_rows, B, F, self.proj_out.out_features // (p * p), Hh, Ww, p)
         if not return_dict:
             return (output,)

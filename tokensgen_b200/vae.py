@@ -284,7 +284,7 @@ class DiagonalGaussianDistribution:
     def sample(self, generator: Optional[torch.Generator] = None, scale: float = 1.0) -> torch.Tensor:
         p = self.parameters
         shape = (p.shape[0], p.shape[1] // 2) + tuple(p.shape[2:])
-        eps = torch.randn(shape, generator=generator, device=p.device, dtype=p.dtype)
+        eps = E.randn_tensor(shape, generator, p.device, p.dtype)
         out = [E.vae_posterior_sample(p[b].contiguous(), eps[b].contiguous(), scale) for b in range(p.shape[0])]
         return torch.stack(out)
 
@@ -323,6 +323,12 @@ class AutoencoderKLCogVideoX(nn.Module):
         self.decode_chunk_frames = 13  # the in-tree tiled_decode's 13-frame chunk loop (:1317-1337)
 
     # ---- reference API
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, torch_dtype=None, **kwargs):
+        """diffusers-style loader: <path>/<subfolder>/config.json + weights (the pipeline loads subfolder "vae")."""
+        from .loading import build_from_pretrained
+        return build_from_pretrained(cls, pretrained_model_name_or_path, subfolder, torch_dtype, **kwargs)
+
     @property
     def dtype(self):
         return self.decoder.conv_out.conv.weight.dtype
