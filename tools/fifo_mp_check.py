@@ -1,0 +1,40 @@
+"""Developer / CI tool: the tiny pipeline's FIFO stage under torchrun with P ranks (NCCL boundary exchange, base-state
+broadcast) must reproduce the single-process latents bit for bit.
+usage: torchrun --nproc-per-node P tools/fifo_mp_check.py out.pt   (P = 1 writes the reference)"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from test_pipeline_gpu import _tiny_pipe  # noqa: E402
+from tokensgen_b200.fifo import broadcast_base_output, cogvideo_fifo_mp_v2  # noqa: E402
+
+world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+pipe = _tiny_pipe().to(dev)
+base = None
+if rank == 0:
+    g = torch.Generator().manual_seed(3)
+    frames = torch.rand(1, 36, 3, 64, 96, generator=g) * 2 - 1
+    base = pipe(frames=frames, prompt_embeds=torch.randn(1, 10, 128, generator=g), negative_prompt_embeds=torch.randn(1, 10, 128, generator=g),
+                height=64, width=96, num_frames_per_chunk=9, max_num_chunks=4, max_num_chunks_w_fifo=25, max_num_chunks_wo_fifo=1,
+                num_inference_steps=12, guidance_scale=6.0, generator=torch.Generator().manual_seed(11), vip_scale=[0.6],
+                sampling_mode="fifo", sampling_params={"num_partitions": 4}, output_type="latent", return_dict=False)
+    base.condition_frames = None
+else:
+    pipe.preprare_for_fifo(num_inference_steps=12, vip_scale=[0.6])
+base = broadcast_base_output(base, src=0, device=dev)
+orig, latents, _ = cogvideo_fifo_mp_v2([pipe], base, seed=11)
+if rank == 0:
+    torch.save(latents.cpu(), sys.argv[1])
+    print(f"world={world}: latents {tuple(latents.shape)} mean {latents.float().mean().item():.6f}")
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

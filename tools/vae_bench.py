@@ -1,0 +1,82 @@
+"""BASELINE.json configs[4]: 3D causal VAE decode throughput sweep, T_lat latent frames of 60x90 (-> 480x720), full-size
+CogVideoX VAE (random-init weights of the true shapes), one B200.  Also encode of one 49-frame clip.
+Prints one JSON line per point: ms, TFLOP/s of the conv kernels (algorithmic conv FLOPs / total time) and the per-op
+breakdown, against MEASURED_PEAKS.json.
+usage: python tools/vae_bench.py [T_lat ...]   (default 13 25 49)"""
+import json
+import os
+import re
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tokensgen_b200 import _ext as E  # noqa: E402
+from tokensgen_b200.vae import AutoencoderKLCogVideoX  # noqa: E402
+
+
+def conv_flops(tag: str) -> float:
+    m = re.match(r"vae_conv\[(\d+)x(\d+)x(\d+),(\d+)->(\d+),k(\d)(\d)(\d)s(\d)\]", tag)
+    t, h, w, cin, cout, kt, kh, kw, _ = (int(x) for x in m.groups())
+    return 2.0 * t * h * w * cin * cout * kt * kh * kw
+
+
+def run(fn, tiled):
+    torch.cuda.synchronize()
+    fn()  # warm-up (allocations, tensor maps)
+    torch.cuda.synchronize()
+    E.profile = {}
+    s, e = torch.cuda.Event(True), torch.cuda.Event(True)
+    s.record()
+    fn()
+    e.record()
+    torch.cuda.synchronize()
+    prof, E.profile = E.profile, None
+    ms = s.elapsed_time(e)
+    per = {}
+    flops = 0.0
+    for k, v in prof.items():
+        t = sum(a.elapsed_time(b) for a, b in v)
+        if k.startswith("vae_conv"):
+            flops += conv_flops(k) * len(v)
+            per["vae_conv"] = per.get("vae_conv", 0.0) + t
+        else:
+            per[k] = per.get(k, 0.0) + t
+    return ms, flops, {k: round(v, 2) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+
+
+def main():
+    frames = [int(a) for a in sys.argv[1:]] or [13, 25, 49]
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    torch.manual_seed(0)
+    vae = AutoencoderKLCogVideoX(scaling_factor=0.7)
+    for p in vae.parameters():
+        torch.nn.init.normal_(p, std=0.02)
+    vae = vae.to("cuda", torch.bfloat16).eval()
+    g = torch.Generator().manual_seed(42)
+    with torch.no_grad():
+        for tiled in (False, True):
+            vae.enable_tiling() if tiled else vae.disable_tiling()
+            for T in frames:
+                z = torch.randn(1, 16, T, 60, 90, generator=g).cuda().bfloat16()
+                ms, fl, per = run(lambda: vae.decode(z).sample, tiled)
+                px = (T - 1) * 4 + 1
+                print(json.dumps({"op": "decode", "tiled": tiled, "latent_frames": T, "pixel_frames": px, "ms": round(ms, 1),
+                                  "pixel_frames_per_s": round(px / ms * 1e3, 1), "conv_tflop": round(fl / 1e12, 1),
+                                  "tflops_whole_pass": round(fl / ms / 1e9, 1), "frac_of_sustained_peak": round(fl / ms / 1e9 / tf_peak, 3),
+                                  "conv_kernel_tflops": round(fl / per.get("vae_conv", ms) / 1e9, 1), "ms_by_op": per}), flush=True)
+                del z
+                if tiled:
+                    break
+        vae.disable_tiling()
+        x = (torch.rand(1, 3, 49, 480, 720, generator=g) * 2 - 1).cuda().bfloat16()
+        ms, fl, per = run(lambda: vae.encode(x).latent_dist.parameters, False)
+        print(json.dumps({"op": "encode", "tiled": False, "pixel_frames": 49, "ms": round(ms, 1), "conv_tflop": round(fl / 1e12, 1),
+                          "tflops_whole_pass": round(fl / ms / 1e9, 1), "conv_kernel_tflops": round(fl / per.get("vae_conv", ms) / 1e9, 1),
+                          "ms_by_op": per}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
