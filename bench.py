@@ -37,6 +37,25 @@ WORKLOAD = ("configs[1] To2V edit.yaml single clip: 13x30x45 latent window (49 f
             "CogVideoX-5b DiT 42 layers + video-IP-adapter (480 condensed tokens), one denoise step per bench step")
 
 
+def attn_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch of this shape, from the committed
+    `ncu --set full` capture summary (profiles/r01_attn3_full_summary.md); None if the summary is missing."""
+    import re
+    path = os.path.join(ROOT, "profiles", "r01_attn3_full_summary.md")
+    if not os.path.exists(path):
+        return None
+    txt = open(path).read()
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(r"\| " + re.escape(key) + r" \| ([0-9.]+) \| (\w+) \|", txt)
+        if not m:
+            return None
+        tot += float(m.group(1)) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[m.group(2)]
+    heads = re.search(r"self-attention, (\d+)x48 heads", txt)
+    scale = 2.0 / float(heads.group(1)) if heads else 1.0   # the capture may hold one CFG branch; a bench launch has two
+    return tot * scale
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -282,7 +301,9 @@ def run_ours(args):
                              "achieved": achieved, "peak": tf_sust * 1.0, "unit": "TFLOP/s", "frac": achieved / tf_sust,
                              "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                              "frac_of_burst_peak": achieved / tf_burst, "avg_launch_ms": avg_ms,
-                             "share_of_step": per[dom] / ms_step, "traffic": None},
+                             "share_of_step": per[dom] / ms_step, "traffic": attn_dram_traffic(),
+                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_attn3_full_summary.md)",
+                             "algorithmic_bytes": 4 * 2 * 48 * N * 64 * 2},
                 "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
                 "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:

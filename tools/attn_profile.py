@@ -1,4 +1,4 @@
-"""Small driver for ncu captures of the attention kernel (one batch of the full 17 776-token problem).
+"""Small driver for ncu captures of the attention kernel (the bench launch: CFG pair x 48 heads x 17 776 tokens).
 usage: attn_profile.py [heads] [impl] [emu] [stagger]"""
 import os
 import sys
@@ -17,10 +17,11 @@ if len(sys.argv) > 4:
     E.set_tuning("attn_stagger", int(sys.argv[4]))
 N = 17776
 torch.manual_seed(0)
-q = torch.randn(1, H, N, 64, device="cuda").bfloat16()
-k = torch.randn(1, H, N, 64, device="cuda").bfloat16()
-v = torch.randn(1, H, N, 64, device="cuda").bfloat16()
-out = torch.empty(1, N, H * 64, device="cuda", dtype=torch.bfloat16)
+B = 2
+q = torch.randn(B, H, N, 64, device="cuda").bfloat16()
+k = torch.randn(B, H, N, 64, device="cuda").bfloat16()
+v = torch.randn(B, H, N, 64, device="cuda").bfloat16()
+out = torch.empty(B, N, H * 64, device="cuda", dtype=torch.bfloat16)
 for _ in range(3):
     E.attn_fwd(q, k, v, out)
 torch.cuda.synchronize()
