@@ -89,7 +89,7 @@ def report(rep, title):
 launches()
 report("attn_full", "tg::attn_fwd_kernel (v1: 8 softmax warps) — self-attention, 1x48 heads x 17776^2 x 64")
 report("attn2_full", "tg::attn2_fwd_kernel (v2: 16 softmax warps) — self-attention, 1x48 heads x 17776^2 x 64")
-report("attn3_full", "tg::attn3_fwd_kernel (v3: lean waits, packed FMA-pipe exponentials 1/8, 112 softmax registers) — self-attention, 1x48 heads x 17776^2 x 64")
+report("attn3_full", "tg::attn3_fwd_kernel (v3: lean waits, packed FMA-pipe exponentials 1/8, 112 softmax registers) — self-attention, 2x48 heads x 17776^2 x 64")
 for extra in sys.argv[2:]:
     report(extra, extra)
 print(sorted(os.listdir(out_dir)))
