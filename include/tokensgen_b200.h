@@ -134,6 +134,17 @@ int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_ro
                 int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,
                 float out_scale, void* stream);
 
+/* K4 + K5 in ONE launch: out[q] = softmax(Q K^T * scale) V  +  out_scale2 * softmax(Q2 K2'^T * scale) V2' for the same
+ * q_rows query rows, where K2'/V2' are rows [kv_row0_2, kv_row0_2 + kv_rows2) of k2/v2.  This is the self-attention over
+ * [text; video] plus `hidden + scale * cross-attention to the vip tokens` of VideoIPAdapterCogVideoXAttnProcessor2_0
+ * (attention_processor.py:2066-2069 followed by :2117-2119,2126-2134): the second, short problem (480 keys) reuses the
+ * CTA's TMEM / barrier / K-V ring set-up and its result is added before the output row leaves the SM's cache.
+ * q,k,v: [B,H,rows_alloc,64] (rows 0..q_rows / 0..kv_rows used); q2,k2,v2: [B,H,rows_alloc2,64]; out: [B,out_rows_alloc,H*64]. */
+int tg_attn_fwd_pair(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
+                     const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
+                     int kv_rows2, tg_bf16* out, int64_t out_rows_alloc, int B, int H, float softmax_scale, float out_scale2,
+                     void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * K9/K11 index maps (bit-exact class).
  * tg_patchify: latents [B,F,C,H,W] -> rows [B*F*(H/p)*(W/p), C*p*p] in Conv2d weight order (c, pi, pj);

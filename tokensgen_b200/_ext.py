@@ -76,6 +76,7 @@ SYMBOLS = {
                                         C.POINTER(ModVec), _VP]),
     "tg_qkv_rope_gemm": (C.c_int, [_VP, _I64, _VP, _VP, _I, _I, _I, C.POINTER(RowMap), C.POINTER(QkvProj), _I, _F, _VP]),
     "tg_attn_fwd": (C.c_int, [_VP, _I64, _I64, _I, _VP, _VP, _I64, _I64, _I, _VP, _I64, _I64, _I, _I, _F, _I, _F, _VP]),
+    "tg_attn_fwd_pair": (C.c_int, [_VP, _VP, _VP, _I64, _I, _I, _VP, _VP, _VP, _I64, _I64, _I, _VP, _I64, _I, _I, _F, _F, _VP]),
     "tg_patchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "tg_unpatchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "tg_cfg_dpm_step": (C.c_int, [C.POINTER(DpmStepArgs), _VP]),
@@ -132,6 +133,8 @@ def load() -> C.CDLL:
             fn.argtypes = args
         if lib.tg_version() != 1:
             raise TokensGenError(f"ABI version mismatch: library reports {lib.tg_version()}")
+        if _os.environ.get("TG_GEMM_IMPL"):  # developer A/B switch: 1 = single-CTA tiles, 2 = CTA pairs (default)
+            lib.tg_set_gemm_impl(int(_os.environ["TG_GEMM_IMPL"]))
         _lib = lib
     return _lib
 
@@ -272,6 +275,21 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
                "tg_attn_fwd")
 
 
+def attn_fwd_pair(q, k, v, q_rows: int, kv_rows: int, q2, k2, v2, kv_row0_2: int, kv_rows2: int, out: torch.Tensor,
+                  out_scale2: float, softmax_scale: Optional[float] = None) -> None:
+    """Self-attention (q,k,v rows [0,q_rows)/[0,kv_rows)) + out_scale2 * cross-attention of q2 to rows
+    [kv_row0_2, +kv_rows2) of k2/v2, one launch (tg_attn_fwd_pair)."""
+    lib = load()
+    B, H, alloc, D = q.shape
+    alloc2 = q2.shape[2]
+    scale = D ** -0.5 if softmax_scale is None else softmax_scale
+    with _Timed(f"attn_fwd_pair[q{q_rows},kv{kv_rows}+kv{kv_rows2}]", 1):
+        _check(lib.tg_attn_fwd_pair(_bf16_cuda(q, "q").data_ptr(), _bf16_cuda(k, "k").data_ptr(), _bf16_cuda(v, "v").data_ptr(),
+                                    alloc, q_rows, kv_rows, _bf16_cuda(q2, "q2").data_ptr(), _bf16_cuda(k2, "k2").data_ptr(),
+                                    _bf16_cuda(v2, "v2").data_ptr(), alloc2, kv_row0_2, kv_rows2, _bf16_cuda(out, "out").data_ptr(),
+                                    out.shape[1], B, H, float(scale), float(out_scale2), _stream()), "tg_attn_fwd_pair")
+
+
 def patchify(latents: torch.Tensor, p: int) -> torch.Tensor:
     lib = load()
     B, F, Cc, H, W = latents.shape
@@ -374,7 +392,7 @@ def vae_group_stats(x: torch.Tensor, groups: int) -> torch.Tensor:
     Cc = x.shape[-1]
     pixels = x.numel() // Cc
     sums = torch.zeros(2 * groups, device=x.device, dtype=torch.float64)
-    with _Timed("vae_group_stats", 1):
+    with _Timed(f"vae_group_stats[{pixels}x{Cc}]", 1):
         _check(lib.tg_vae_group_stats(_bf16_cuda(x, "x").data_ptr(), pixels, Cc, Cc, groups, sums.data_ptr(), _stream()),
                "tg_vae_group_stats")
     return sums
@@ -395,7 +413,7 @@ def vae_norm_act(x: torch.Tensor, sums: torch.Tensor, groups: int, eps: float, g
     if not (out.is_cuda and out.dtype == torch.bfloat16 and out.stride(-1) == 1):
         raise TokensGenError("vae_norm_act: bad out")
     a.y, a.ldy = out.data_ptr(), out.stride(2)
-    with _Timed("vae_norm_act", 1):
+    with _Timed(f"vae_norm_act[{T * H * W}x{Cc}]", 1):
         _check(lib.tg_vae_norm_act(C.byref(a), _stream()), "tg_vae_norm_act")
 
 

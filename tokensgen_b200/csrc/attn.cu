@@ -40,6 +40,9 @@ struct AttnParams {
     int accumulate;
     float out_scale;
     long long* trace;  // developer timeline (tools/attn_trace.py): [16 softmax warps][n_blocks][6] clock64 stamps of CTA (0,0)
+    int n_pass;        // v3: 1, or 2 = a second (Q2, K2, V2) problem over the same query rows, accumulated into the same output
+    int kv_rows2;      // v3 pass 1
+    float out_scale2;  // v3 pass 1: out += out_scale2 * attn2
     int mutex;    // v2: the two tiles take turns on the MUFU pipe (named-barrier hand-off) instead of sharing it
     int stagger;  // v2: cycles by which tile 1 starts after tile 0 (keeps the two tiles' softmax phases interleaved)
 };
@@ -723,7 +726,9 @@ __device__ __forceinline__ constexpr bool a3_emulated(int pair) {  // EMU8 of ev
 template <int EMU8, bool ALT>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
+                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q2,
+                 const __grid_constant__ CUtensorMap tmap_k2, const __grid_constant__ CUtensorMap tmap_v2,
+                 const __grid_constant__ AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t q_smem = smem_base;
@@ -738,7 +743,8 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     auto o_done = [&](int t) { return bar_base + 8u * (5 + 2 * AT_STAGES + t); };
     auto s_free = [&](int t) { return bar_base + 8u * (7 + 2 * AT_STAGES + t); };
     auto turn = [&](int t, int q) { return bar_base + 8u * (9 + 2 * AT_STAGES + t * 4 + q); };
-    const uint32_t tmem_slot = bar_base + 8u * (17 + 2 * AT_STAGES);
+    const uint32_t q_empty = bar_base + 8u * (17 + 2 * AT_STAGES);  // the pass's last QK^T has read Q: the next pass may load its Q
+    const uint32_t tmem_slot = bar_base + 8u * (18 + 2 * AT_STAGES);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -746,15 +752,26 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const int lane = threadIdx.x & 31;
     const int bh = blockIdx.y;
     const int q0 = blockIdx.x * (2 * AT_BLOCK_Q);
-    const int n_blocks = (p.kv_rows + AT_BLOCK_KV - 1) / AT_BLOCK_KV;
+    // Up to two passes over the SAME query rows in one CTA (tg_attn_fwd_pair): pass 0 = (Q, K, V), pass 1 = (Q2, K2, V2)
+    // accumulated into the same output rows — the self-attention and the text/video -> vip cross-attention of the
+    // video-IP-adapter processor.  TMEM, barriers and the K/V ring are set up once; barrier parities run on the cumulative
+    // block index g.
+    const int n_pass = p.n_pass;
+    auto pass_blocks = [&](int pass) { return ((pass == 0 ? p.kv_rows : p.kv_rows2) + AT_BLOCK_KV - 1) / AT_BLOCK_KV; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_k);
         tma_prefetch_desc(&tmap_v);
+        if (n_pass > 1) {
+            tma_prefetch_desc(&tmap_q2);
+            tma_prefetch_desc(&tmap_k2);
+            tma_prefetch_desc(&tmap_v2);
+        }
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
+        mbar_init(q_empty, 2);
         for (int s = 0; s < AT_STAGES; ++s) {
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 2);
@@ -782,20 +799,27 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (warp == 0) {
             // -------------------------------------------------------------- TMA producer
             if (lane == 0) {
-                mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
-                tma_load_3d(q_smem, &tmap_q, q_full, 0, q0, bh);
-                tma_load_3d(q_smem + AT_TILE_BYTES, &tmap_q, q_full, 0, q0 + AT_BLOCK_Q, bh);
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int j = 0; j < n_blocks; ++j) {
-                    mbar_wait_fast(kv_empty(stage), phase ^ 1u);
-                    const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
-                    mbar_arrive_expect_tx(kv_full(stage), 2 * AT_TILE_BYTES);
-                    tma_load_3d(ks, &tmap_k, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
-                    tma_load_3d(ks + AT_TILE_BYTES, &tmap_v, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
-                    if (++stage == AT_STAGES) {
-                        stage = 0;
-                        phase ^= 1u;
+                for (int pass = 0; pass < n_pass; ++pass) {
+                    const CUtensorMap* mq = pass == 0 ? &tmap_q : &tmap_q2;
+                    const CUtensorMap* mk = pass == 0 ? &tmap_k : &tmap_k2;
+                    const CUtensorMap* mv = pass == 0 ? &tmap_v : &tmap_v2;
+                    if (pass > 0) mbar_wait_fast(q_empty, uint32_t((pass - 1) & 1));
+                    mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+                    tma_load_3d(q_smem, mq, q_full, 0, q0, bh);
+                    tma_load_3d(q_smem + AT_TILE_BYTES, mq, q_full, 0, q0 + AT_BLOCK_Q, bh);
+                    const int nb = pass_blocks(pass);
+                    for (int j = 0; j < nb; ++j) {
+                        mbar_wait_fast(kv_empty(stage), phase ^ 1u);
+                        const uint32_t ks = kv_smem + stage * 2 * AT_TILE_BYTES;
+                        mbar_arrive_expect_tx(kv_full(stage), 2 * AT_TILE_BYTES);
+                        tma_load_3d(ks, mk, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                        tma_load_3d(ks + AT_TILE_BYTES, mv, kv_full(stage), 0, j * AT_BLOCK_KV, bh);
+                        if (++stage == AT_STAGES) {
+                            stage = 0;
+                            phase ^= 1u;
+                        }
                     }
                 }
             }
@@ -826,32 +850,39 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         umma_ts(o_t, p_t + uint32_t(k * 8), db, idesc_pv, (first && k == 0) ? 0u : 1u);
                     }
                 };
-                mbar_wait_fast(q_full, 0);
-                mbar_wait_fast(kv_full(0), 0);
-                tc_fence_after();
-                issue_qk(0);
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int j = 0; j < n_blocks; ++j) {
-                    int nstage = stage + 1;
-                    uint32_t nphase = phase;
-                    if (nstage == AT_STAGES) {
-                        nstage = 0;
-                        nphase ^= 1u;
-                    }
-                    if (j + 1 < n_blocks) {
-                        mbar_wait_fast(bar_sfree, uint32_t(j & 1));  // S_t(j) is in registers: overwrite it
-                        mbar_wait_fast(kv_full(nstage), nphase);
-                        tc_fence_after();
-                        issue_qk(nstage);
-                    }
-                    mbar_wait_fast(bar_pfull, uint32_t(j & 1));
+                int g = 0;  // cumulative block index over the passes
+                for (int pass = 0; pass < n_pass; ++pass) {
+                    const int nb = pass_blocks(pass);
+                    mbar_wait_fast(q_full, uint32_t(pass & 1));
+                    if (g > 0) mbar_wait_fast(bar_sfree, uint32_t((g - 1) & 1));  // the previous pass's last S_t is in registers
+                    mbar_wait_fast(kv_full(stage), phase);
                     tc_fence_after();
-                    issue_pv(stage, j == 0);
-                    umma_commit(kv_empty(stage));
-                    umma_commit(bar_odone);
-                    stage = nstage;
-                    phase = nphase;
+                    issue_qk(stage);
+                    if (nb == 1) umma_commit(q_empty);
+                    for (int j = 0; j < nb; ++j, ++g) {
+                        int nstage = stage + 1;
+                        uint32_t nphase = phase;
+                        if (nstage == AT_STAGES) {
+                            nstage = 0;
+                            nphase ^= 1u;
+                        }
+                        if (j + 1 < nb) {
+                            mbar_wait_fast(bar_sfree, uint32_t(g & 1));  // S_t(j) is in registers: overwrite it
+                            mbar_wait_fast(kv_full(nstage), nphase);
+                            tc_fence_after();
+                            issue_qk(nstage);
+                            if (j + 2 == nb) umma_commit(q_empty);  // the pass's last QK^T is in flight: Q may be replaced when it lands
+                        }
+                        mbar_wait_fast(bar_pfull, uint32_t(g & 1));
+                        tc_fence_after();
+                        issue_pv(stage, j == 0);
+                        umma_commit(kv_empty(stage));
+                        umma_commit(bar_odone);
+                        stage = nstage;
+                        phase = nphase;
+                    }
                 }
             }
         }
@@ -887,12 +918,17 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const float inv_c = 1.0f / c;
         const uint64_t c2 = pack_f32x2(c, c);
         constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
+        int g = 0;   // cumulative block index over the passes (mbarrier parities)
+        int xg = 0;  // exchange-slot parity: advances with every use of the pair's shared-memory slots
+        for (int pass = 0; pass < n_pass; ++pass) {
+        const int n_blocks = pass_blocks(pass);
+        const int kv_rows = pass == 0 ? p.kv_rows : p.kv_rows2;
         float mc = 0.f;    // reference max in log2 units, integer-valued
         float smin = 0.f;  // scores below this are clamped before an emulated exponential (2^-126)
         float l = 0.f;
 
-        for (int j = 0; j < n_blocks; ++j) {
-            mbar_wait_fast(bar_sfull, uint32_t(j & 1));
+        for (int j = 0; j < n_blocks; ++j, ++g) {
+            mbar_wait_fast(bar_sfull, uint32_t(g & 1));
             tc_fence_after();
             uint32_t r[64];
             {
@@ -905,7 +941,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_sfree);
-            const int valid = p.kv_rows - j * AT_BLOCK_KV - half * 64;
+            const int valid = kv_rows - j * AT_BLOCK_KV - half * 64;
             if (valid < 64) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
@@ -921,7 +957,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     pm[k] = fmaxf(pm[k], fmaxf(__uint_as_float(r[i + 2 * k]), __uint_as_float(r[i + 2 * k + 1])));
             float mx = fmaxf(fmaxf(pm[0], pm[1]), fmaxf(pm[2], pm[3]));
             {
-                const uint32_t par = uint32_t(j & 1) * 2048u;
+                const uint32_t par = uint32_t(xg++ & 1) * 2048u;
                 sts_f32(xs_mine + par, mx);
                 named_bar_sync(pair_bar, 64);
                 mx = fmaxf(mx, lds_f32(xs_other + par));
@@ -933,7 +969,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             } else {
                 const bool need = fmaf(mx, c, -mc) > 8.0f;
                 if (__any_sync(0xffffffffu, need)) {
-                    mbar_wait_fast(bar_odone, uint32_t((j - 1) & 1));
+                    mbar_wait_fast(bar_odone, uint32_t((g - 1) & 1));
                     tc_fence_after();
                     waited = true;
                     float alpha = 1.0f;
@@ -956,7 +992,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const float Kf = MAGIC - mc;
             const uint64_t K2 = pack_f32x2(Kf, Kf);
             uint64_t ps2[4] = {0ull, 0ull, 0ull, 0ull};
-            if (ALT && (j > 0 || t == 1)) mbar_wait_fast(bar_my_turn, uint32_t((t == 1 ? j : j - 1) & 1));
+            if (ALT && (g > 0 || t == 1)) mbar_wait_fast(bar_my_turn, uint32_t((t == 1 ? g : g - 1) & 1));
             // exponentials: a pure FFMA2 / MUFU.EX2 / FADD2 stream (nothing in it waits on a MUFU result except the row sum)
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
@@ -996,7 +1032,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #pragma unroll
             for (int i = 0; i < 32; ++i) pk[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1]));
             if (j > 0 && !waited) {  // PV_t(j-1) must have read P_t before it is overwritten (long done by now)
-                mbar_wait_fast(bar_odone, uint32_t((j - 1) & 1));
+                mbar_wait_fast(bar_odone, uint32_t((g - 1) & 1));
                 tc_fence_after();
             }
             tmem_st32(p_addr, pk);
@@ -1010,20 +1046,22 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 
         // ---- epilogue: O / l -> global (this thread: 32 of the row's 64 output columns)
         {
-            const uint32_t par = uint32_t(n_blocks & 1) * 2048u;
+            const uint32_t par = uint32_t(xg++ & 1) * 2048u;
             sts_f32(xs_mine + par, l);
             named_bar_sync(pair_bar, 64);
             l += lds_f32(xs_other + par);
         }
-        mbar_wait_fast(bar_odone, uint32_t((n_blocks - 1) & 1));
+        mbar_wait_fast(bar_odone, uint32_t((g - 1) & 1));
         tc_fence_after();
         const float inv_l = 1.0f / l;
+        const bool accumulate = pass == 0 ? (p.accumulate != 0) : true;
+        const float out_scale = pass == 0 ? p.out_scale : p.out_scale2;
         const bool store = q_row < p.q_rows;
         const int b = bh / p.H, h = bh - b * p.H;
         __nv_bfloat16* o_ptr =
             p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D + half * 32;
         uint4 prev[4];
-        if (store && p.accumulate) {
+        if (store && accumulate) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) prev[i] = reinterpret_cast<const uint4*>(o_ptr)[i];
         }
@@ -1036,12 +1074,12 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 float f[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) f[k] = __uint_as_float(ro[i + k]) * inv_l;
-                if (p.accumulate) {
+                if (accumulate) {
                     const uint4 old = prev[i / 8];
-                    f[0] = fmaf(p.out_scale, f[0], bf16_lo(old.x)); f[1] = fmaf(p.out_scale, f[1], bf16_hi(old.x));
-                    f[2] = fmaf(p.out_scale, f[2], bf16_lo(old.y)); f[3] = fmaf(p.out_scale, f[3], bf16_hi(old.y));
-                    f[4] = fmaf(p.out_scale, f[4], bf16_lo(old.z)); f[5] = fmaf(p.out_scale, f[5], bf16_hi(old.z));
-                    f[6] = fmaf(p.out_scale, f[6], bf16_lo(old.w)); f[7] = fmaf(p.out_scale, f[7], bf16_hi(old.w));
+                    f[0] = fmaf(out_scale, f[0], bf16_lo(old.x)); f[1] = fmaf(out_scale, f[1], bf16_hi(old.x));
+                    f[2] = fmaf(out_scale, f[2], bf16_lo(old.y)); f[3] = fmaf(out_scale, f[3], bf16_hi(old.y));
+                    f[4] = fmaf(out_scale, f[4], bf16_lo(old.z)); f[5] = fmaf(out_scale, f[5], bf16_hi(old.z));
+                    f[6] = fmaf(out_scale, f[6], bf16_lo(old.w)); f[7] = fmaf(out_scale, f[7], bf16_hi(old.w));
                 }
                 uint4 v;
                 v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
@@ -1049,6 +1087,8 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 reinterpret_cast<uint4*>(o_ptr + i)[0] = v;
             }
         }
+        tc_fence_before();  // O_t is in registers: the next pass may overwrite it
+        }  // pass
     }
 
     tc_fence_before();
@@ -1083,7 +1123,7 @@ static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const
 
 template <int EMU8, bool ALT>
 static int launch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-                        const AttnParams& p) {
+                        const CUtensorMap& tq2, const CUtensorMap& tk2, const CUtensorMap& tv2, const AttnParams& p) {
     static bool attr_set = false;
     auto kern = attn3_fwd_kernel<EMU8, ALT>;
     if (!attr_set) {
@@ -1091,9 +1131,12 @@ static int launch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const
         if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    kern<<<grid, A3_THREADS, A3_SMEM_BYTES, st>>>(tq, tk, tv, p);
+    kern<<<grid, A3_THREADS, A3_SMEM_BYTES, st>>>(tq, tk, tv, tq2, tk2, tv2, p);
     return check_launch("attn_fwd");
 }
+
+static int dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                          const CUtensorMap& tq2, const CUtensorMap& tk2, const CUtensorMap& tv2, const AttnParams& p);
 
 }  // namespace tg
 
@@ -1133,6 +1176,7 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.accumulate = accumulate;
     p.out_scale = out_scale;
+    p.n_pass = 1;
     p.stagger = g_attn_stagger;
     p.trace = g_attn_trace;
     p.mutex = g_attn_mutex;
@@ -1144,16 +1188,7 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     }
     dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (g_attn_impl == 3) {
-#define TG_A3(E)                                                                                  \
-    case E:                                                                                       \
-        return g_attn_alt ? launch_attn3<E, true>(grid, st, tq, tk, tv, p) : launch_attn3<E, false>(grid, st, tq, tk, tv, p);
-        switch (g_attn_emu) {
-            TG_A3(0) TG_A3(1) TG_A3(2) TG_A3(3) TG_A3(4)
-            default: return fail(-7, "attn_fwd: attn_emu must be 0..4 (eighths of the exponentials on the FMA pipe)");
-        }
-#undef TG_A3
-    }
+    if (g_attn_impl == 3) return dispatch_attn3(grid, st, tq, tk, tv, tq, tk, tv, p);
     if (g_attn_impl == 2) {
         if (g_attn_trace != nullptr) return launch_attn2<0, false, true, false>(grid, st, tq, tk, tv, p);
         return g_attn_packed ? launch_attn2<0, false, false, true>(grid, st, tq, tk, tv, p)
@@ -1161,6 +1196,64 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     }
     attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd");
+}
+
+static int tg::dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                              const CUtensorMap& tq2, const CUtensorMap& tk2, const CUtensorMap& tv2, const AttnParams& p) {
+#define TG_A3(E)                                                                                      \
+    case E:                                                                                           \
+        return g_attn_alt ? launch_attn3<E, true>(grid, st, tq, tk, tv, tq2, tk2, tv2, p)             \
+                          : launch_attn3<E, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);
+    switch (g_attn_emu) {
+        TG_A3(0) TG_A3(1) TG_A3(2) TG_A3(3) TG_A3(4)
+        default: return fail(-7, "attn_fwd: attn_emu must be 0..4 (eighths of the exponentials on the FMA pipe)");
+    }
+#undef TG_A3
+}
+
+extern "C" int tg_attn_fwd_pair(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
+                                const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
+                                int kv_rows2, tg_bf16* out, int64_t out_rows_alloc, int B, int H, float softmax_scale,
+                                float out_scale2, void* stream) {
+    if (!q || !k || !v || !q2 || !k2 || !v2 || !out) return fail(-1, "attn_fwd_pair: null pointer");
+    if (B <= 0 || H <= 0 || q_rows <= 0 || kv_rows <= 0 || kv_rows2 <= 0) return fail(-2, "attn_fwd_pair: non-positive shape");
+    if (q_rows > rows_alloc || kv_rows > rows_alloc || q_rows > rows_alloc2 || kv_row0_2 < 0 || kv_row0_2 + kv_rows2 > rows_alloc2)
+        return fail(-3, "attn_fwd_pair: row window outside the allocation");
+    if (q_rows > out_rows_alloc) return fail(-4, "attn_fwd_pair: output window outside the allocation");
+    if ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) | reinterpret_cast<uintptr_t>(v) |
+         reinterpret_cast<uintptr_t>(q2) | reinterpret_cast<uintptr_t>(k2) | reinterpret_cast<uintptr_t>(v2) |
+         reinterpret_cast<uintptr_t>(out)) & 15)
+        return fail(-5, "attn_fwd_pair: pointers must be 16-byte aligned");
+    const int BH = B * H;
+    if (BH > 65535) return fail(-6, "attn_fwd_pair: B*H too large");
+    if (g_attn_impl != 3) return fail(-8, "attn_fwd_pair: needs attention kernel generation 3");
+    CUtensorMap tq, tk, tv, tq2, tk2, tv2;
+    int rc;
+    auto mk = [&](CUtensorMap* m, const tg_bf16* base, int64_t row0, int rows, int64_t alloc, int box_rows) {
+        return make_tmap_3d(m, base + row0 * AT_D, AT_D, uint64_t(rows), uint64_t(BH), AT_D * 2, uint64_t(alloc) * AT_D * 2, AT_D,
+                            box_rows);
+    };
+    if ((rc = mk(&tq, q, 0, q_rows, rows_alloc, AT_BLOCK_Q))) return rc;
+    if ((rc = mk(&tk, k, 0, kv_rows, rows_alloc, AT_BLOCK_KV))) return rc;
+    if ((rc = mk(&tv, v, 0, kv_rows, rows_alloc, AT_BLOCK_KV))) return rc;
+    if ((rc = mk(&tq2, q2, 0, q_rows, rows_alloc2, AT_BLOCK_Q))) return rc;
+    if ((rc = mk(&tk2, k2, kv_row0_2, kv_rows2, rows_alloc2, AT_BLOCK_KV))) return rc;
+    if ((rc = mk(&tv2, v2, kv_row0_2, kv_rows2, rows_alloc2, AT_BLOCK_KV))) return rc;
+    AttnParams p{};
+    p.q_rows = q_rows;
+    p.kv_rows = kv_rows;
+    p.H = H;
+    p.out = reinterpret_cast<__nv_bfloat16*>(out);
+    p.out_rows_alloc = out_rows_alloc;
+    p.out_row0 = 0;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
+    p.accumulate = 0;
+    p.out_scale = 1.0f;
+    p.n_pass = 2;
+    p.kv_rows2 = kv_rows2;
+    p.out_scale2 = out_scale2;
+    dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
+    return dispatch_attn3(grid, static_cast<cudaStream_t>(stream), tq, tk, tv, tq2, tk2, tv2, p);
 }
 
 extern "C" int tg_debug_attn_trace(void* device_buffer) {  // developer hook, not in the public header

@@ -392,7 +392,204 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
 }
 
+// =====================================================================================================================
+// CTA-pair GEMM (cta_group::2): one 2-CTA cluster = one 256 x 256 output tile.  CTA r of the pair loads A rows
+// [128 r, 128 r + 128) and W rows (output columns) [128 r, 128 r + 128) of the tile — 32 KB per 64-deep k-block instead of
+// the 48 KB a single-CTA 128 x 256 tile needs — and the leader's one MMA thread issues tcgen05.mma.cta_group::2
+// (M = 256, N = 256): each SM's tensor core reads its own A half and BOTH W halves (the peer's over the pair link) and
+// accumulates its 128 rows x 256 columns in its own TMEM.  Fewer operand bytes per flop through L2 / TMA / shared
+// memory is what this buys on a power-capped part.
+//   full barrier   (leader only) : leader's expect_tx covers both CTAs' 2 x 32 KB; the peer's TMA completes on it remotely
+//   empty barrier  (both CTAs)   : leader's tcgen05.commit multicast -> each CTA's producer refills its own half
+//   tmem full      (both CTAs)   : commit multicast -> each CTA's epilogue warps drain their own 128 rows
+//   tmem empty     (leader only) : 4 local + 4 remote arrivals (the peer's epilogue warps arrive through the cluster)
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = 128 * BLOCK_K * 2;  // 16 KB
+constexpr int G2_B_BYTES = 128 * BLOCK_K * 2;  // 16 KB (this CTA's half of the 256 output columns)
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + G2_STAGES * G2_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (G2_STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * G2_STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * G2_STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_tiles = p.m_tiles * p.n_tiles;  // 256 x 256 tiles
+    const int k_blocks = p.K / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < G2_STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 8);  // 4 epilogue warps of each CTA of the pair
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync();  // barrier inits and the TMEM allocation of both CTAs are visible pair-wide
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------ TMA producer (both CTAs; bytes land on the LEADER's full barrier)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                int mt, nt;
+                tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u, 0x181);
+                    const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
+                    const uint32_t bar = mapa_shared(full_bar(stage), 0);
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * G2_STAGE_BYTES);
+                    tma_load_2d_2cta(sa, &tmap_a, bar, kb * BLOCK_K, mt * 256 + int(rank) * 128);
+                    tma_load_2d_2cta(sa + G2_A_BYTES, &tmap_b, bar, kb * BLOCK_K, nt * 256 + int(rank) * 128);
+                    if (++stage == G2_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, 256, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x182);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * 256);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x183);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * G2_STAGE_BYTES;
+                    const uint32_t sb = sa + G2_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t da = make_smem_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
+                        const uint64_t db = make_smem_desc_sw128(sb + k * UMMA_K * 2, 16, 1024);
+                        umma_ss_2cta(d_tmem, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit_2cta(empty_bar(stage), 0b11);  // both CTAs' smem slots are free once these MMAs have read them
+                    if (++stage == G2_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_2cta(tfull_bar(acc), 0b11);  // both CTAs' accumulator halves are complete
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------ epilogue (both CTAs, each its own 128 rows x 256 columns)
+        const int ew = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+            int mt, nt;
+            tile_coords(tile, p.m_tiles, p.n_tiles, mt, nt);
+            const int row = mt * 256 + int(rank) * 128 + ew * 32 + lane;
+            mbar_wait(tfull_bar(acc), acc_phase, 0x184);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 256);
+            if constexpr (EPI == EPI_QKV) {
+#pragma unroll 1
+                for (int c = 0; c < 256; c += 64) {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_row + c, r0);
+                    tmem_ld32(t_row + c + 32, r1);
+                    tmem_wait_ld();
+                    float accv[64];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        accv[i] = __uint_as_float(r0[i]);
+                        accv[32 + i] = __uint_as_float(r1[i]);
+                    }
+                    epi_qkv(p, accv, row, nt * 256 + c);
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < 256; c += 32) {
+                    uint32_t r0[32];
+                    tmem_ld32(t_row + c, r0);
+                    tmem_wait_ld();
+                    float accv[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) accv[i] = __uint_as_float(r0[i]);
+                    if constexpr (EPI == EPI_BIAS_ACT)
+                        epi_bias_act(p, accv, row, nt * 256 + c);
+                    else
+                        epi_gate_residual(p, accv, row, nt * 256 + c);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();  // neither CTA may free TMEM or exit while the other still reads its shared memory / signals its barriers
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
 // ------------------------------------------------------------------------------------------- host side
+static int g_gemm_impl = 2;  // 1 = single-CTA 128 x BLOCK_N tiles, 2 = CTA pairs (256 x 256) where the shape allows
+
+template <int EPI>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+    auto kern = gemm2_kernel<EPI>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "gemm2: cudaFuncSetAttribute(smem=%d): %s", G2_SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = p.m_tiles * p.n_tiles;
+    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    kern<<<2 * clusters, 256, G2_SMEM_BYTES, stream>>>(ta, tb, p);
+    return check_launch("gemm2");
+}
+
 template <int BLOCK_N, int EPI>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N>;
@@ -422,6 +619,16 @@ static int check_common(const void* A, int64_t lda, const void* W, int M, int N,
 
 template <int EPI>
 static int dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W, GemmParams& p, cudaStream_t stream) {
+    if (g_gemm_impl == 2 && p.N % 256 == 0 && p.M >= 256) {
+        p.m_tiles = (p.M + 255) / 256;
+        p.n_tiles = p.N / 256;
+        CUtensorMap ta, tb;
+        int rc = make_tmap_2d(&ta, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, BLOCK_K, 128);
+        if (rc) return rc;
+        rc = make_tmap_2d(&tb, W, uint64_t(p.K), uint64_t(p.N), uint64_t(p.K) * 2, BLOCK_K, 128);
+        if (rc) return rc;
+        return launch_gemm2<EPI>(ta, tb, p, stream);
+    }
     const int bn = (EPI == EPI_QKV) ? 256 : (p.N % 256 == 0 ? 256 : (p.N % 128 == 0 ? 128 : 64));
     p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = p.N / bn;
@@ -532,4 +739,10 @@ extern "C" int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W,
     }
     return dispatch<EPI_QKV>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
                              p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_set_gemm_impl(int impl) {  // developer hook (1 = single-CTA tiles, 2 = CTA pairs); not in the public header
+    if (impl != 1 && impl != 2) return tg::fail(-1, "gemm impl must be 1 or 2");
+    tg::g_gemm_impl = impl;
+    return 0;
 }

@@ -247,21 +247,48 @@ def _attention_core(attn, proc, y, B, rowmap, rope, img_rope, cond_rope, bufs):
     projs = _qkv_projs(attn, proc, bufs.qkv, n_tv, rope, img_rope, cond_rope)
     E.qkv_rope_gemm(y, w, b, B, H, rowmap, projs, eps)
     qb, kb, vb = bufs.qkv[:3]
-    E.attn_fwd(qb, kb, vb, bufs.A, out_row0=0)
-    if proc is not None:
+    side = None
+    if proc is not None and _SIDE_STREAM:
+        # K6 (480 vip queries x 18 256 keys: 192 CTAs, 1.3 waves on 148 SMs) is independent of K4/K5 — it writes other rows
+        # of A — so it runs on a side stream and its CTAs fill the SMs the self-attention's last wave leaves idle.
         qv, kv, vv = bufs.qkv[3:]
+        main = torch.cuda.current_stream()
+        side = bufs.side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
+    scales = None
+    if proc is not None:
         scale = proc.scale
         scales = [float(s) for s in (scale if isinstance(scale, (list, tuple)) else [scale])]
         if len(scales) != B:
             scales = [scales[0]] * B  # attention_processor.py:2130-2131
-        if len(set(scales)) == 1:
+    if scales is not None and len(set(scales)) == 1 and _FUSE_PAIR:
+        qv, kv, vv = bufs.qkv[3:]   # K4 + K5 in one launch
+        E.attn_fwd_pair(qb, kb, vb, n_tv, n_tv, qv, kv, vv, n_tv, rowmap.n_vip, bufs.A, _bf16_scalar(scales[0]))
+    else:
+        E.attn_fwd(qb, kb, vb, bufs.A, out_row0=0)
+    if proc is not None:
+        qv, kv, vv = bufs.qkv[3:]
+        if len(set(scales)) == 1 and _FUSE_PAIR:
+            pass
+        elif len(set(scales)) == 1:
             E.attn_fwd(qv, kv, vv, bufs.A, q_row0=0, q_rows=n_tv, kv_row0=n_tv, kv_rows=rowmap.n_vip, out_row0=0,
                        accumulate=True, out_scale=_bf16_scalar(scales[0]))
         else:
             for bi, s in enumerate(scales):
                 E.attn_fwd(qv[bi:bi + 1], kv[bi:bi + 1], vv[bi:bi + 1], bufs.A[bi:bi + 1], q_row0=0, q_rows=n_tv,
                            kv_row0=n_tv, kv_rows=rowmap.n_vip, out_row0=0, accumulate=True, out_scale=_bf16_scalar(s))
-        E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
+        if side is None:
+            E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
+        else:
+            torch.cuda.current_stream().wait_stream(side)
+
+
+# Both measured neutral on the power-capped step (839.8 ms either way, profiles/r01_energy.md): off by default so that the
+# per-kernel event timings of bench.py stay one kernel per stream.
+_SIDE_STREAM = os.environ.get("TG_SIDE_STREAM", "0") != "0"
+_FUSE_PAIR = os.environ.get("TG_FUSE_PAIR", "0") != "0"
 
 
 class _Buffers:
@@ -277,6 +304,7 @@ class _Buffers:
         self.qkv = [torch.empty(B, H, n_tv, 64, **bf) for _ in range(3)]
         if use_vip:
             self.qkv += [torch.empty(B, H, rows, 64, **bf) for _ in range(3)]
+        self.side_stream = torch.cuda.Stream(device=device) if torch.device(device).type == "cuda" else None
 
 
 def _run_attention(attn, proc, hidden_states, encoder_hidden_states, rope, img_rope, cond_rope):

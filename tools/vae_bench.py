@@ -36,14 +36,27 @@ def run(fn, tiled):
     ms = s.elapsed_time(e)
     per = {}
     flops = 0.0
+    hbm = {"vae_norm_act": [0.0, 0.0], "vae_group_stats": [0.0, 0.0]}   # [algorithmic bytes, ms]
     for k, v in prof.items():
         t = sum(a.elapsed_time(b) for a, b in v)
         if k.startswith("vae_conv"):
             flops += conv_flops(k) * len(v)
             per["vae_conv"] = per.get("vae_conv", 0.0) + t
+        elif k.startswith(("vae_norm_act[", "vae_group_stats[")):
+            name = k.split("[")[0]
+            px, c = (int(x) for x in k.split("[")[1].rstrip("]").split("x"))
+            hbm[name][0] += (2 if name == "vae_norm_act" else 1) * px * c * 2.0 * len(v)   # read (+ write) of the bf16 activation
+            hbm[name][1] += t
+            per[name] = per.get(name, 0.0) + t
+        elif k.startswith("gemm_bias_act"):
+            per["gemm_1x1"] = per.get("gemm_1x1", 0.0) + t
         else:
             per[k] = per.get(k, 0.0) + t
-    return ms, flops, {k: round(v, 2) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+    out = {k: round(v, 2) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
+    for name, (b, t) in hbm.items():
+        if t > 0:
+            out[name + "_GBps"] = round(b / t / 1e6, 0)
+    return ms, flops, out
 
 
 def main():
