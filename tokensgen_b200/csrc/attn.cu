@@ -1100,7 +1100,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 static int g_attn_impl = 3;  // 1 = v1 (8 softmax warps), 2 = v2 (16), 3 = v3 (16, alternating tiles)
-static int g_attn_emu = 1;   // v3: eighths of the exponentials evaluated on the FMA pipe
+static int g_attn_emu = 0;   // v3: eighths of the exponentials evaluated on the FMA pipe (1 is ~2 % faster in a burst, 0 wins at the power cap)
 static int g_attn_stagger = 0;
 static long long* g_attn_trace = nullptr;
 static int g_attn_mutex = 0;

@@ -74,7 +74,19 @@ cases = [("self-attention 2x48x17776^2 (7.77 TFLOP)", lambda: E.attn_fwd(q, k, v
          ("FF1 GEMM + GELU 36512x12288x3072 (2.76 TFLOP)", lambda: E.gemm_bias_act(a, w1, b1, hbuf, act=E.ACT_GELU_TANH), 2.757),
          ("FF2 GEMM + gate residual 36512x3072x12288 (2.76 TFLOP)", lambda: E.gemm_gate_residual(hbuf, w2, b2, x, B, rm, gate), 2.757),
          ("LN + modulate 36512x3072 (0.45 GB)", lambda: E.ln_modulate(x, y, B, rm, lnw, lnb, lnw, lnb, 1e-5, shift, scale), 0.0)]
-for name, fn, tflop in cases:
+if len(sys.argv) > 1 and sys.argv[1] == "attn":   # sustained comparison of attention settings: impl:emu ...
+    cases = []
+    for spec in sys.argv[2:]:
+        impl, emu = (int(t) for t in spec.split(":"))
+
+        def fn(impl=impl, emu=emu):
+            E.attn_fwd(q, k, v, o)
+        cases.append((f"self-attention impl={impl} emu={emu}", fn, 7.766, (impl, emu)))
+else:
+    cases = [c + (None,) for c in cases]
+for name, fn, tflop, tune in cases:
+    if tune is not None:
+        E.set_tuning("attn_impl", tune[0]); E.set_tuning("attn_emu", tune[1] if tune[0] == 3 else 0)
     ms, clk, pw = sample(fn)
     extra = f"  {tflop / ms * 1e3:7.1f} TFLOP/s  {pw * ms / 1e3 / tflop:6.3f} J/TFLOP" if tflop else ""
     print(f"{name:58s} {ms:8.3f} ms  {clk:6.0f} MHz  {pw:6.0f} W  {pw * ms / 1e3:7.3f} J/call{extra}", flush=True)

@@ -207,7 +207,7 @@ def run_attn():
         E.set_tuning("attn_packed", packed)
         E.set_tuning("attn_alt", alt)
         ok &= run_attn_variant(full_ref=(impl, emu, packed, alt) == variants[-1])
-    E.set_tuning("attn_impl", 3); E.set_tuning("attn_emu", 1); E.set_tuning("attn_alt", 0)
+    E.set_tuning("attn_impl", 3); E.set_tuning("attn_emu", 0); E.set_tuning("attn_alt", 0)
     return ok
 
 
