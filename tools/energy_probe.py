@@ -82,6 +82,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "attn":   # sustained comparison of atte
         def fn(impl=impl, emu=emu):
             E.attn_fwd(q, k, v, o)
         cases.append((f"self-attention impl={impl} emu={emu}", fn, 7.766, (impl, emu)))
+    cases.append(("torch SDPA (library kernel, same tensors)", lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), 7.766, None))
+    a8 = torch.randn(8192, 8192, device=dev).bfloat16()
+    b8 = torch.randn(8192, 8192, device=dev).bfloat16()
+    cases.append(("torch.matmul 8192^3 (cuBLAS; the MEASURED_PEAKS workload)", lambda: torch.matmul(a8, b8), 2 * 8192 ** 3 / 1e12, None))
 else:
     cases = [c + (None,) for c in cases]
 for name, fn, tflop, tune in cases:
