@@ -110,6 +110,13 @@ def main(args):
             sampling_params=args.get("sampling_params"), cache_idx=args.get("cache_idx"),
             video_ipadapter_start_frame_idx=vip_params.video_ipadapter_start_frame_idx if args.use_vip else 1000,
             return_dict=False, output_type="np")
+        # two extensions of the yaml schema (absent from the shipped configs): a non-default resolution, and precomputed
+        # prompt embeddings for checkpoints without the T5 encoder
+        if args.get("height") is not None:
+            call.update(height=args.height, width=args.width)
+        if args.get("prompt_embeds_path") is not None:
+            pe = torch.load(args.prompt_embeds_path, weights_only=True)
+            call.update(prompt=None, prompt_embeds=pe["prompt_embeds"], negative_prompt_embeds=pe["negative_prompt_embeds"])
         video = image_embeddings = base_outputs = None
         if rank == 0:
             print(f"Processing {name}: [{prompt}]")
