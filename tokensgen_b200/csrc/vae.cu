@@ -106,33 +106,55 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ t
             of[j] = fmaf(-sh_mean[g], sc[j], bt[j]);
         }
     }
-    const bool spatial = a.zy != nullptr;
-    const int HW = a.H * a.W;
+    if (a.zy == nullptr) {
+        for (int64_t p = int64_t(blockIdx.x) * ppb + pl; p < pixels; p += int64_t(gridDim.x) * ppb) {
+            float f[8];
+            unpack8v(__ldg(reinterpret_cast<const uint4*>(a.x + p * a.ldx) + v), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], of[j]);
+            if (a.silu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+            }
+            reinterpret_cast<uint4*>(a.y + p * a.ldy)[v] = pack8v(f);
+        }
+        return;
+    }
+    // SpatialNorm: walk image rows so that the nearest-source indices of F.interpolate cost two divisions per ROW (t, h)
+    // and a shift per pixel (W / Wz is a power of two everywhere in the decoder) instead of five divisions per pixel.
     const bool odd_t = a.T > 1 && (a.T & 1);
-    for (int64_t p = int64_t(blockIdx.x) * ppb + pl; p < pixels; p += int64_t(gridDim.x) * ppb) {
-        float f[8];
-        unpack8v(__ldg(reinterpret_cast<const uint4*>(a.x + p * a.ldx) + v), f);
+    const int rows = a.T * a.H;
+    int wshift = -1;
+    if (a.W % a.Wz == 0) {
+        const int ratio = a.W / a.Wz;
+        if ((ratio & (ratio - 1)) == 0) wshift = 31 - __clz(ratio);
+    }
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int t = row / a.H, h = row - t * a.H;
+        // nearest source index of F.interpolate; first frame apart when T is odd and > 1 (autoencoder_kl_cogvideox.py:176-186)
+        const int tz = odd_t ? (t == 0 ? 0 : 1 + ((t - 1) * (a.Tz - 1)) / (a.T - 1)) : (t * a.Tz) / a.T;
+        const int hz = (h * a.Hz) / a.H;
+        const uint4* zy_row = reinterpret_cast<const uint4*>(a.zy + (int64_t(tz) * a.Hz + hz) * a.Wz * C) + v;
+        const uint4* zb_row = reinterpret_cast<const uint4*>(a.zb + (int64_t(tz) * a.Hz + hz) * a.Wz * C) + v;
+        const tg_bf16* x_row = a.x + int64_t(row) * a.W * a.ldx;
+        tg_bf16* y_row = a.y + int64_t(row) * a.W * a.ldy;
+        for (int w = pl; w < a.W; w += ppb) {
+            float f[8], y[8], b[8];
+            const int wz = wshift >= 0 ? (w >> wshift) : (w * a.Wz) / a.W;
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x_row + int64_t(w) * a.ldx) + v);
+            const uint4 yv = __ldg(zy_row + wz * V);
+            const uint4 bv = __ldg(zb_row + wz * V);
+            unpack8v(xv, f);
+            unpack8v(yv, y);
+            unpack8v(bv, b);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], of[j]);
-        if (spatial) {
-            const int t = int(p / HW);
-            const int r = int(p - int64_t(t) * HW);
-            const int h = r / a.W, w = r - h * a.W;
-            // nearest source index of F.interpolate; first frame apart when T is odd and > 1 (autoencoder_kl_cogvideox.py:176-186)
-            const int tz = odd_t ? (t == 0 ? 0 : 1 + ((t - 1) * (a.Tz - 1)) / (a.T - 1)) : (t * a.Tz) / a.T;
-            const int hz = (h * a.Hz) / a.H, wz = (w * a.Wz) / a.W;
-            const int64_t zi = (int64_t(tz) * a.Hz + hz) * a.Wz + wz;
-            float y[8], b[8];
-            unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zy + zi * C) + v), y);
-            unpack8v(__ldg(reinterpret_cast<const uint4*>(a.zb + zi * C) + v), b);
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf(f[j], sc[j], of[j]), y[j], b[j]);
+            if (a.silu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], y[j], b[j]);
+                for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
+            }
+            reinterpret_cast<uint4*>(y_row + int64_t(w) * a.ldy)[v] = pack8v(f);
         }
-        if (a.silu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
-        }
-        reinterpret_cast<uint4*>(a.y + p * a.ldy)[v] = pack8v(f);
     }
 }
 
@@ -268,7 +290,7 @@ extern "C" int tg_vae_norm_act(const tg_norm_args* a, void* stream) {
     if (a->zy != nullptr && (a->Tz <= 0 || a->Hz <= 0 || a->Wz <= 0 || a->Tz > a->T)) return fail(-4, "vae_norm_act: bad latent grid");
     const int ppb = 256 / (a->C / 8);
     const int64_t pixels = int64_t(a->T) * a->H * a->W;
-    int64_t blocks = (pixels + ppb - 1) / ppb;
+    int64_t blocks = a->zy != nullptr ? int64_t(a->T) * a->H : (pixels + ppb - 1) / ppb;   // spatial: one image row per block pass
     const int64_t cap = int64_t(sm_count()) * 8;
     if (blocks > cap) blocks = cap;
     norm_act_kernel<<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(*a);
