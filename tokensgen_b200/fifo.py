@@ -268,17 +268,19 @@ def decode_latents_parallel(pipe, latents: torch.Tensor, nf: int, rank: int = 0,
     outs = {c: pipe.decode_latents(latents[:, c * nf:(c + 1) * nf], nf) for c in range(rank, chunks, world)}
     if world == 1:
         return torch.cat([outs[c] for c in range(chunks)], dim=2)
+    ops = []
     if rank != 0:
-        for c in sorted(outs):
-            dist.send(outs[c].contiguous(), dst=0)
-        return None
-    like = outs[0]
-    for c in range(chunks):
-        if c % world:
-            buf = torch.empty_like(like)
-            dist.recv(buf, src=c % world)
-            outs[c] = buf
-    return torch.cat([outs[c] for c in range(chunks)], dim=2)
+        ops = [dist.P2POp(dist.isend, outs[c].contiguous(), 0) for c in sorted(outs)]
+    else:
+        like = outs[0]
+        for c in range(chunks):
+            if c % world:
+                outs[c] = torch.empty_like(like)
+                ops.append(dist.P2POp(dist.irecv, outs[c], c % world))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):   # one grouped NCCL launch; messages between a pair of ranks match in order
+            req.wait()
+    return None if rank != 0 else torch.cat([outs[c] for c in range(chunks)], dim=2)
 
 
 def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **kwargs):
