@@ -83,6 +83,26 @@ def test_conv_tile_edges_stride2_and_residual(env):
     assert rel_l2(y, ref) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,T,H,W", [(128, 256, 3, 8, 32), (64, 256, 1, 19, 70), (256, 512, 2, 9, 33), (128, 128, 3, 8, 32)])
+def test_conv_cta_pair_tiles(cin, cout, T, H, W):
+    """The CTA-pair kernels: 256-channel pair tiles (one accumulator buffer), 128-channel ones (two), and an ODD number of
+    256-pixel tiles (the last pair's second CTA runs a padding tile whose loads zero-fill and whose stores are masked)."""
+    from tokensgen_b200 import _ext as E
+    from tokensgen_b200.vae import _PackedConv
+    g = torch.Generator().manual_seed(cin + cout + W)
+    conv = torch.nn.Conv3d(cin, cout, 3)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (27 * cin) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    conv = conv.to(torch.bfloat16)
+    x = torch.randn(1, cin, T + 2, H, W, generator=g).bfloat16()      # the two leading frames are the causal context
+    ref = torch.nn.functional.conv3d(torch.nn.functional.pad(x.float(), (1, 1, 1, 1)), conv.weight.float(), conv.bias.float())
+    w, b = _PackedConv().get(conv.cuda())
+    y = E.vae_conv(x[0].permute(1, 2, 3, 0).contiguous().cuda(), w, b, cout, 3, 3, 3, T, H, W)
+    torch.cuda.synchronize()
+    assert rel_l2(y.permute(3, 0, 1, 2).unsqueeze(0), ref) < 5e-3
+
+
 def test_spatial_norm_silu_vs_oracle(env):
     ov, cfg, sd, vae = env
     from tokensgen_b200 import vae as V

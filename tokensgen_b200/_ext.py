@@ -135,6 +135,8 @@ def load() -> C.CDLL:
             raise TokensGenError(f"ABI version mismatch: library reports {lib.tg_version()}")
         if _os.environ.get("TG_GEMM_IMPL"):  # developer A/B switch: 1 = single-CTA tiles, 2 = CTA pairs (default)
             lib.tg_set_gemm_impl(int(_os.environ["TG_GEMM_IMPL"]))
+        if _os.environ.get("TG_CONV_IMPL"):
+            lib.tg_set_conv_impl(int(_os.environ["TG_CONV_IMPL"]))
         _lib = lib
     return _lib
 

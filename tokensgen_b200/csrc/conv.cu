@@ -63,6 +63,61 @@ __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int tile, 
     t = r / p.h_tiles;
 }
 
+// Epilogue of one accumulator row (one output pixel): BLOCK_N columns starting at output channel nt * BLOCK_N.
+template <int BLOCK_N>
+__device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int nt, bool ok, int64_t pix) {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+            uint32_t r[32];
+            tmem_ld32(t_row + c, r);
+            tmem_wait_ld();
+            const int n0 = nt * BLOCK_N + c;
+            if (!ok || n0 >= p.Cout) continue;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+            if (p.layout == 0 && n0 + 32 <= p.Cout) {
+                if (p.bias != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) {
+                        const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + i));
+                        v[i] += bf16_lo(bv.x); v[i + 1] += bf16_hi(bv.x); v[i + 2] += bf16_lo(bv.y); v[i + 3] += bf16_hi(bv.y);
+                        v[i + 4] += bf16_lo(bv.z); v[i + 5] += bf16_hi(bv.z); v[i + 6] += bf16_lo(bv.w); v[i + 7] += bf16_hi(bv.w);
+                    }
+                }
+                if (p.residual != nullptr) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + n0);
+                    uint4 rv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rv[i] = rp[i];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i * 8] += bf16_lo(rv[i].x); v[i * 8 + 1] += bf16_hi(rv[i].x);
+                        v[i * 8 + 2] += bf16_lo(rv[i].y); v[i * 8 + 3] += bf16_hi(rv[i].y);
+                        v[i * 8 + 4] += bf16_lo(rv[i].z); v[i * 8 + 5] += bf16_hi(rv[i].z);
+                        v[i * 8 + 6] += bf16_lo(rv[i].w); v[i * 8 + 7] += bf16_hi(rv[i].w);
+                    }
+                }
+                uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.ldy + n0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 o;
+                    o.x = pack_bf16x2(v[i * 8], v[i * 8 + 1]); o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
+                    o.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); o.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
+                    yp[i] = o;
+                }
+            } else {
+                // narrow outputs (conv_out: 3 image channels / 32 moment channels) and channel-plane layout
+                for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
+                    float o = v[i] + (p.bias != nullptr ? __bfloat162float(p.bias[n0 + i]) : 0.f);
+                    if (p.residual != nullptr) o += __bfloat162float(p.residual[pix * p.ld_res + n0 + i]);
+                    if (p.layout == 0) p.y[pix * p.ldy + n0 + i] = __float2bfloat16_rn(o);
+                    else p.y[int64_t(n0 + i) * p.plane_stride + pix] = __float2bfloat16_rn(o);
+                }
+            }
+        }
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -186,56 +241,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const bool ok = h < p.H_out && w < p.W_out;
                 const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
                 const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + half * BLOCK_N);
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld32(t_row + c, r);
-                    tmem_wait_ld();
-                    const int n0 = nt * BLOCK_N + c;
-                    if (!ok || n0 >= p.Cout) continue;
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    if (p.layout == 0 && n0 + 32 <= p.Cout) {
-                        if (p.bias != nullptr) {
-#pragma unroll
-                            for (int i = 0; i < 32; i += 8) {
-                                const uint4 bv = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + i));
-                                v[i] += bf16_lo(bv.x); v[i + 1] += bf16_hi(bv.x); v[i + 2] += bf16_lo(bv.y); v[i + 3] += bf16_hi(bv.y);
-                                v[i + 4] += bf16_lo(bv.z); v[i + 5] += bf16_hi(bv.z); v[i + 6] += bf16_lo(bv.w); v[i + 7] += bf16_hi(bv.w);
-                            }
-                        }
-                        if (p.residual != nullptr) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pix * p.ld_res + n0);
-                            uint4 rv[4];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) rv[i] = rp[i];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                v[i * 8] += bf16_lo(rv[i].x); v[i * 8 + 1] += bf16_hi(rv[i].x);
-                                v[i * 8 + 2] += bf16_lo(rv[i].y); v[i * 8 + 3] += bf16_hi(rv[i].y);
-                                v[i * 8 + 4] += bf16_lo(rv[i].z); v[i * 8 + 5] += bf16_hi(rv[i].z);
-                                v[i * 8 + 6] += bf16_lo(rv[i].w); v[i * 8 + 7] += bf16_hi(rv[i].w);
-                            }
-                        }
-                        uint4* yp = reinterpret_cast<uint4*>(p.y + pix * p.ldy + n0);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            uint4 o;
-                            o.x = pack_bf16x2(v[i * 8], v[i * 8 + 1]); o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
-                            o.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); o.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
-                            yp[i] = o;
-                        }
-                    } else {
-                        // narrow outputs (conv_out: 3 image channels / 32 moment channels) and channel-plane layout
-                        for (int i = 0; i < 32 && n0 + i < p.Cout; ++i) {
-                            float o = v[i] + (p.bias != nullptr ? __bfloat162float(p.bias[n0 + i]) : 0.f);
-                            if (p.residual != nullptr) o += __bfloat162float(p.residual[pix * p.ld_res + n0 + i]);
-                            if (p.layout == 0) p.y[pix * p.ldy + n0 + i] = __float2bfloat16_rn(o);
-                            else p.y[int64_t(n0 + i) * p.plane_stride + pix] = __float2bfloat16_rn(o);
-                        }
-                    }
-                }
+                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix);
             }
             tc_fence_before();
             __syncwarp();
@@ -253,6 +259,200 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
+}
+
+// =====================================================================================================================
+// CTA-pair convolution (cta_group::2).  The single-CTA kernel above is bound by operand delivery, not by the tensor pipe
+// (ncu: 29.3 GB through the L2 -> SM crossbar for one 8 x 480 x 720 x 128 -> 128 layer = 13.1 TB/s, tensor pipe 58 %).
+// Here the two CTAs of a cluster take two DIFFERENT 256-pixel tiles and the SAME BLOCK_N output channels: each loads its
+// own activation boxes and HALF of the weight tile, and the leader's MMA thread issues M = 256 (128 pixels of each CTA)
+// x N = BLOCK_N instructions, so the weight operand crosses L2 -> SM once per pair.  Operand bytes per 256 x 128 x 64 MACs:
+// 48 KB (single CTA) -> 40 KB (BLOCK_N = 128) -> 24 KB (BLOCK_N = 256, one accumulator buffer: 2 x 256 TMEM columns per
+// pixel half).  Barrier protocol as in gemm2_kernel.
+template <int BLOCK_N>
+struct Conv2Cfg {
+    static constexpr int HALF_N = BLOCK_N / 2;
+    static constexpr int B_BYTES = HALF_N * 64 * 2;
+    static constexpr int STAGE_BYTES = CV_A_BYTES + B_BYTES;  // 40 / 48 KB
+    static constexpr int STAGES = (BLOCK_N == 128) ? 5 : 4;   // 200 / 192 KB
+    static constexpr int ACC_BUFS = (BLOCK_N == 128) ? 2 : 1;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+             const __grid_constant__ ConvParams p) {
+    using Cfg = Conv2Cfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = int(cluster_ctarank());
+    const bool leader = rank == 0;
+    const int n_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
+    const int pixel_tiles = p.T_out * p.h_tiles * p.w_tiles;
+    const int num_tiles = ((pixel_tiles + 1) >> 1) * p.n_tiles;  // (pair of pixel tiles) x channel tile
+    const int taps = p.kt * p.kh * p.kw;
+    const int k_blocks = taps * p.c_chunks;
+    // this CTA's pixel tile of pair tile `tile`; t == T_out marks the padding tile of an odd count (loads zero-fill, stores are masked)
+    auto my_coords = [&](int tile, int& nt, int& wt, int& ht, int& t) {
+        nt = tile % p.n_tiles;
+        const int q = 2 * (tile / p.n_tiles) + rank;
+        wt = q % p.w_tiles;
+        const int r = q / p.w_tiles;
+        ht = r % p.h_tiles;
+        t = r / p.h_tiles;
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                int nt, wt, ht, t;
+                my_coords(tile, nt, wt, ht, t);
+                const int w_in0 = wt * CV_TW * p.stride - p.pad_w;
+                const int h_in0 = ht * CV_TH * p.stride - p.pad_h;
+                int kb = 0;
+                for (int it = 0; it < p.kt; ++it)
+                    for (int ih = 0; ih < p.kh; ++ih)
+                        for (int iw = 0; iw < p.kw; ++iw)
+                            for (int cc = 0; cc < p.c_chunks; ++cc, ++kb) {
+                                mbar_wait(empty_bar(stage), phase ^ 1u, 0x481);
+                                const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                                const uint32_t bar = mapa_shared(full_bar(stage), 0);
+                                if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+                                tma_load_4d_2cta(sa, &tmap_x, bar, cc * 64, w_in0 + iw, h_in0 + ih, t + it);
+                                tma_load_2d_2cta(sa + CV_A_BYTES, &tmap_w, bar, kb * 64, nt * BLOCK_N + rank * Cfg::HALF_N);
+                                if (++stage == STAGES) {
+                                    stage = 0;
+                                    phase ^= 1u;
+                                }
+                            }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x482);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * 2 * BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x483);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+                    const uint32_t sb = sa + CV_A_BYTES;
+#pragma unroll
+                    for (int half = 0; half < 2; ++half)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = make_smem_desc_sw128(sa + half * (CV_A_BYTES / 2) + k * 32, 16, 1024);
+                            const uint64_t db = make_smem_desc_sw128(sb + k * 32, 16, 1024);
+                            umma_ss_2cta(d_tmem + uint32_t(half * BLOCK_N), da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
+                    umma_commit_2cta(empty_bar(stage), 0b11);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_2cta(tfull_bar(acc), 0b11);
+                if (++acc == Cfg::ACC_BUFS) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+            int nt, wt, ht, t;
+            my_coords(tile, nt, wt, ht, t);
+            mbar_wait(tfull_bar(acc), acc_phase, 0x484);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int R = half * 128 + ew * 32 + lane;
+                const int h = ht * CV_TH + (R >> 5), w = wt * CV_TW + (R & 31);
+                const bool ok = t < p.T_out && h < p.H_out && w < p.W_out;
+                const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
+                const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + half * BLOCK_N);
+                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+            if (++acc == Cfg::ACC_BUFS) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
+static int g_conv_impl = 2;  // 1 = single-CTA tiles, 2 = CTA pairs where Cout_pad is a multiple of 128
+
+template <int BLOCK_N>
+static int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    using Cfg = Conv2Cfg<BLOCK_N>;
+    auto kern = conv2_kernel<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "vae_conv: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = ((p.T_out * p.h_tiles * p.w_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    kern<<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(tx, tw, p);
+    return check_launch("vae_conv");
 }
 
 template <int BLOCK_N>
@@ -302,8 +502,13 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     int rc = make_tmap_nd(&tx, a->x, 4, dims, strides, box, estr);
     if (rc) return rc;
     const int K = a->kt * a->kh * a->kw * a->Cin;
-    const int bn = (a->Cout_pad % 128 == 0) ? 128 : 64;
-    rc = make_tmap_2d(&tw, a->w, uint64_t(K), uint64_t(a->Cout_pad), uint64_t(K) * 2, 64, uint32_t(bn));
+    // CTA pairs halve the number of work units: keep single-CTA tiles for small layers (tiled coding, low-resolution blocks)
+    // where there would be fewer than two waves of pair tiles
+    const int64_t px_tiles = int64_t(a->T_out) * ((a->H_out + CV_TH - 1) / CV_TH) * ((a->W_out + CV_TW - 1) / CV_TW);
+    const int pair_bn = a->Cout_pad % 256 == 0 ? 256 : 128;
+    const bool pair = g_conv_impl == 2 && a->Cout_pad % 128 == 0 && ((px_tiles + 1) / 2) * (a->Cout_pad / pair_bn) >= sm_count();
+    const int bn = pair ? (a->Cout_pad % 256 == 0 ? 256 : 128) : ((a->Cout_pad % 128 == 0) ? 128 : 64);
+    rc = make_tmap_2d(&tw, a->w, uint64_t(K), uint64_t(a->Cout_pad), uint64_t(K) * 2, 64, uint32_t(pair ? bn / 2 : bn));
     if (rc) return rc;
     ConvParams p{};
     p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out; p.Cout = a->Cout;
@@ -320,5 +525,12 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     p.plane_stride = a->plane_stride;
     p.layout = a->layout;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pair) return bn == 256 ? launch_conv2<256>(tx, tw, p, st) : launch_conv2<128>(tx, tw, p, st);
     return bn == 128 ? launch_conv<128>(tx, tw, p, st) : launch_conv<64>(tx, tw, p, st);
+}
+
+extern "C" int tg_set_conv_impl(int impl) {  // developer hook (1 = single-CTA tiles, 2 = CTA pairs); not in the public header
+    if (impl != 1 && impl != 2) return fail(-1, "conv impl must be 1 or 2");
+    g_conv_impl = impl;
+    return 0;
 }
