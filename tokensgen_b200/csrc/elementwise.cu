@@ -49,6 +49,68 @@ __device__ __forceinline__ const __nv_bfloat16* mod_row(const tg_modvec& v, cons
     return reinterpret_cast<const __nv_bfloat16*>(p);
 }
 
+// Common case (no second LayerNorm): the row stays in registers as PACKED bf16 (NV uint4 per lane) and is unpacked in each
+// of the three passes (sum, centred sum of squares, normalise + modulate).  Half the registers of the fp32-resident form
+// below -> two to three CTAs per SM instead of one, i.e. enough loads in flight to stream HBM.
+template <int NV>
+__global__ void __launch_bounds__(256, (NV <= 12) ? 2 : 1) ln_modulate_packed_kernel(const __grid_constant__ LnParams p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + warp;
+    if (row >= p.M) return;
+    const int b = row / p.map.rows_per_batch;
+    const int r = row - b * p.map.rows_per_batch;
+    int seg, frame = 0;
+    if (r < p.map.n_text) seg = 0;
+    else if (r < p.map.n_text + p.map.n_video) { seg = 1; frame = (r - p.map.n_text) / p.map.hw; }
+    else seg = 2;
+    const __nv_bfloat16* sh = mod_row(p.shift, p.map, b, seg, frame);
+    const __nv_bfloat16* sc = mod_row(p.scale, p.map, b, seg, frame);
+    if (sh == nullptr || sc == nullptr) return;
+    const uint4* w = reinterpret_cast<const uint4*>((seg == 2) ? p.vip_ln_w : p.ln_w) + lane;
+    const uint4* bb = reinterpret_cast<const uint4*>((seg == 2) ? p.vip_ln_b : p.ln_b) + lane;
+    const uint4* shv4 = reinterpret_cast<const uint4*>(sh) + lane;
+    const uint4* scv4 = reinterpret_cast<const uint4*>(sc) + lane;
+    const uint4* xr = reinterpret_cast<const uint4*>(p.x + int64_t(row) * p.d) + lane;
+    uint4 raw[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) raw[i] = __ldg(xr + i * 32);   // all loads of the row in flight at once
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float f[8];
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[j];
+    }
+    const float inv_d = 1.0f / float(p.d);
+    const float mean = warp_sum(s) * inv_d;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float f[8];
+        unpack8(raw[i], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float dlt = f[j] - mean;
+            ss = fmaf(dlt, dlt, ss);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(ss) * inv_d + p.eps);
+    uint4* orow = reinterpret_cast<uint4*>(p.out + int64_t(row) * p.d) + lane;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float f[8], wv[8], bv[8], shv[8], scv[8];
+        unpack8(raw[i], f);
+        unpack8(__ldg(w + i * 32), wv);
+        unpack8(__ldg(bb + i * 32), bv);
+        unpack8(__ldg(shv4 + i * 32), shv);
+        unpack8(__ldg(scv4 + i * 32), scv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf((f[j] - mean) * rstd, wv[j], bv[j]), 1.0f + scv[j], shv[j]);
+        orow[i * 32] = pack8(f);
+    }
+}
+
 // One warp per row; the row stays in registers between the statistics passes (two-pass mean/variance, fp32).
 template <int NV>  // uint4 (8 x bf16) vectors per lane: d = NV * 256
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant__ LnParams p) {
@@ -375,6 +437,18 @@ extern "C" int tg_ln_modulate(const tg_bf16* x, tg_bf16* out, int B, int d, cons
     p.scale = *scale;
     const int grid = (p.M + 7) / 8;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (ln2_w == nullptr) {
+        switch (d / 256) {
+            case 1: ln_modulate_packed_kernel<1><<<grid, 256, 0, st>>>(p); break;
+            case 2: ln_modulate_packed_kernel<2><<<grid, 256, 0, st>>>(p); break;
+            case 4: ln_modulate_packed_kernel<4><<<grid, 256, 0, st>>>(p); break;
+            case 8: ln_modulate_packed_kernel<8><<<grid, 256, 0, st>>>(p); break;
+            case 12: ln_modulate_packed_kernel<12><<<grid, 256, 0, st>>>(p); break;
+            case 16: ln_modulate_packed_kernel<16><<<grid, 256, 0, st>>>(p); break;
+            default: return fail(-7, "ln_modulate: d=%d not instantiated (256, 512, 1024, 2048, 3072, 4096)", d);
+        }
+        return check_launch("ln_modulate");
+    }
     switch (d / 256) {
         case 1: ln_modulate_kernel<1><<<grid, 256, 0, st>>>(p); break;
         case 2: ln_modulate_kernel<2><<<grid, 256, 0, st>>>(p); break;
