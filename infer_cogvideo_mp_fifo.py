@@ -74,6 +74,9 @@ def main(args):
     if rank == 0:
         args.output_dir = create_output_folders(args.output_dir, args, args.name_prefix)
     pipe = init_pipeline(local, args, dtype)              # every rank loads its own weights, in parallel
+    # with >= 2 ranks the serial base clip runs CFG-parallel on ranks 0 and 1 (one guidance branch each; `cfg_parallel: false`
+    # in the yaml turns it off).  new_group is collective: every rank creates it.
+    cfg_group = dist.new_group([0, 1]) if world > 1 and args.get("cfg_parallel", True) else None
     pipe_list = [pipe]
     vip_params = args.video_ipadapter_params if args.use_vip else None
 
@@ -118,8 +121,10 @@ def main(args):
             pe = torch.load(args.prompt_embeds_path, weights_only=True)
             call.update(prompt=None, prompt_embeds=pe["prompt_embeds"], negative_prompt_embeds=pe["negative_prompt_embeds"])
         video = image_embeddings = base_outputs = None
-        if rank == 0:
-            print(f"Processing {name}: [{prompt}]")
+        base_rank = rank == 0 or (cfg_group is not None and rank == 1 and not args.use_2nd_stage)
+        if base_rank:
+            if rank == 0:
+                print(f"Processing {name}: [{prompt}]")
             if args.use_vip:
                 if args.use_2nd_stage:
                     rp = vip_params.resampler_params
@@ -134,7 +139,8 @@ def main(args):
                     video = load_video(item["video"], dps.output_res, args.num_frames_per_chunk, dps.pad_to_fit, dps.sample_fps,
                                        dps.start_t, dps.end_t, dps.max_num_chunks, dps.crop_to_fit)
             base_outputs = pipe(frames=video, image_embeddings=image_embeddings,
-                                generator=torch.Generator().manual_seed(args.seed), **call)
+                                generator=torch.Generator().manual_seed(args.seed),
+                                cfg_parallel_group=cfg_group if not args.use_2nd_stage else None, **call)
             base_outputs.condition_frames = None      # not needed by the FIFO stage; keeps the broadcast small
         else:
             pipe.preprare_for_fifo(**call)

@@ -322,7 +322,7 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
                  output_type: str = "pil", return_dict: bool = True, attention_kwargs=None, callback_on_step_end=None,
                  callback_on_step_end_tensor_inputs=("latents",), max_sequence_length: int = 226, decode_chunk_size=None,
                  vip_scale=1.0, sampling_mode: str = None, sampling_params: Dict[str, Any] = None, cache_idx=(),
-                 video_ipadapter_start_frame_idx: Optional[int] = 1000):
+                 video_ipadapter_start_frame_idx: Optional[int] = 1000, cfg_parallel_group=None):
         if use_separate_guidance:
             raise NotImplementedError("use_separate_guidance (3-branch CFG) is off in both shipped configs (edit.yaml:11, gen.yaml)")
         if callback_on_step_end is not None:
@@ -383,18 +383,41 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         old_x0 = None
         ts = [int(t) for t in timesteps]
         B = 2 if do_cfg else 1
+        # CFG-parallel base stage: the two guidance branches are independent until they are combined, so with
+        # `cfg_parallel_group` (two ranks that call this method with identical arguments) each rank runs ONE branch through the
+        # DiT (B = 1) and the pair all-gathers the 2.25 MB predictions over NVLink; everything else (latents, scheduler
+        # noise, FIFO capture) is computed redundantly and identically on both, so no other state moves.
+        cfgp = cfg_parallel_group if (do_cfg and cfg_parallel_group is not None) else None
+        if cfgp is not None:
+            import torch.distributed as dist
+            branch = dist.get_rank(cfgp)
+            if dist.get_world_size(cfgp) != 2:
+                raise ValueError("cfg_parallel_group must hold exactly two ranks (uncond, cond)")
+            pe_mine = prompt_embeds[branch:branch + 1].contiguous()
+            vip_mine = vip_states[branch:branch + 1].contiguous() if use_vip else None
         for i, t in enumerate(ts):
             k = max(0, compressed_nf_per_chunk - 1 - i)
             fifo_latents.insert(0, latents[:, [k]])
             fifo_old.insert(0, None if old_x0 is None else old_x0[:, [k]])
-            model_in = torch.cat([latents] * B) if do_cfg else latents
-            timestep = torch.full((B,), t, device=device, dtype=torch.int64)
-            kw = dict(vip_image_rotary_emb=img_rope, vip_condition_rotary_emb=cond_rope,
-                      vip_encoder_hidden_states=vip_states) if use_vip else {}
-            noise_pred = self.transformer(hidden_states=model_in, encoder_hidden_states=prompt_embeds, timestep=timestep,
-                                          image_rotary_emb=image_rotary_emb, attention_kwargs=attention_kwargs,
-                                          return_dict=False, **kw)[0]
-            noise_pred = noise_pred.float()
+            if cfgp is not None:
+                kw = dict(vip_image_rotary_emb=img_rope, vip_condition_rotary_emb=cond_rope,
+                          vip_encoder_hidden_states=vip_mine) if use_vip else {}
+                mine = self.transformer(hidden_states=latents, encoder_hidden_states=pe_mine,
+                                        timestep=torch.full((1,), t, device=device, dtype=torch.int64),
+                                        image_rotary_emb=image_rotary_emb, attention_kwargs=attention_kwargs,
+                                        return_dict=False, **kw)[0].contiguous()
+                both = torch.empty((2,) + tuple(mine.shape[1:]), device=device, dtype=mine.dtype)
+                dist.all_gather_into_tensor(both, mine, group=cfgp)
+                noise_pred = both.float()
+            else:
+                model_in = torch.cat([latents] * B) if do_cfg else latents
+                timestep = torch.full((B,), t, device=device, dtype=torch.int64)
+                kw = dict(vip_image_rotary_emb=img_rope, vip_condition_rotary_emb=cond_rope,
+                          vip_encoder_hidden_states=vip_states) if use_vip else {}
+                noise_pred = self.transformer(hidden_states=model_in, encoder_hidden_states=prompt_embeds, timestep=timestep,
+                                              image_rotary_emb=image_rotary_emb, attention_kwargs=attention_kwargs,
+                                              return_dict=False, **kw)[0]
+                noise_pred = noise_pred.float()
             g = guidance_scale
             if use_dynamic_cfg:
                 g = 1 + guidance_scale * ((1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2)
