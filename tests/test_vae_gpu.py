@@ -103,6 +103,31 @@ def test_conv_cta_pair_tiles(cin, cout, T, H, W):
     assert rel_l2(y.permute(3, 0, 1, 2).unsqueeze(0), ref) < 5e-3
 
 
+@pytest.mark.parametrize("cin,cout,T,H,W,res", [(64, 128, 2, 160, 250, False), (128, 256, 1, 150, 300, True), (128, 128, 3, 97, 129, True)])
+def test_conv_tap_reuse_kernel(cin, cout, T, H, W, res):
+    """conv3_kernel (CTA pairs + one halo'd activation box per (kt, kh) serving the three kw taps through swizzle-phase
+    descriptors): engages on stride-1 3x3x3 layers with >= two waves of 128 x 2 pixel tiles.  Ragged widths / heights, an odd
+    number of tiles, two channel tiles and the residual epilogue."""
+    from tokensgen_b200 import _ext as E
+    from tokensgen_b200.vae import _PackedConv
+    g = torch.Generator().manual_seed(cin * 7 + W)
+    conv = torch.nn.Conv3d(cin, cout, 3)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (27 * cin) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    conv = conv.to(torch.bfloat16)
+    x = torch.randn(1, cin, T + 2, H, W, generator=g).bfloat16()
+    r = torch.randn(T, H, W, cout, generator=g).bfloat16() if res else None
+    ref = torch.nn.functional.conv3d(torch.nn.functional.pad(x.float(), (1, 1, 1, 1)), conv.weight.float(), conv.bias.float())
+    ref = ref[0].permute(1, 2, 3, 0)
+    if res:
+        ref = ref + r.float()
+    w, b = _PackedConv().get(conv.cuda())
+    y = E.vae_conv(x[0].permute(1, 2, 3, 0).contiguous().cuda(), w, b, cout, 3, 3, 3, T, H, W, residual=None if r is None else r.cuda())
+    torch.cuda.synchronize()
+    assert rel_l2(y, ref) < 5e-3
+
+
 def test_spatial_norm_silu_vs_oracle(env):
     ov, cfg, sd, vae = env
     from tokensgen_b200 import vae as V

@@ -437,7 +437,202 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
 }
 
-static int g_conv_impl = 2;  // 1 = single-CTA tiles, 2 = CTA pairs where Cout_pad is a multiple of 128
+// =====================================================================================================================
+// Tap-reuse CTA-pair convolution (stride 1, kw = 3).  conv2 still streams every activation box once per TAP: 27 boxes of
+// 32 KB per 256-pixel tile and 64 input channels.  The three kw taps of one (kt, kh) read the same pixels shifted by one
+// pixel along w, so here the tile is 128 w x 2 h (each h row = one 128-row UMMA operand, contiguous in w) and ONE halo'd
+// box {64 c, 130 w, 2 h} per (kt, kh, channel chunk) serves all three kw taps: the A descriptor of tap kw simply starts
+// kw rows (kw x 128 B) further into the box.  That start is not at a 1024-byte boundary of the 128-byte swizzle pattern;
+// measured on B200 (tests/test_vae_gpu.py::test_conv_tap_reuse_kernel): the tensor core applies the swizzle XOR to the
+// ABSOLUTE shared-memory address bits, exactly as the TMA did when it wrote the box, so a plain descriptor with the shifted
+// start address is correct and the descriptor's base-offset field must stay 0 (setting it to the swizzle phase
+// double-corrects and gives wrong sums).  Activation traffic drops 3x
+// (9 boxes of 33 KB instead of 27 of 32 KB); with the weight tile split across the CTA pair a 256-pixel x 128-channel x
+// 64-deep unit moves ~19 KB instead of 40 KB (conv2<128>) / 48 KB (single CTA).
+constexpr int C3_TW = 128, C3_TH = 2;
+constexpr int C3_ROW_BYTES = (C3_TW + 2) * 128;                       // one h row of the halo'd box: 130 pixels x 64 c
+constexpr int C3_A_BYTES = C3_TH * C3_ROW_BYTES;                       // 33 280 B delivered by the TMA
+constexpr int C3_A_SLOT = (C3_A_BYTES + 1023) / 1024 * 1024;           // 33 792 B
+constexpr int C3_HALF_N = 64;                                           // weight rows (output channels) this CTA loads
+constexpr int C3_B_BYTES = C3_HALF_N * 64 * 2;                          // 8 KB per tap
+constexpr int C3_STAGE_BYTES = C3_A_SLOT + 3 * C3_B_BYTES;             // 58 368 B
+constexpr int C3_STAGE_TX = C3_A_BYTES + 3 * C3_B_BYTES;               // bytes the TMA actually delivers per CTA and stage
+constexpr int C3_STAGES = 3;
+constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 256 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+             const __grid_constant__ ConvParams p) {
+    constexpr int BLOCK_N = 128;
+    constexpr int STAGES = C3_STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar_base = smem_base + STAGES * C3_STAGE_BYTES;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = int(cluster_ctarank());
+    const bool leader = rank == 0;
+    const int n_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x >> 1;
+    const int pixel_tiles = p.T_out * p.h_tiles * p.w_tiles;       // h_tiles / w_tiles in units of the 128 x 2 tile
+    const int num_tiles = ((pixel_tiles + 1) >> 1) * p.n_tiles;
+    const int k_blocks = p.kt * p.kh * p.c_chunks;                 // one k-block = (kt, kh, channel chunk): three kw taps
+    auto my_coords = [&](int tile, int& nt, int& wt, int& ht, int& t) {
+        nt = tile % p.n_tiles;
+        const int q = 2 * (tile / p.n_tiles) + rank;
+        wt = q % p.w_tiles;
+        const int r = q / p.w_tiles;
+        ht = r % p.h_tiles;
+        t = r / p.h_tiles;
+    };
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_2cta(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                int nt, wt, ht, t;
+                my_coords(tile, nt, wt, ht, t);
+                const int w_in0 = wt * C3_TW - p.pad_w;
+                const int h_in0 = ht * C3_TH - p.pad_h;
+                for (int it = 0; it < p.kt; ++it)
+                    for (int ih = 0; ih < p.kh; ++ih)
+                        for (int cc = 0; cc < p.c_chunks; ++cc) {
+                            mbar_wait(empty_bar(stage), phase ^ 1u, 0x4a1);
+                            const uint32_t sa = smem_base + stage * C3_STAGE_BYTES;
+                            const uint32_t bar = mapa_shared(full_bar(stage), 0);
+                            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C3_STAGE_TX);
+                            tma_load_4d_2cta(sa, &tmap_x, bar, cc * 64, w_in0, h_in0 + ih, t + it);
+#pragma unroll
+                            for (int iw = 0; iw < 3; ++iw) {
+                                const int kb = ((it * p.kh + ih) * 3 + iw) * p.c_chunks + cc;
+                                tma_load_2d_2cta(sa + C3_A_SLOT + iw * C3_B_BYTES, &tmap_w, bar, kb * 64,
+                                                 nt * BLOCK_N + rank * C3_HALF_N);
+                            }
+                            if (++stage == STAGES) {
+                                stage = 0;
+                                phase ^= 1u;
+                            }
+                        }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(256, BLOCK_N, false, false);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u, 0x4a2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + uint32_t(acc * 2 * BLOCK_N);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, 0x4a3);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C3_STAGE_BYTES;
+                    const uint32_t sb = sa + C3_A_SLOT;
+#pragma unroll
+                    for (int row = 0; row < C3_TH; ++row)
+#pragma unroll
+                        for (int iw = 0; iw < 3; ++iw)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const uint64_t da = make_smem_desc_sw128(sa + row * C3_ROW_BYTES + iw * 128 + k * 32, 16, 1024);
+                                const uint64_t db = make_smem_desc_sw128(sb + iw * C3_B_BYTES + k * 32, 16, 1024);
+                                umma_ss_2cta(d_tmem + uint32_t(row * BLOCK_N), da, db, idesc, (kb | iw | k) != 0 ? 1u : 0u);
+                            }
+                    umma_commit_2cta(empty_bar(stage), 0b11);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_2cta(tfull_bar(acc), 0b11);
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        const int ew = warp & 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+            int nt, wt, ht, t;
+            my_coords(tile, nt, wt, ht, t);
+            mbar_wait(tfull_bar(acc), acc_phase, 0x4a4);
+            tc_fence_after();
+#pragma unroll 1
+            for (int row = 0; row < C3_TH; ++row) {
+                const int h = ht * C3_TH + row, w = wt * C3_TW + ew * 32 + lane;
+                const bool ok = t < p.T_out && h < p.H_out && w < p.W_out;
+                const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
+                const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + row * BLOCK_N);
+                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_shared(tempty_bar(acc), 0));
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_2cta(tmem_base, 512);
+    }
+}
+
+static int launch_conv3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "vae_conv: cudaFuncSetAttribute(smem=%d): %s", C3_SMEM_BYTES, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    const int tiles = ((p.T_out * p.h_tiles * p.w_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    conv3_kernel<<<2 * clusters, 256, C3_SMEM_BYTES, stream>>>(tx, tw, p);
+    return check_launch("vae_conv");
+}
+
+static int g_conv_impl = 3;  // 1 = single-CTA tiles, 2 = CTA pairs, 3 = CTA pairs + kw-tap reuse where stride 1 / kw 3 allow
 
 template <int BLOCK_N>
 static int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
@@ -495,6 +690,36 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
         return fail(-10, "vae_conv: residual must be 16-byte aligned with ld_res %% 8 == 0");
     const int s = a->stride_hw;
     CUtensorMap tx, tw;
+    {
+        // tap-reuse kernel: stride 1, kw = 3, 128-channel weight tiles, at least two waves of pair tiles
+        const int64_t t3 = int64_t(a->T_out) * ((a->H_out + C3_TH - 1) / C3_TH) * ((a->W_out + C3_TW - 1) / C3_TW);
+        if (g_conv_impl == 3 && s == 1 && a->kw == 3 && a->Cout_pad % 128 == 0 && ((t3 + 1) / 2) * (a->Cout_pad / 128) >= sm_count()) {
+            const uint64_t dims3[4] = {uint64_t(a->Cin), uint64_t(a->W_in), uint64_t(a->H_in), uint64_t(a->T_in)};
+            const uint64_t strides3[3] = {uint64_t(a->Cin) * 2, uint64_t(a->W_in) * a->Cin * 2, uint64_t(a->H_in) * a->W_in * a->Cin * 2};
+            const uint32_t box3[4] = {64, uint32_t(C3_TW + 2), uint32_t(C3_TH), 1};
+            const uint32_t estr3[4] = {1, 1, 1, 1};
+            int rc3 = make_tmap_nd(&tx, a->x, 4, dims3, strides3, box3, estr3);
+            if (rc3) return rc3;
+            const int K3 = a->kt * a->kh * a->kw * a->Cin;
+            rc3 = make_tmap_2d(&tw, a->w, uint64_t(K3), uint64_t(a->Cout_pad), uint64_t(K3) * 2, 64, uint32_t(C3_HALF_N));
+            if (rc3) return rc3;
+            ConvParams p{};
+            p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out; p.Cout = a->Cout;
+            p.kt = a->kt; p.kh = a->kh; p.kw = a->kw; p.stride = 1; p.pad_h = a->pad_h0; p.pad_w = a->pad_w0;
+            p.c_chunks = a->Cin / 64;
+            p.h_tiles = (a->H_out + C3_TH - 1) / C3_TH;
+            p.w_tiles = (a->W_out + C3_TW - 1) / C3_TW;
+            p.n_tiles = a->Cout_pad / 128;
+            p.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
+            p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
+            p.ld_res = a->ld_res;
+            p.y = reinterpret_cast<__nv_bfloat16*>(a->y);
+            p.ldy = a->ldy;
+            p.plane_stride = a->plane_stride;
+            p.layout = a->layout;
+            return launch_conv3(tx, tw, p, static_cast<cudaStream_t>(stream));
+        }
+    }
     const uint64_t dims[4] = {uint64_t(a->Cin), uint64_t(a->W_in), uint64_t(a->H_in), uint64_t(a->T_in)};
     const uint64_t strides[3] = {uint64_t(a->Cin) * 2, uint64_t(a->W_in) * a->Cin * 2, uint64_t(a->H_in) * a->W_in * a->Cin * 2};
     const uint32_t box[4] = {64, uint32_t(CV_TW * s), uint32_t(CV_TH * s), 1};
@@ -506,7 +731,7 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     // where there would be fewer than two waves of pair tiles
     const int64_t px_tiles = int64_t(a->T_out) * ((a->H_out + CV_TH - 1) / CV_TH) * ((a->W_out + CV_TW - 1) / CV_TW);
     const int pair_bn = a->Cout_pad % 256 == 0 ? 256 : 128;
-    const bool pair = g_conv_impl == 2 && a->Cout_pad % 128 == 0 && ((px_tiles + 1) / 2) * (a->Cout_pad / pair_bn) >= sm_count();
+    const bool pair = g_conv_impl >= 2 && a->Cout_pad % 128 == 0 && ((px_tiles + 1) / 2) * (a->Cout_pad / pair_bn) >= sm_count();
     const int bn = pair ? (a->Cout_pad % 256 == 0 ? 256 : 128) : ((a->Cout_pad % 128 == 0) ? 128 : 64);
     rc = make_tmap_2d(&tw, a->w, uint64_t(K), uint64_t(a->Cout_pad), uint64_t(K) * 2, 64, uint32_t(pair ? bn / 2 : bn));
     if (rc) return rc;
@@ -530,7 +755,7 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
 }
 
 extern "C" int tg_set_conv_impl(int impl) {  // developer hook (1 = single-CTA tiles, 2 = CTA pairs); not in the public header
-    if (impl != 1 && impl != 2) return fail(-1, "conv impl must be 1 or 2");
+    if (impl < 1 || impl > 3) return fail(-1, "conv impl must be 1, 2 or 3");
     g_conv_impl = impl;
     return 0;
 }
