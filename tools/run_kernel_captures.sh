@@ -1,6 +1,6 @@
 # ncu --set full captures of the non-attention hot kernels at their bench shapes (one launch each) + the VAE sweep
 mkdir -p gpurun_out
-for k in gemm_ff1:gemm2 gemm_qkv:gemm2 gemm_ff2:gemm2 conv:conv2_kernel ln:ln_modulate norm_act:norm_act; do
+for k in gemm_ff1:gemm2 gemm_qkv:gemm2 gemm_ff2:gemm2 conv:conv3_kernel ln:ln_modulate norm_act:norm_act; do
   name=${k%%:*}; pat=${k##*:}
   timeout 300 ncu --set full --clock-control none --import-source on -k regex:$pat -s 2 -c 1 -f -o gpurun_out/${name}_full python tools/kernel_profile.py $name > gpurun_out/ncu_${name}.log 2>&1; echo "$name rc=$?"
 done
