@@ -256,6 +256,8 @@ typedef struct {
     int silu;
     tg_bf16* y;
     int64_t ldy;
+    int64_t ldz; /* elements between latent pixels of zy / zb (0 = C): lets every SpatialNorm of the decoder read its columns of ONE
+                    [latent pixels, sum of 2C] table produced by a single GEMM over all conv_y / conv_b weights */
 } tg_norm_args;
 int tg_vae_norm_act(const tg_norm_args* args, void* stream);
 

@@ -56,7 +56,7 @@ class NormArgs(C.Structure):
     _fields_ = [("x", C.c_void_p), ("ldx", C.c_int64), ("T", C.c_int), ("H", C.c_int), ("W", C.c_int), ("C", C.c_int),
                 ("groups", C.c_int), ("eps", C.c_float), ("sums", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
                 ("zy", C.c_void_p), ("zb", C.c_void_p), ("Tz", C.c_int), ("Hz", C.c_int), ("Wz", C.c_int), ("silu", C.c_int),
-                ("y", C.c_void_p), ("ldy", C.c_int64)]
+                ("y", C.c_void_p), ("ldy", C.c_int64), ("ldz", C.c_int64)]
 
 
 ACT_NONE, ACT_GELU_TANH, ACT_SILU = 0, 1, 2
@@ -408,9 +408,16 @@ def vae_norm_act(x: torch.Tensor, sums: torch.Tensor, groups: int, eps: float, g
     T, H, W, Cc = x.shape
     a.x, a.ldx, a.T, a.H, a.W, a.C, a.groups, a.eps = _bf16_cuda(x, "x").data_ptr(), Cc, T, H, W, Cc, groups, float(eps)
     a.sums, a.gamma, a.beta = sums.data_ptr(), _bf16_cuda(gamma, "gamma").data_ptr(), _bf16_cuda(beta, "beta").data_ptr()
-    if zy is not None:
-        a.zy, a.zb = _bf16_cuda(zy, "zy").data_ptr(), _bf16_cuda(zb, "zb").data_ptr()
+    if zy is not None:   # [Tz,Hz,Wz,C] tables; may be column slices of a wider table (row stride = stride(2))
+        for t_ in (zy, zb):
+            if not (t_.is_cuda and t_.dtype == torch.bfloat16 and t_.stride(3) == 1 and t_.stride(1) == t_.shape[2] * t_.stride(2)
+                    and t_.stride(0) == t_.shape[1] * t_.stride(1)):
+                raise TokensGenError("vae_norm_act: zy/zb must be [Tz,Hz,Wz,C] bf16 with a uniform pixel stride")
+        a.zy, a.zb = zy.data_ptr(), zb.data_ptr()
         a.Tz, a.Hz, a.Wz = zy.shape[0], zy.shape[1], zy.shape[2]
+        a.ldz = zy.stride(2)
+        if zb.stride(2) != zy.stride(2):
+            raise TokensGenError("vae_norm_act: zy and zb must share the pixel stride")
     a.silu = int(silu)
     if not (out.is_cuda and out.dtype == torch.bfloat16 and out.stride(-1) == 1):
         raise TokensGenError("vae_norm_act: bad out")

@@ -134,16 +134,18 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ t
         // nearest source index of F.interpolate; first frame apart when T is odd and > 1 (autoencoder_kl_cogvideox.py:176-186)
         const int tz = odd_t ? (t == 0 ? 0 : 1 + ((t - 1) * (a.Tz - 1)) / (a.T - 1)) : (t * a.Tz) / a.T;
         const int hz = (h * a.Hz) / a.H;
-        const uint4* zy_row = reinterpret_cast<const uint4*>(a.zy + (int64_t(tz) * a.Hz + hz) * a.Wz * C) + v;
-        const uint4* zb_row = reinterpret_cast<const uint4*>(a.zb + (int64_t(tz) * a.Hz + hz) * a.Wz * C) + v;
+        const int64_t ldz = a.ldz > 0 ? a.ldz : C;
+        const int ldz4 = int(ldz / 8);
+        const uint4* zy_row = reinterpret_cast<const uint4*>(a.zy + (int64_t(tz) * a.Hz + hz) * a.Wz * ldz) + v;
+        const uint4* zb_row = reinterpret_cast<const uint4*>(a.zb + (int64_t(tz) * a.Hz + hz) * a.Wz * ldz) + v;
         const tg_bf16* x_row = a.x + int64_t(row) * a.W * a.ldx;
         tg_bf16* y_row = a.y + int64_t(row) * a.W * a.ldy;
         for (int w = pl; w < a.W; w += ppb) {
             float f[8], y[8], b[8];
             const int wz = wshift >= 0 ? (w >> wshift) : (w * a.Wz) / a.W;
             const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x_row + int64_t(w) * a.ldx) + v);
-            const uint4 yv = __ldg(zy_row + wz * V);
-            const uint4 bv = __ldg(zb_row + wz * V);
+            const uint4 yv = __ldg(zy_row + wz * ldz4);
+            const uint4 bv = __ldg(zb_row + wz * ldz4);
             unpack8v(xv, f);
             unpack8v(yv, y);
             unpack8v(bv, b);
@@ -287,6 +289,7 @@ extern "C" int tg_vae_norm_act(const tg_norm_args* a, void* stream) {
         a->C % a->groups != 0 || a->ldx < a->C || a->ldy < a->C || a->ldx % 8 != 0 || a->ldy % 8 != 0)
         return fail(-2, "vae_norm_act: bad shape T=%d H=%d W=%d C=%d groups=%d", a->T, a->H, a->W, a->C, a->groups);
     if ((a->zy == nullptr) != (a->zb == nullptr)) return fail(-3, "vae_norm_act: zy and zb come together");
+    if (a->zy != nullptr && a->ldz != 0 && (a->ldz < a->C || a->ldz % 8 != 0)) return fail(-5, "vae_norm_act: bad ldz=%lld", (long long)a->ldz);
     if (a->zy != nullptr && (a->Tz <= 0 || a->Hz <= 0 || a->Wz <= 0 || a->Tz > a->T)) return fail(-4, "vae_norm_act: bad latent grid");
     const int ppb = 256 / (a->C / 8);
     const int64_t pixels = int64_t(a->T) * a->H * a->W;

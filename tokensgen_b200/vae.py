@@ -230,12 +230,35 @@ def _causal_conv(mod: CogVideoXCausalConv3d, buf: torch.Tensor, T: int, cout: in
 
 
 class _ZqTables:
-    """conv_y(zq) / conv_b(zq) of one SpatialNorm at latent resolution, channels-last [Tz, hz, wz, C]."""
+    """conv_y(zq) / conv_b(zq) of EVERY SpatialNorm of the decoder at latent resolution, from ONE GEMM: the 1x1x1 convolutions
+    all read the same latent, so their weights are stacked into one [sum of 2C, 64] matrix and each norm reads its own
+    column slice of the [latent pixels, sum of 2C] result (tg_norm_args.ldz).  One launch per latent batch instead of ~100
+    (the tiled coder calls this for 9 tiles x 6 frame batches)."""
 
-    def __init__(self, zq_cl: torch.Tensor):
+    def __init__(self, zq_cl: torch.Tensor, norms=None):
         self.zq = zq_cl  # [Tz, hz, wz, 64-padded latent channels]
+        self.slices = None
+        if norms:
+            owner = norms[0]
+            pack = owner.__dict__.setdefault("_tg_zq_pack", {})
+            key = tuple((c.conv.weight.data_ptr(), c.conv.weight._version) for n in norms for c in (n.conv_y, n.conv_b))
+            if pack.get("key") != key:
+                ws, bs, offs, off = [], [], {}, 0
+                for n in norms:
+                    for c in (n.conv_y, n.conv_b):
+                        w, _ = c._pack.get(c.conv)
+                        ws.append(w)
+                        bs.append(c._pack.b_pad)
+                        offs[id(c)] = (off, c.conv.out_channels)
+                        off += w.shape[0]
+                pack.update(key=key, w=torch.cat(ws).contiguous(), b=torch.cat(bs).contiguous(), offs=offs)
+            Tz, hz, wz, cp = self.zq.shape
+            table = E.gemm_bias_act(self.zq.view(-1, cp), pack["w"], pack["b"]).view(Tz, hz, wz, -1)
+            self.slices = {k: table[..., o:o + c] for k, (o, c) in pack["offs"].items()}
 
     def tables(self, norm: CogVideoXSpatialNorm3D):
+        if self.slices is not None:
+            return [self.slices[id(norm.conv_y)], self.slices[id(norm.conv_b)]]
         Tz, hz, wz, cp = self.zq.shape
         rows = self.zq.view(-1, cp)
         return [conv._pack.linear(conv.conv, rows).view(Tz, hz, wz, -1) for conv in (norm.conv_y, norm.conv_b)]
@@ -392,13 +415,20 @@ class AutoencoderKLCogVideoX(nn.Module):
         _causal_conv(enc.conv_out, buf, T2, enc.conv_out.conv.out_channels, planes_out=out_planes, plane_stride=plane_stride)
         return T2
 
+    def _spatial_norms(self):
+        lst = self.__dict__.get("_tg_spatial_norms")
+        if lst is None:
+            lst = [m for m in self.decoder.modules() if isinstance(m, CogVideoXSpatialNorm3D)]
+            self.__dict__["_tg_spatial_norms"] = lst
+        return lst
+
     def _decoder_batch(self, z_cf: torch.Tensor, out_planes: torch.Tensor, plane_stride: int) -> int:
         """z_cf [16, T, h, w] -> video frames written as channel planes; returns the number of frames produced."""
         dec = self.decoder
         C, T, H, W = z_cf.shape
         buf = torch.empty(T + 2, H, W, 64, device=z_cf.device, dtype=torch.bfloat16)
         E.vae_to_channels_last(z_cf, 64, buf[2:])
-        zq = _ZqTables(buf[2:])
+        zq = _ZqTables(buf[2:], self._spatial_norms())
         h = _causal_conv(dec.conv_in, buf, T, dec.conv_in.conv.out_channels)
         # buf[2:] (zq) stays alive and unmodified: the conv only rewrites the two causal frames in front of it
         for r in dec.mid_block.resnets:
