@@ -47,7 +47,14 @@ typedef struct {
     int n_vip;
     int hw;     /* video tokens per latent frame (30*45 = 1350) */
     int frames; /* latent frames per window (13) */
+    /* Sequence-parallel shard (Ulysses single-clip path): the buffers of a row-local call hold only rows
+     * [row0, row0 + rows_local) of every batch, i.e. they are [B, rows_local, *] and local row i is row row0 + i of its
+     * batch.  rows_local == 0 (and row0 == 0): unsharded, all rows_per_batch rows. */
+    int row0;
+    int rows_local;
 } tg_rowmap;
+
+#define TG_MAX_PEERS 8 /* GPUs of one NVSwitch domain */
 
 /* One modulation vector source: row (b*frames + f) of a [B*frames, ld] bf16 table, f = 0 unless the row is a
  * video row.  Replaces the `repeat "b f c -> b (f hw) c"` broadcasts of
@@ -122,6 +129,21 @@ typedef struct {
 int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H, int K,
                      const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps, void* stream);
 
+/* K3 fused with the first Ulysses all-to-all (sequence-sharded rows -> head-sharded Q/K/V): the same GEMM + epilogue
+ * over THIS rank's rows (map->row0 / rows_local), but head h of projection p is stored into rank (h / (H/world))'s
+ * buffer peer[p][h / (H/world)], laid out [B, H/world, out_rows, 64], at local head h % (H/world) and batch row r —
+ * plain 16-byte stores through NVLink peer mappings issued by the epilogue warps while the tensor cores work on the next
+ * tile (the reference has no counterpart: its base stage runs on one GPU, pipeline_cogvideox_mp_fifo.py:1186-1305).
+ * peer[p][own rank] is the local buffer.  proj[p].out is ignored.  The caller orders this kernel before the consumers on
+ * the other ranks (a cross-rank stream barrier). */
+typedef struct {
+    int world; /* ranks of the sequence-parallel group; H % world == 0, world <= TG_MAX_PEERS */
+    tg_bf16* peer[6][TG_MAX_PEERS];
+} tg_qkv_scatter;
+int tg_qkv_rope_gemm_sp(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H, int K,
+                        const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps,
+                        const tg_qkv_scatter* scatter, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------
  * K4/K5/K6: non-causal softmax(Q K^T * scale) V, head_dim 64, tcgen05 flash attention.
  * Replaces the three F.scaled_dot_product_attention calls at attention_processor.py:2066-2069, 2117-2125
@@ -144,6 +166,27 @@ int tg_attn_fwd_pair(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64
                      const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
                      int kv_rows2, tg_bf16* out, int64_t out_rows_alloc, int B, int H, float softmax_scale, float out_scale2,
                      void* stream);
+
+/* K4/K5/K6 fused with the second Ulysses all-to-all (head-sharded attention output -> sequence-sharded rows): this rank
+ * attends over its H local heads (global heads head0 .. head0+H-1) and ALL rows; output row g (= out_row0 + query index) of
+ * a batch goes to its owner rank o = min(g / chunk, world-1), whose buffer peer[o] is [B, rows_local(o), H_total*64]
+ * (rows_local(o) = chunk, or rows_per_batch - (world-1)*chunk for the last rank), at local row g - o*chunk and columns
+ * [(head0 + h)*64, +64) — peer stores (and, with accumulate, peer loads) from the attention epilogue. */
+typedef struct {
+    int world;
+    int chunk;          /* rows of each batch owned by every rank but the last */
+    int rows_per_batch; /* rows of the full residual stream per batch */
+    int H_total;        /* heads of the model (row stride of the output = H_total*64) */
+    int head0;          /* first global head of this call's q/k/v */
+    tg_bf16* peer[TG_MAX_PEERS];
+} tg_attn_scatter;
+int tg_attn_fwd_sp(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
+                   const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, const tg_attn_scatter* out,
+                   int64_t out_row0, int B, int H, float softmax_scale, int accumulate, float out_scale, void* stream);
+int tg_attn_fwd_pair_sp(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
+                        const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
+                        int kv_rows2, const tg_attn_scatter* out, int B, int H, float softmax_scale, float out_scale2,
+                        void* stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * K9/K11 index maps (bit-exact class).

@@ -22,7 +22,7 @@ class TokensGenError(RuntimeError):
 
 class RowMap(C.Structure):
     _fields_ = [("rows_per_batch", C.c_int), ("n_text", C.c_int), ("n_video", C.c_int), ("n_vip", C.c_int),
-                ("hw", C.c_int), ("frames", C.c_int)]
+                ("hw", C.c_int), ("frames", C.c_int), ("row0", C.c_int), ("rows_local", C.c_int)]
 
 
 class ModVec(C.Structure):
@@ -33,6 +33,18 @@ class ModVec(C.Structure):
 class QkvProj(C.Structure):
     _fields_ = [("out", C.c_void_p), ("out_rows", C.c_int), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
                 ("cos_video", C.c_void_p), ("sin_video", C.c_void_p), ("cos_vip", C.c_void_p), ("sin_vip", C.c_void_p)]
+
+
+MAX_PEERS = 8
+
+
+class QkvScatter(C.Structure):
+    _fields_ = [("world", C.c_int), ("peer", (C.c_void_p * MAX_PEERS) * 6)]
+
+
+class AttnScatter(C.Structure):
+    _fields_ = [("world", C.c_int), ("chunk", C.c_int), ("rows_per_batch", C.c_int), ("H_total", C.c_int),
+                ("head0", C.c_int), ("peer", C.c_void_p * MAX_PEERS)]
 
 
 class DpmStepArgs(C.Structure):
@@ -75,6 +87,12 @@ SYMBOLS = {
     "tg_gemm_gate_residual": (C.c_int, [_VP, _I64, _VP, _VP, _VP, _I64, _I, _I, _I, C.POINTER(RowMap),
                                         C.POINTER(ModVec), _VP]),
     "tg_qkv_rope_gemm": (C.c_int, [_VP, _I64, _VP, _VP, _I, _I, _I, C.POINTER(RowMap), C.POINTER(QkvProj), _I, _F, _VP]),
+    "tg_qkv_rope_gemm_sp": (C.c_int, [_VP, _I64, _VP, _VP, _I, _I, _I, C.POINTER(RowMap), C.POINTER(QkvProj), _I, _F,
+                                      C.POINTER(QkvScatter), _VP]),
+    "tg_attn_fwd_sp": (C.c_int, [_VP, _I64, _I64, _I, _VP, _VP, _I64, _I64, _I, C.POINTER(AttnScatter), _I64, _I, _I, _F, _I,
+                                 _F, _VP]),
+    "tg_attn_fwd_pair_sp": (C.c_int, [_VP, _VP, _VP, _I64, _I, _I, _VP, _VP, _VP, _I64, _I64, _I, C.POINTER(AttnScatter), _I, _I,
+                                      _F, _F, _VP]),
     "tg_attn_fwd": (C.c_int, [_VP, _I64, _I64, _I, _VP, _VP, _I64, _I64, _I, _VP, _I64, _I64, _I, _I, _F, _I, _F, _VP]),
     "tg_attn_fwd_pair": (C.c_int, [_VP, _VP, _VP, _I64, _I, _I, _VP, _VP, _VP, _I64, _I64, _I, _VP, _I64, _I, _I, _F, _F, _VP]),
     "tg_patchify": (C.c_int, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
@@ -175,8 +193,13 @@ def randn_tensor(shape, generator, device, dtype) -> torch.Tensor:
     return torch.randn(tuple(shape), generator=generator, device=device, dtype=dtype)
 
 
-def make_rowmap(n_text: int, n_video: int, n_vip: int, hw: int, frames: int) -> RowMap:
-    return RowMap(n_text + n_video + n_vip, n_text, n_video, n_vip, hw, frames)
+def make_rowmap(n_text: int, n_video: int, n_vip: int, hw: int, frames: int, row0: int = 0, rows_local: int = 0) -> RowMap:
+    """row0 / rows_local: sequence-parallel shard (this rank holds rows [row0, row0+rows_local) of every batch); 0 = all."""
+    return RowMap(n_text + n_video + n_vip, n_text, n_video, n_vip, hw, frames, row0, rows_local)
+
+
+def rows_local(rowmap: RowMap) -> int:
+    return rowmap.rows_local or rowmap.rows_per_batch
 
 
 def make_modvec(text: Optional[torch.Tensor], video: Optional[torch.Tensor], vip: Optional[torch.Tensor]) -> ModVec:
@@ -247,16 +270,43 @@ def gemm_gate_residual(a: torch.Tensor, w: torch.Tensor, bias, x: torch.Tensor, 
 
 
 def qkv_rope_gemm(a: torch.Tensor, w: torch.Tensor, bias, B: int, H: int, rowmap: RowMap,
-                  projs: Sequence[QkvProj], ln_eps: float) -> None:
+                  projs: Sequence[QkvProj], ln_eps: float, scatter: Optional[QkvScatter] = None) -> None:
+    """scatter: sequence-parallel peer buffers (tg_qkv_rope_gemm_sp) — head h lands on rank h // (H // world)."""
     lib = load()
     K = a.shape[-1]
     arr = (QkvProj * len(projs))(*projs)
     with _Timed(f"qkv_rope_gemm[{a.shape[0]}x{w.shape[0]}x{K}]", 1):
-        _check(lib.tg_qkv_rope_gemm(_bf16_cuda(a, "a").data_ptr(), a.stride(-2), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
-                                    B, H, K, C.byref(rowmap), arr, len(projs), float(ln_eps), _stream()), "tg_qkv_rope_gemm")
+        if scatter is None:
+            _check(lib.tg_qkv_rope_gemm(_bf16_cuda(a, "a").data_ptr(), a.stride(-2), _bf16_cuda(w, "w").data_ptr(), _ptr(bias),
+                                        B, H, K, C.byref(rowmap), arr, len(projs), float(ln_eps), _stream()), "tg_qkv_rope_gemm")
+        else:
+            _check(lib.tg_qkv_rope_gemm_sp(_bf16_cuda(a, "a").data_ptr(), a.stride(-2), _bf16_cuda(w, "w").data_ptr(),
+                                           _ptr(bias), B, H, K, C.byref(rowmap), arr, len(projs), float(ln_eps),
+                                           C.byref(scatter), _stream()), "tg_qkv_rope_gemm_sp")
 
 
-def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, q_row0: int = 0,
+def make_qkv_scatter(peer_ptrs: Sequence[Sequence[int]]) -> QkvScatter:
+    """peer_ptrs[p][q]: device address (peer-mapped) of projection p's [B, H/world, out_rows, 64] buffer on rank q."""
+    sc = QkvScatter()
+    sc.world = len(peer_ptrs[0])
+    if not 1 <= sc.world <= MAX_PEERS or len(peer_ptrs) > 6:
+        raise TokensGenError("make_qkv_scatter: at most 6 projections over 1..8 ranks")
+    for p_, row in enumerate(peer_ptrs):
+        for q_, ptr in enumerate(row):
+            sc.peer[p_][q_] = ptr
+    return sc
+
+
+def make_attn_scatter(peer_ptrs: Sequence[int], chunk: int, rows_per_batch: int, H_total: int, head0: int) -> AttnScatter:
+    """peer_ptrs[q]: device address of rank q's [B, rows_local(q), H_total*64] attention-output buffer."""
+    sc = AttnScatter()
+    sc.world, sc.chunk, sc.rows_per_batch, sc.H_total, sc.head0 = len(peer_ptrs), chunk, rows_per_batch, H_total, head0
+    for q_, ptr in enumerate(peer_ptrs):
+        sc.peer[q_] = ptr
+    return sc
+
+
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out, *, q_row0: int = 0,
              q_rows: Optional[int] = None, kv_row0: int = 0, kv_rows: Optional[int] = None, out_row0: int = 0,
              softmax_scale: Optional[float] = None, accumulate: bool = False, out_scale: float = 1.0) -> None:
     """q [B,H,Nq_alloc,64], k/v [B,H,Nkv_alloc,64] (same alloc for k and v), out [B,Nout_alloc,H*64]."""
@@ -270,6 +320,12 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
     q_rows = nq_alloc - q_row0 if q_rows is None else q_rows
     kv_rows = nkv_alloc - kv_row0 if kv_rows is None else kv_rows
     scale = D ** -0.5 if softmax_scale is None else softmax_scale
+    if isinstance(out, AttnScatter):
+        with _Timed(f"attn_fwd[q{q_rows},kv{kv_rows}]", 1):
+            _check(lib.tg_attn_fwd_sp(_bf16_cuda(q, "q").data_ptr(), nq_alloc, q_row0, q_rows, _bf16_cuda(k, "k").data_ptr(),
+                                      _bf16_cuda(v, "v").data_ptr(), nkv_alloc, kv_row0, kv_rows, C.byref(out), out_row0, B, H,
+                                      float(scale), int(accumulate), float(out_scale), _stream()), "tg_attn_fwd_sp")
+        return
     with _Timed(f"attn_fwd[q{q_rows},kv{kv_rows}]", 1):
         _check(lib.tg_attn_fwd(_bf16_cuda(q, "q").data_ptr(), nq_alloc, q_row0, q_rows, _bf16_cuda(k, "k").data_ptr(),
                                _bf16_cuda(v, "v").data_ptr(), nkv_alloc, kv_row0, kv_rows, _bf16_cuda(out, "out").data_ptr(),
@@ -277,7 +333,7 @@ def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tenso
                "tg_attn_fwd")
 
 
-def attn_fwd_pair(q, k, v, q_rows: int, kv_rows: int, q2, k2, v2, kv_row0_2: int, kv_rows2: int, out: torch.Tensor,
+def attn_fwd_pair(q, k, v, q_rows: int, kv_rows: int, q2, k2, v2, kv_row0_2: int, kv_rows2: int, out,
                   out_scale2: float, softmax_scale: Optional[float] = None) -> None:
     """Self-attention (q,k,v rows [0,q_rows)/[0,kv_rows)) + out_scale2 * cross-attention of q2 to rows
     [kv_row0_2, +kv_rows2) of k2/v2, one launch (tg_attn_fwd_pair)."""
@@ -285,6 +341,14 @@ def attn_fwd_pair(q, k, v, q_rows: int, kv_rows: int, q2, k2, v2, kv_row0_2: int
     B, H, alloc, D = q.shape
     alloc2 = q2.shape[2]
     scale = D ** -0.5 if softmax_scale is None else softmax_scale
+    if isinstance(out, AttnScatter):
+        with _Timed(f"attn_fwd_pair[q{q_rows},kv{kv_rows}+kv{kv_rows2}]", 1):
+            _check(lib.tg_attn_fwd_pair_sp(_bf16_cuda(q, "q").data_ptr(), _bf16_cuda(k, "k").data_ptr(),
+                                           _bf16_cuda(v, "v").data_ptr(), alloc, q_rows, kv_rows, _bf16_cuda(q2, "q2").data_ptr(),
+                                           _bf16_cuda(k2, "k2").data_ptr(), _bf16_cuda(v2, "v2").data_ptr(), alloc2, kv_row0_2,
+                                           kv_rows2, C.byref(out), B, H, float(scale), float(out_scale2), _stream()),
+                   "tg_attn_fwd_pair_sp")
+        return
     with _Timed(f"attn_fwd_pair[q{q_rows},kv{kv_rows}+kv{kv_rows2}]", 1):
         _check(lib.tg_attn_fwd_pair(_bf16_cuda(q, "q").data_ptr(), _bf16_cuda(k, "k").data_ptr(), _bf16_cuda(v, "v").data_ptr(),
                                     alloc, q_rows, kv_rows, _bf16_cuda(q2, "q2").data_ptr(), _bf16_cuda(k2, "k2").data_ptr(),

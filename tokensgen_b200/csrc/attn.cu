@@ -45,7 +45,22 @@ struct AttnParams {
     float out_scale2;  // v3 pass 1: out += out_scale2 * attn2
     int mutex;    // v2: the two tiles take turns on the MUFU pipe (named-barrier hand-off) instead of sharing it
     int stagger;  // v2: cycles by which tile 1 starts after tile 0 (keeps the two tiles' softmax phases interleaved)
+    // sequence-parallel scatter of the output rows (tg_attn_fwd_sp): sp_world > 0 -> row g of a batch goes to its owner rank
+    int sp_world, sp_chunk, sp_rows, sp_h_total, sp_head0;
+    __nv_bfloat16* sp_peer[TG_MAX_PEERS];
 };
+
+// Address of output row (batch b, query q_row) of local head h: token-major [B, rows, H*64] locally, or — sequence
+// parallel — the row's owner rank's [B, rows_local(owner), H_total*64] buffer over NVLink (second Ulysses all-to-all).
+__device__ __forceinline__ __nv_bfloat16* attn_out_row(const AttnParams& p, int b, int h, int q_row) {
+    if (p.sp_world > 0) {
+        const int g = int(p.out_row0) + q_row;
+        const int owner = min(g / p.sp_chunk, p.sp_world - 1);
+        const int rl = owner == p.sp_world - 1 ? p.sp_rows - owner * p.sp_chunk : p.sp_chunk;
+        return p.sp_peer[owner] + ((int64_t(b) * rl + (g - owner * p.sp_chunk)) * p.sp_h_total + p.sp_head0 + h) * AT_D;
+    }
+    return p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D;
+}
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -294,7 +309,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const bool store = q_row < p.q_rows;
         const int b = bh / p.H, h = bh - b * p.H;
         __nv_bfloat16* o_ptr =
-            p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D;
+            attn_out_row(p, b, h, q_row);
         uint4 prev[8];
         if (store && p.accumulate) {  // all loads of the read-modify-write first (see gemm.cu: epi_gate_residual)
 #pragma unroll
@@ -649,7 +664,7 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const bool store = q_row < p.q_rows;
         const int b = bh / p.H, h = bh - b * p.H;
         __nv_bfloat16* o_ptr =
-            p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D + half * 32;
+            attn_out_row(p, b, h, q_row) + half * 32;
         uint4 prev[4];
         if (store && p.accumulate) {
 #pragma unroll
@@ -1059,7 +1074,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         const bool store = q_row < p.q_rows;
         const int b = bh / p.H, h = bh - b * p.H;
         __nv_bfloat16* o_ptr =
-            p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D + half * 32;
+            attn_out_row(p, b, h, q_row) + half * 32;
         uint4 prev[4];
         if (store && accumulate) {
 #pragma unroll
@@ -1142,10 +1157,31 @@ static int dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, con
 
 using namespace tg;
 
-extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
-                           const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, tg_bf16* out,
-                           int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,
-                           float out_scale, void* stream) {
+// Validates a tg_attn_scatter for output rows [out_row0, out_row0 + q_rows) and copies it into the kernel parameters.
+static int set_scatter(AttnParams& p, const tg_attn_scatter* sc, int64_t out_row0, int q_rows, int H) {
+    if (sc->world < 1 || sc->world > TG_MAX_PEERS || sc->chunk <= 0 || sc->rows_per_batch <= 0 ||
+        int64_t(sc->chunk) * (sc->world - 1) >= sc->rows_per_batch || int64_t(sc->chunk) * sc->world < sc->rows_per_batch)
+        return fail(-9, "attn_fwd_sp: bad shard geometry (world=%d chunk=%d rows=%d)", sc->world, sc->chunk, sc->rows_per_batch);
+    if (sc->head0 < 0 || sc->head0 + H > sc->H_total) return fail(-9, "attn_fwd_sp: heads [%d, %d) outside H_total=%d", sc->head0, sc->head0 + H, sc->H_total);
+    if (out_row0 < 0 || out_row0 + q_rows > sc->rows_per_batch) return fail(-4, "attn_fwd_sp: output rows outside the batch");
+    for (int i = 0; i < sc->world; ++i) {
+        if (sc->peer[i] == nullptr || (reinterpret_cast<uintptr_t>(sc->peer[i]) & 15))
+            return fail(-9, "attn_fwd_sp: no (16-byte aligned) output buffer for rank %d", i);
+        p.sp_peer[i] = reinterpret_cast<__nv_bfloat16*>(sc->peer[i]);
+    }
+    p.sp_world = sc->world;
+    p.sp_chunk = sc->chunk;
+    p.sp_rows = sc->rows_per_batch;
+    p.sp_h_total = sc->H_total;
+    p.sp_head0 = sc->head0;
+    return 0;
+}
+
+static int attn_fwd_impl(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
+                         const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, tg_bf16* out,
+                         int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,
+                         float out_scale, const tg_attn_scatter* scatter, void* stream) {
+    if (scatter != nullptr) { out = scatter->peer[0]; out_rows_alloc = scatter->rows_per_batch; }
     if (!q || !k || !v || !out) return fail(-1, "attn_fwd: null pointer");
     if (B <= 0 || H <= 0 || q_rows <= 0 || kv_rows <= 0) return fail(-2, "attn_fwd: non-positive shape");
     if (q_row0 < 0 || kv_row0 < 0 || q_row0 + q_rows > q_rows_alloc || kv_row0 + kv_rows > kv_rows_alloc)
@@ -1180,6 +1216,10 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     p.stagger = g_attn_stagger;
     p.trace = g_attn_trace;
     p.mutex = g_attn_mutex;
+    if (scatter != nullptr) {
+        rc = set_scatter(p, scatter, out_row0, q_rows, H);
+        if (rc) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
@@ -1198,6 +1238,23 @@ extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row
     return check_launch("attn_fwd");
 }
 
+extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
+                           const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, tg_bf16* out,
+                           int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,
+                           float out_scale, void* stream) {
+    return attn_fwd_impl(q, q_rows_alloc, q_row0, q_rows, k, v, kv_rows_alloc, kv_row0, kv_rows, out, out_rows_alloc, out_row0,
+                         B, H, softmax_scale, accumulate, out_scale, nullptr, stream);
+}
+
+extern "C" int tg_attn_fwd_sp(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
+                              const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows,
+                              const tg_attn_scatter* out, int64_t out_row0, int B, int H, float softmax_scale,
+                              int accumulate, float out_scale, void* stream) {
+    if (out == nullptr) return fail(-1, "attn_fwd_sp: scatter is null");
+    return attn_fwd_impl(q, q_rows_alloc, q_row0, q_rows, k, v, kv_rows_alloc, kv_row0, kv_rows, nullptr, 0, out_row0, B, H,
+                         softmax_scale, accumulate, out_scale, out, stream);
+}
+
 static int tg::dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                               const CUtensorMap& tq2, const CUtensorMap& tk2, const CUtensorMap& tv2, const AttnParams& p) {
 #define TG_A3(E)                                                                                      \
@@ -1211,10 +1268,11 @@ static int tg::dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq,
 #undef TG_A3
 }
 
-extern "C" int tg_attn_fwd_pair(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
-                                const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
-                                int kv_rows2, tg_bf16* out, int64_t out_rows_alloc, int B, int H, float softmax_scale,
-                                float out_scale2, void* stream) {
+static int attn_fwd_pair_impl(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
+                              const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
+                              int kv_rows2, tg_bf16* out, int64_t out_rows_alloc, int B, int H, float softmax_scale,
+                              float out_scale2, const tg_attn_scatter* scatter, void* stream) {
+    if (scatter != nullptr) { out = scatter->peer[0]; out_rows_alloc = scatter->rows_per_batch; }
     if (!q || !k || !v || !q2 || !k2 || !v2 || !out) return fail(-1, "attn_fwd_pair: null pointer");
     if (B <= 0 || H <= 0 || q_rows <= 0 || kv_rows <= 0 || kv_rows2 <= 0) return fail(-2, "attn_fwd_pair: non-positive shape");
     if (q_rows > rows_alloc || kv_rows > rows_alloc || q_rows > rows_alloc2 || kv_row0_2 < 0 || kv_row0_2 + kv_rows2 > rows_alloc2)
@@ -1252,8 +1310,29 @@ extern "C" int tg_attn_fwd_pair(const tg_bf16* q, const tg_bf16* k, const tg_bf1
     p.n_pass = 2;
     p.kv_rows2 = kv_rows2;
     p.out_scale2 = out_scale2;
+    if (scatter != nullptr) {
+        rc = set_scatter(p, scatter, 0, q_rows, H);
+        if (rc) return rc;
+    }
     dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
     return dispatch_attn3(grid, static_cast<cudaStream_t>(stream), tq, tk, tv, tq2, tk2, tv2, p);
+}
+
+extern "C" int tg_attn_fwd_pair(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
+                                const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2, int64_t kv_row0_2,
+                                int kv_rows2, tg_bf16* out, int64_t out_rows_alloc, int B, int H, float softmax_scale,
+                                float out_scale2, void* stream) {
+    return attn_fwd_pair_impl(q, k, v, rows_alloc, q_rows, kv_rows, q2, k2, v2, rows_alloc2, kv_row0_2, kv_rows2, out,
+                              out_rows_alloc, B, H, softmax_scale, out_scale2, nullptr, stream);
+}
+
+extern "C" int tg_attn_fwd_pair_sp(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows,
+                                   int kv_rows, const tg_bf16* q2, const tg_bf16* k2, const tg_bf16* v2, int64_t rows_alloc2,
+                                   int64_t kv_row0_2, int kv_rows2, const tg_attn_scatter* out, int B, int H,
+                                   float softmax_scale, float out_scale2, void* stream) {
+    if (out == nullptr) return fail(-1, "attn_fwd_pair_sp: scatter is null");
+    return attn_fwd_pair_impl(q, k, v, rows_alloc, q_rows, kv_rows, q2, k2, v2, rows_alloc2, kv_row0_2, kv_rows2, nullptr, 0, B, H,
+                              softmax_scale, out_scale2, out, stream);
 }
 
 extern "C" int tg_debug_attn_trace(void* device_buffer) {  // developer hook, not in the public header

@@ -18,6 +18,17 @@ int check_launch(const char* what);
 
 int sm_count();
 
+// tg_rowmap sequence-parallel shard (row0, rows_local): rows_local == 0 means "all rows of the batch".
+inline bool rowmap_shard_ok(const tg_rowmap* m) {
+    if (m->rows_local == 0) return m->row0 == 0;
+    return m->row0 >= 0 && m->rows_local > 0 && m->row0 + m->rows_local <= m->rows_per_batch;
+}
+inline tg_rowmap normalised_rowmap(const tg_rowmap* m) {
+    tg_rowmap r = *m;
+    if (r.rows_local == 0) { r.rows_local = r.rows_per_batch; r.row0 = 0; }
+    return r;
+}
+
 // Row-major bf16 tensor maps with 128-byte swizzle and zero fill of out-of-bounds elements.
 //   2D: dims (inner, rows), box (box_inner, box_rows), row stride in bytes.
 //   3D: dims (inner, rows, batch), box (box_inner, box_rows, 1).

@@ -57,8 +57,8 @@ __global__ void __launch_bounds__(256, (NV <= 12) ? 2 : 1) ln_modulate_packed_ke
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
     if (row >= p.M) return;
-    const int b = row / p.map.rows_per_batch;
-    const int r = row - b * p.map.rows_per_batch;
+    const int b = row / p.map.rows_local;  // host entry normalises rows_local (> 0) / row0: sequence-parallel shard
+    const int r = row - b * p.map.rows_local + p.map.row0;
     int seg, frame = 0;
     if (r < p.map.n_text) seg = 0;
     else if (r < p.map.n_text + p.map.n_video) { seg = 1; frame = (r - p.map.n_text) / p.map.hw; }
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
     if (row >= p.M) return;
-    const int b = row / p.map.rows_per_batch;
-    const int r = row - b * p.map.rows_per_batch;
+    const int b = row / p.map.rows_local;  // host entry normalises rows_local (> 0) / row0: sequence-parallel shard
+    const int r = row - b * p.map.rows_local + p.map.row0;
     int seg, frame = 0;
     if (r < p.map.n_text) seg = 0;
     else if (r < p.map.n_text + p.map.n_video) { seg = 1; frame = (r - p.map.n_text) / p.map.hw; }
@@ -416,15 +416,16 @@ extern "C" int tg_ln_modulate(const tg_bf16* x, tg_bf16* out, int B, int d, cons
     if (map->rows_per_batch != map->n_text + map->n_video + map->n_vip || map->rows_per_batch <= 0 || map->frames <= 0 ||
         (map->n_video > 0 && (map->hw <= 0 || map->n_video != map->hw * map->frames)))
         return fail(-3, "ln_modulate: inconsistent rowmap");
+    if (!rowmap_shard_ok(map)) return fail(-3, "ln_modulate: rowmap shard [row0, row0+rows_local) outside the batch");
     if (!ln_w || !ln_b) return fail(-4, "ln_modulate: ln_w/ln_b required");
     if (map->n_vip > 0 && shift->vip && (!vip_ln_w || !vip_ln_b)) return fail(-5, "ln_modulate: vip rows need vip_ln_w/b");
     if ((ln2_w == nullptr) != (ln2_b == nullptr)) return fail(-6, "ln_modulate: ln2_w/ln2_b must come together");
     LnParams p{};
     p.x = reinterpret_cast<const __nv_bfloat16*>(x);
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
-    p.M = B * map->rows_per_batch;
+    p.map = normalised_rowmap(map);
+    p.M = B * p.map.rows_local;
     p.d = d;
-    p.map = *map;
     p.ln_w = reinterpret_cast<const __nv_bfloat16*>(ln_w);
     p.ln_b = reinterpret_cast<const __nv_bfloat16*>(ln_b);
     p.vip_ln_w = reinterpret_cast<const __nv_bfloat16*>(vip_ln_w);

@@ -51,6 +51,10 @@ struct GemmParams {
     QkvProjDev proj[6];
     int heads;
     float ln_eps;
+    // EPI_QKV, sequence-parallel scatter (tg_qkv_rope_gemm_sp): sp_world > 1 -> head h of projection j goes to
+    // sp_peer[j][h / sp_hpr], laid out [B, sp_hpr, out_rows, 64]
+    int sp_world, sp_hpr;
+    __nv_bfloat16* sp_peer[6][TG_MAX_PEERS];
 };
 
 template <int BLOCK_N>
@@ -69,8 +73,8 @@ struct RowInfo {
 };
 __device__ __forceinline__ RowInfo row_info(const tg_rowmap& m, int row) {
     RowInfo ri;
-    ri.b = row / m.rows_per_batch;
-    ri.r = row - ri.b * m.rows_per_batch;
+    ri.b = row / m.rows_local;  // host entries pass normalised_rowmap(): rows_local > 0
+    ri.r = row - ri.b * m.rows_local + m.row0;
     if (ri.r < m.n_text) {
         ri.seg = 0;
         ri.frame = 0;
@@ -227,7 +231,13 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], i
             acc[i + 3] = x3 * c.w + x2 * s.w;
         }
     }
-    __nv_bfloat16* o = pr.out + (int64_t(ri.b * p.heads + head) * pr.out_rows + ri.r) * 64;
+    __nv_bfloat16* o;
+    if (p.sp_world > 1) {  // Ulysses all-to-all fused into the store: the head's owner rank receives the row over NVLink
+        const int dst = head / p.sp_hpr;
+        o = p.sp_peer[pi][dst] + (int64_t(ri.b * p.sp_hpr + (head - dst * p.sp_hpr)) * pr.out_rows + ri.r) * 64;
+    } else {
+        o = pr.out + (int64_t(ri.b * p.heads + head) * pr.out_rows + ri.r) * 64;
+    }
 #pragma unroll
     for (int i = 0; i < 64; i += 8) store8_bf16(o + i, &acc[i]);
 }
@@ -674,6 +684,7 @@ static int check_rowmap(const tg_rowmap* map) {
     if (map->n_video > 0 && (map->hw <= 0 || map->frames <= 0 || map->n_video != map->hw * map->frames))
         return fail(-12, "rowmap: n_video must equal hw*frames");
     if (map->frames <= 0) return fail(-13, "rowmap: frames must be positive");
+    if (!rowmap_shard_ok(map)) return fail(-13, "rowmap: shard [row0, row0+rows_local) outside the batch");
     return 0;
 }
 
@@ -683,7 +694,7 @@ extern "C" int tg_gemm_gate_residual(const tg_bf16* A, int64_t lda, const tg_bf1
     int rc = check_rowmap(map);
     if (rc) return rc;
     if (B <= 0) return fail(-2, "gemm_gate_residual: B=%d", B);
-    const int M = B * map->rows_per_batch;
+    const int M = B * normalised_rowmap(map).rows_local;
     rc = check_common(A, lda, W, M, N, K);
     if (rc) return rc;
     if (X == nullptr || ldx % 8 != 0 || ldx < N || (reinterpret_cast<uintptr_t>(X) & 15))
@@ -696,33 +707,45 @@ extern "C" int tg_gemm_gate_residual(const tg_bf16* A, int64_t lda, const tg_bf1
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
     p.out = reinterpret_cast<__nv_bfloat16*>(X);
     p.ldo = ldx;
-    p.map = *map;
+    p.map = normalised_rowmap(map);
     p.gate = *gate;
     return dispatch<EPI_GATE_RESIDUAL>(reinterpret_cast<const __nv_bfloat16*>(A), lda,
                                        reinterpret_cast<const __nv_bfloat16*>(W), p,
                                        static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H,
-                                int K, const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps,
-                                void* stream) {
+static int qkv_rope_gemm_impl(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H,
+                              int K, const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps,
+                              const tg_qkv_scatter* scatter, void* stream) {
     int rc = check_rowmap(map);
     if (rc) return rc;
     if (B <= 0 || H <= 0) return fail(-2, "qkv_rope_gemm: B=%d H=%d", B, H);
     if (nproj < 1 || nproj > 6 || proj == nullptr) return fail(-16, "qkv_rope_gemm: nproj=%d (1..6)", nproj);
     if ((H * 64) % 256 != 0) return fail(-17, "qkv_rope_gemm: H*64 must be a multiple of 256");
-    const int M = B * map->rows_per_batch;
+    const int M = B * normalised_rowmap(map).rows_local;
     const int N = nproj * H * 64;
     rc = check_common(A, lda, W, M, N, K);
     if (rc) return rc;
     GemmParams p{};
     p.M = M; p.N = N; p.K = K;
     p.bias = reinterpret_cast<const __nv_bfloat16*>(bias);
-    p.map = *map;
+    p.map = normalised_rowmap(map);
     p.heads = H;
     p.ln_eps = ln_eps;
+    if (scatter != nullptr) {
+        if (scatter->world < 1 || scatter->world > TG_MAX_PEERS || H % scatter->world != 0)
+            return fail(-20, "qkv_rope_gemm_sp: world=%d must be in 1..%d and divide H=%d", scatter->world, TG_MAX_PEERS, H);
+        p.sp_world = scatter->world;
+        p.sp_hpr = H / scatter->world;
+        for (int i = 0; i < nproj; ++i)
+            for (int q = 0; q < scatter->world; ++q) {
+                if (scatter->peer[i][q] == nullptr || (reinterpret_cast<uintptr_t>(scatter->peer[i][q]) & 15))
+                    return fail(-21, "qkv_rope_gemm_sp: projection %d has no (16-byte aligned) buffer on rank %d", i, q);
+                p.sp_peer[i][q] = reinterpret_cast<__nv_bfloat16*>(scatter->peer[i][q]);
+            }
+    }
     for (int i = 0; i < nproj; ++i) {
-        if (proj[i].out == nullptr || proj[i].out_rows <= 0 || proj[i].out_rows > map->rows_per_batch)
+        if ((scatter == nullptr && proj[i].out == nullptr) || proj[i].out_rows <= 0 || proj[i].out_rows > map->rows_per_batch)
             return fail(-18, "qkv_rope_gemm: projection %d has a bad output", i);
         if ((proj[i].ln_w == nullptr) != (proj[i].ln_b == nullptr) ||
             (proj[i].cos_video == nullptr) != (proj[i].sin_video == nullptr) ||
@@ -739,6 +762,19 @@ extern "C" int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W,
     }
     return dispatch<EPI_QKV>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
                              p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H,
+                                int K, const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps,
+                                void* stream) {
+    return qkv_rope_gemm_impl(A, lda, W, bias, B, H, K, map, proj, nproj, ln_eps, nullptr, stream);
+}
+
+extern "C" int tg_qkv_rope_gemm_sp(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H,
+                                   int K, const tg_rowmap* map, const tg_qkv_proj* proj, int nproj, float ln_eps,
+                                   const tg_qkv_scatter* scatter, void* stream) {
+    if (scatter == nullptr) return fail(-20, "qkv_rope_gemm_sp: scatter is null");
+    return qkv_rope_gemm_impl(A, lda, W, bias, B, H, K, map, proj, nproj, ln_eps, scatter, stream);
 }
 
 extern "C" int tg_set_gemm_impl(int impl) {  // developer hook (1 = single-CTA tiles, 2 = CTA pairs); not in the public header

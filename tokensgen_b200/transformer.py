@@ -245,6 +245,8 @@ def _attention_core(attn, proc, y, B, rowmap, rope, img_rope, cond_rope, bufs):
     w, b = cache.get(linears)
     eps = attn.norm_q.eps if attn.norm_q is not None else 1e-6
     projs = _qkv_projs(attn, proc, bufs.qkv, n_tv, rope, img_rope, cond_rope)
+    if getattr(bufs, "sp", None) is not None:
+        return _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs)
     E.qkv_rope_gemm(y, w, b, B, H, rowmap, projs, eps)
     qb, kb, vb = bufs.qkv[:3]
     side = None
@@ -283,6 +285,37 @@ def _attention_core(attn, proc, y, B, rowmap, rope, img_rope, cond_rope, bufs):
             E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
         else:
             torch.cuda.current_stream().wait_stream(side)
+
+
+def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
+    """Sequence-parallel form of the kernel sequence K3 -> K4 -> K5 -> K6 (seqpar.py): y holds this rank's rows; the Q/K/V
+    GEMM scatters heads to their owner ranks, the attention kernels (this rank's heads, all rows) scatter output rows to
+    theirs.  Two cross-rank stream barriers order producers before consumers; the second also keeps the next layer's Q/K/V
+    stores behind every rank's attention reads."""
+    sp = bufs.sp
+    n_tv = rowmap.n_text + rowmap.n_video
+    E.qkv_rope_gemm(y, w, b, B, attn.heads, rowmap, projs, eps, scatter=bufs.qkv_scatter)
+    sp.barrier()
+    qb, kb, vb = bufs.qkv[:3]
+    out = bufs.attn_scatter
+    if proc is None:
+        E.attn_fwd(qb, kb, vb, out, out_row0=0)
+    else:
+        qv, kv, vv = bufs.qkv[3:]
+        scale = proc.scale
+        scales = [float(s_) for s_ in (scale if isinstance(scale, (list, tuple)) else [scale])]
+        if len(scales) != B:
+            scales = [scales[0]] * B  # attention_processor.py:2130-2131
+        if len(set(scales)) == 1:
+            # K4 + K5 in one launch: the vip cross-attention is added before the row leaves the SM, so the peer buffer is
+            # written once instead of read-modified-written over NVLink
+            E.attn_fwd_pair(qb, kb, vb, n_tv, n_tv, qv, kv, vv, n_tv, rowmap.n_vip, out, _bf16_scalar(scales[0]))
+        else:
+            for bi, s_ in enumerate(scales):
+                E.attn_fwd_pair(qb[bi:bi + 1], kb[bi:bi + 1], vb[bi:bi + 1], n_tv, n_tv, qv[bi:bi + 1], kv[bi:bi + 1],
+                                vv[bi:bi + 1], n_tv, rowmap.n_vip, bufs.attn_scatter_for_batch(bi), _bf16_scalar(s_))
+        E.attn_fwd(qv, kv, vv, out, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
+    sp.barrier()
 
 
 # Both measured neutral on the power-capped step (839.8 ms either way, profiles/r01_energy.md): off by default so that the
@@ -386,7 +419,7 @@ class CogVideoXBlock(nn.Module):
         """One block on the resident stream bufs.X.  `ada` [B*frames, *]: this block's AdaLN vectors start at column col0
         in the order norm1(6d) | norm2(6d) | vip_norm1(3d) | vip_norm2(3d)."""
         d = self.dim
-        rows = rowmap.rows_per_batch
+        rows = E.rows_local(rowmap)  # all rows, or this rank's shard (sequence parallel)
         proc = self.attn1.processor if self.use_vip else None
         X2, Y2 = bufs.X.view(B * rows, d), bufs.Y.view(B * rows, d)
         c = lambda i: ada[:, col0 + i * d: col0 + (i + 1) * d]
@@ -515,6 +548,17 @@ class CogVideoXTransformer3DModel(nn.Module):
                 assert key in own, key
             self.load_state_dict(sd, strict=False)
 
+    def enable_sequence_parallel(self, group=None) -> None:
+        """Runs every later forward sequence-parallel (Ulysses) over `group` (default: all ranks): all ranks must call
+        forward with identical inputs and all get the full output.  See tokensgen_b200/seqpar.py."""
+        from .seqpar import SeqParallel
+        self.__dict__["_tg_sp"] = SeqParallel(group)
+        self._tg_bufs.clear()
+
+    def disable_sequence_parallel(self) -> None:
+        self.__dict__.pop("_tg_sp", None)
+        self._tg_bufs.clear()
+
     def save_vip_layers(self, vip_ckpt_dir=None):
         assert self.use_vip
         out = {n: p.to("cpu").to(torch.float32) for n, p in self.named_parameters() if "vip_" in n}
@@ -574,12 +618,18 @@ class CogVideoXTransformer3DModel(nn.Module):
         ada = self._ada_table(silu_emb)
 
         rowmap = E.make_rowmap(n_text, n_video, n_vip, n_video // frames, frames)
-        key = (B, n_text, n_video, n_vip, str(dev))
+        sp = self.__dict__.get("_tg_sp")
+        key = (B, n_text, n_video, n_vip, str(dev), sp is not None)
         if key not in self._tg_bufs:
             self._tg_bufs.clear()
-            self._tg_bufs[key] = _Buffers(B, rowmap, d, cfg.num_attention_heads,
-                                          self.transformer_blocks[0].ff.net[0].proj.out_features, use_vip, dev)
+            ff_dim = self.transformer_blocks[0].ff.net[0].proj.out_features
+            if sp is None:
+                self._tg_bufs[key] = _Buffers(B, rowmap, d, cfg.num_attention_heads, ff_dim, use_vip, dev)
+            else:
+                from .seqpar import ShardedBuffers
+                self._tg_bufs[key] = ShardedBuffers(sp, B, rowmap, d, cfg.num_attention_heads, ff_dim, use_vip, dev)
         bufs = self._tg_bufs[key]
+        x_full = bufs.X if sp is None else bufs.Xfull  # sequence parallel: every rank embeds all rows, keeps its shard
 
         # 2. patch embedding (K9) straight into the resident stream [text | video | vip]
         pe = self.patch_embed
@@ -592,10 +642,13 @@ class CogVideoXTransformer3DModel(nn.Module):
         if use_vip:
             vip_rows = vip_encoder_hidden_states.to(torch.bfloat16).permute(0, 1, 3, 4, 2).reshape(B, n_vip, -1).contiguous()
         for b in range(B):
-            E.gemm_bias_act(text[b].contiguous(), pe.text_proj.weight, pe.text_proj.bias, bufs.X[b, :n_text])
-            E.gemm_bias_act(patches[b * n_video:(b + 1) * n_video], pw, pe.proj.bias, bufs.X[b, n_text:n_text + n_video])
+            E.gemm_bias_act(text[b].contiguous(), pe.text_proj.weight, pe.text_proj.bias, x_full[b, :n_text])
+            E.gemm_bias_act(patches[b * n_video:(b + 1) * n_video], pw, pe.proj.bias, x_full[b, n_text:n_text + n_video])
             if use_vip:
-                E.gemm_bias_act(vip_rows[b], pe.vip_proj.weight, pe.vip_proj.bias, bufs.X[b, n_text + n_video:])
+                E.gemm_bias_act(vip_rows[b], pe.vip_proj.weight, pe.vip_proj.bias, x_full[b, n_text + n_video:])
+        if sp is not None:
+            bufs.X.copy_(x_full[:, bufs.row0:bufs.row0 + bufs.rows_local])
+            rowmap = bufs.rowmap  # same layout + this rank's (row0, rows_local)
 
         # 3. blocks
         rope = _rope_pair(image_rotary_emb, dev)
@@ -609,7 +662,8 @@ class CogVideoXTransformer3DModel(nn.Module):
         col = len(self.transformer_blocks) * per_block
         shift = E.make_modvec(None, ada[:, col:col + d], None)
         scale = E.make_modvec(None, ada[:, col + d:col + 2 * d], None)
-        X2, Y2 = bufs.X.view(B * rowmap.rows_per_batch, d), bufs.Y.view(B * rowmap.rows_per_batch, d)
+        rows_l = E.rows_local(rowmap)
+        X2, Y2 = bufs.X.view(B * rows_l, d), bufs.Y.view(B * rows_l, d)
         E.ln_modulate(X2, Y2, B, rowmap, self.norm_final.weight, self.norm_final.bias, None, None, cfg.norm_eps, shift, scale,
                       ln2_w=self.norm_out.norm.weight, ln2_b=self.norm_out.norm.bias, eps2=cfg.norm_eps)
         n_out = self.proj_out.out_features
@@ -617,9 +671,18 @@ class CogVideoXTransformer3DModel(nn.Module):
         if n_out % 64:  # patch_size 1: N = 16 -> zero rows up to 64, sliced away below
             ow = self._padded("out_w", self.proj_out.weight, lambda w: torch.nn.functional.pad(w, (0, 0, 0, -w.shape[0] % 64)))
             ob = self._padded("out_b", self.proj_out.bias, lambda b_: torch.nn.functional.pad(b_, (0, -b_.shape[0] % 64)))
-        out_rows = torch.empty(B * n_video, ow.shape[0], device=dev, dtype=torch.bfloat16)
-        for b in range(B):
-            E.gemm_bias_act(bufs.Y[b, n_text:n_text + n_video], ow, ob, out_rows[b * n_video:(b + 1) * n_video])
+        if sp is None:
+            out_rows = torch.empty(B * n_video, ow.shape[0], device=dev, dtype=torch.bfloat16)
+            for b in range(B):
+                E.gemm_bias_act(bufs.Y[b, n_text:n_text + n_video], ow, ob, out_rows[b * n_video:(b + 1) * n_video])
+        else:
+            # proj_out over this rank's rows (text / vip rows of Y hold stale data: they are sliced away after the gather),
+            # then ONE small all-gather of the [rows, p*p*C] projections
+            loc = torch.zeros(B, bufs.chunk, ow.shape[0], device=dev, dtype=torch.bfloat16)
+            for b in range(B):
+                E.gemm_bias_act(bufs.Y[b], ow, ob, loc[b, :rows_l])
+            out_rows = sp.gather_rows(loc, bufs.chunk, rowmap.rows_per_batch)[:, n_text:n_text + n_video]
+            out_rows = out_rows.reshape(B * n_video, ow.shape[0]).contiguous()
         if ow.shape[0] != n_out:
             out_rows = out_rows[:, :n_out].contiguous()
         output = E.unpatchify(out_rows, B, F, self.proj_out.out_features // (p * p), Hh, Ww, p)
