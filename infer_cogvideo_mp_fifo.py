@@ -77,7 +77,11 @@ def main(args):
     pipe = init_pipeline(local, args, dtype)              # every rank loads its own weights, in parallel
     # with >= 2 ranks the serial base clip runs CFG-parallel on ranks 0 and 1 (one guidance branch each; `cfg_parallel: false`
     # in the yaml turns it off).  new_group is collective: every rank creates it.
-    cfg_group = dist.new_group([0, 1]) if world > 1 and args.get("cfg_parallel", True) else None
+    # `sequence_parallel: true` (schema extension; default with more than two ranks whose count divides the head count):
+    # instead, EVERY rank runs the base clip with each DiT forward sharded over all ranks (tokensgen_b200/seqpar.py).
+    heads = pipe.transformer.config.num_attention_heads
+    seq_par = world > 1 and bool(args.get("sequence_parallel", world > 2)) and heads % world == 0 and not args.use_2nd_stage
+    cfg_group = dist.new_group([0, 1]) if world > 1 and args.get("cfg_parallel", True) and not seq_par else None
     pipe_list = [pipe]
     vip_params = args.video_ipadapter_params if args.use_vip else None
 
@@ -122,7 +126,7 @@ def main(args):
             pe = torch.load(args.prompt_embeds_path, weights_only=True)
             call.update(prompt=None, prompt_embeds=pe["prompt_embeds"], negative_prompt_embeds=pe["negative_prompt_embeds"])
         video = image_embeddings = base_outputs = None
-        base_rank = rank == 0 or (cfg_group is not None and rank == 1 and not args.use_2nd_stage)
+        base_rank = rank == 0 or seq_par or (cfg_group is not None and rank == 1 and not args.use_2nd_stage)
         if base_rank:
             if rank == 0:
                 print(f"Processing {name}: [{prompt}]")
@@ -141,7 +145,8 @@ def main(args):
                                        dps.start_t, dps.end_t, dps.max_num_chunks, dps.crop_to_fit)
             base_outputs = pipe(frames=video, image_embeddings=image_embeddings,
                                 generator=torch.Generator().manual_seed(args.seed),
-                                cfg_parallel_group=cfg_group if not args.use_2nd_stage else None, **call)
+                                cfg_parallel_group=cfg_group if not args.use_2nd_stage else None,
+                                sequence_parallel_group=dist.group.WORLD if seq_par else None, **call)
             base_outputs.condition_frames = None      # not needed by the FIFO stage; keeps the broadcast small
         else:
             pipe.preprare_for_fifo(**call)

@@ -179,8 +179,9 @@ __device__ __forceinline__ void epi_gate_residual(const GemmParams& p, float (&a
     }
 }
 
-// One head (64 columns) of one projection for one row.
-__device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], int row, int n) {
+// One head (64 columns) of one projection for one row: bias, LayerNorm(64), RoPE in place on `acc`; returns where the
+// row's 64 bf16 values go (nullptr: the row is not stored).
+__device__ __forceinline__ __nv_bfloat16* epi_qkv_compute(const GemmParams& p, float (&acc)[64], int row, int n) {
     add_bias<64>(acc, p.bias, n);
     const int inner = p.heads * 64;
     const int pi = n / inner;
@@ -207,9 +208,9 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], i
             for (int j = 0; j < 8; ++j) acc[i + j] = fmaf((acc[i + j] - mean) * rstd, w[j], b[j]);
         }
     }
-    if (row >= p.M) return;
+    if (row >= p.M) return nullptr;
     const RowInfo ri = row_info(p.map, row);
-    if (ri.r >= pr.out_rows) return;
+    if (ri.r >= pr.out_rows) return nullptr;
     const float* cs = nullptr;
     const float* sn = nullptr;
     if (ri.seg == 1 && pr.cos_video != nullptr) {
@@ -238,8 +239,43 @@ __device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], i
     } else {
         o = pr.out + (int64_t(ri.b * p.heads + head) * pr.out_rows + ri.r) * 64;
     }
+    return o;
+}
+
+__device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], int row, int n) {
+    __nv_bfloat16* o = epi_qkv_compute(p, acc, row, n);
+    if (o == nullptr) return;
 #pragma unroll
     for (int i = 0; i < 64; i += 8) store8_bf16(o + i, &acc[i]);
+}
+
+// Warp-collective store of 32 rows x 128 bytes through a 4 KB shared-memory transpose: every store instruction then covers
+// four full 128-byte lines (8 lanes per row) instead of 32 scattered 16-byte pieces.  Local L2 merges such pieces for
+// free; an NVLink peer write does not — each piece is its own packet — and the sequence-parallel Q/K/V scatter ran at
+// ~130 GB/s that way.  `o` = this lane's row destination (nullptr = skip).  Chunk slots are XOR-swizzled by the row so
+// both the row-wise writes and the line-wise reads are bank-conflict free per quarter warp.
+__device__ __forceinline__ void store_rows_coalesced(uint32_t stage, int lane, __nv_bfloat16* o, const float (&acc)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t a = stage + uint32_t(lane) * 128u + (uint32_t(c ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pack_bf16x2(acc[c * 8], acc[c * 8 + 1])),
+                     "r"(pack_bf16x2(acc[c * 8 + 2], acc[c * 8 + 3])), "r"(pack_bf16x2(acc[c * 8 + 4], acc[c * 8 + 5])),
+                     "r"(pack_bf16x2(acc[c * 8 + 6], acc[c * 8 + 7]))
+                     : "memory");
+    }
+    __syncwarp();
+    const unsigned long long optr = reinterpret_cast<unsigned long long>(o);
+    const int c = lane & 7;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + (lane >> 3);
+        const unsigned long long po = __shfl_sync(0xffffffffu, optr, src);
+        uint4 v;
+        const uint32_t a = stage + uint32_t(src) * 128u + (uint32_t(c ^ (src & 7)) << 4);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+        if (po != 0ull) *reinterpret_cast<uint4*>(po + uint32_t(c) * 16u) = v;
+    }
+    __syncwarp();  // the staging rows are rewritten by the next head
 }
 
 template <int BLOCK_N, int EPI>
@@ -417,7 +453,8 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = 128 * BLOCK_K * 2;  // 16 KB
 constexpr int G2_B_BYTES = 128 * BLOCK_K * 2;  // 16 KB (this CTA's half of the 256 output columns)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 256 + 1024;
+constexpr int G2_XPOSE_BYTES = 4 * 32 * 128;  // EPI_QKV peer scatter: one 32-row x 128-byte transpose buffer per epilogue warp
+constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 256 + G2_XPOSE_BYTES + 1024;
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
@@ -547,7 +584,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         accv[i] = __uint_as_float(r0[i]);
                         accv[32 + i] = __uint_as_float(r1[i]);
                     }
-                    epi_qkv(p, accv, row, nt * 256 + c);
+                    if (p.sp_world > 1) {
+                        __nv_bfloat16* o = epi_qkv_compute(p, accv, row, nt * 256 + c);
+                        store_rows_coalesced(bar_base + 256u + uint32_t(ew) * 4096u, lane, o, accv);
+                    } else {
+                        epi_qkv(p, accv, row, nt * 256 + c);
+                    }
                 }
             } else {
 #pragma unroll 1

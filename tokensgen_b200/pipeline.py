@@ -322,7 +322,8 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
                  output_type: str = "pil", return_dict: bool = True, attention_kwargs=None, callback_on_step_end=None,
                  callback_on_step_end_tensor_inputs=("latents",), max_sequence_length: int = 226, decode_chunk_size=None,
                  vip_scale=1.0, sampling_mode: str = None, sampling_params: Dict[str, Any] = None, cache_idx=(),
-                 video_ipadapter_start_frame_idx: Optional[int] = 1000, cfg_parallel_group=None):
+                 video_ipadapter_start_frame_idx: Optional[int] = 1000, cfg_parallel_group=None,
+                 sequence_parallel_group=None):
         if use_separate_guidance:
             raise NotImplementedError("use_separate_guidance (3-branch CFG) is off in both shipped configs (edit.yaml:11, gen.yaml)")
         if callback_on_step_end is not None:
@@ -388,6 +389,14 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         # DiT (B = 1) and the pair all-gathers the 2.25 MB predictions over NVLink; everything else (latents, scheduler
         # noise, FIFO capture) is computed redundantly and identically on both, so no other state moves.
         cfgp = cfg_parallel_group if (do_cfg and cfg_parallel_group is not None) else None
+        # Sequence-parallel base stage (tokensgen_b200/seqpar.py): every rank of `sequence_parallel_group`
+        # calls this method with identical arguments; each DiT forward is sharded over the group (rows for LayerNorm /
+        # GEMMs, heads for attention, the two all-to-alls fused into kernel epilogues as NVLink peer stores) and returns
+        # the full, bit-identical prediction on every rank.  Latents, noise and the FIFO capture are computed redundantly.
+        if sequence_parallel_group is not None:
+            if cfgp is not None:
+                raise ValueError("choose one of cfg_parallel_group / sequence_parallel_group for the base stage")
+            self.transformer.enable_sequence_parallel(sequence_parallel_group)
         if cfgp is not None:
             import torch.distributed as dist
             branch = dist.get_rank(cfgp)
@@ -429,6 +438,8 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
             latents, old_x0 = self.scheduler.step(noise_pred, old_x0, t, prev_t, ts[i - 1] if i > 0 else None, latents,
                                                   generator=generator, return_dict=False)
             latents = latents.to(prompt_embeds.dtype)
+        if sequence_parallel_group is not None:
+            self.transformer.disable_sequence_parallel()   # the FIFO stage is window-parallel: one whole window per rank
         orig_latents = latents.clone()
 
         return FIFOCogVideoXPipelineOutput(

@@ -79,8 +79,8 @@ class SeqParallel:
     def barrier(self) -> None:
         """Cross-rank barrier enqueued on the current stream: every rank's earlier kernels (and their peer stores) are
         complete before any rank's later kernels start."""
-        E.launch_count += 1
-        self._hdl.barrier(channel=0)
+        with E._Timed("sp_barrier", 1):
+            self._hdl.barrier(channel=0)
 
     # ---- gather of the (tiny) projected output rows
     def gather_rows(self, local: torch.Tensor, chunk: int, rows: int) -> torch.Tensor:
@@ -119,7 +119,7 @@ class ShardedBuffers:
         self.qkv_scatter = E.make_qkv_scatter([peers[i] for i in iq])
         self._a_peers, self._d, self._rows, self._shards = peers[ia], d, rows, shards
         self.attn_scatter = E.make_attn_scatter(self._a_peers, self.chunk, rows, H, sp.rank * self.Hloc)
-        self.side_stream = None
+        self.side_stream = torch.cuda.Stream(device=device)
 
     def attn_scatter_for_batch(self, bi: int) -> E.AttnScatter:
         """Scatter descriptor for a B = 1 attention call on batch element `bi`."""

@@ -302,6 +302,12 @@ def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
         E.attn_fwd(qb, kb, vb, out, out_row0=0)
     else:
         qv, kv, vv = bufs.qkv[3:]
+        # K6 (480 vip queries x all keys) has only 2 * B * H/world CTAs, each walking every key block: on a side stream its
+        # CTAs share the SMs with K4 + K5 instead of holding a few of them alone (it writes other rows of the output)
+        main, side = torch.cuda.current_stream(), bufs.side_stream
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            E.attn_fwd(qv, kv, vv, out, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
         scale = proc.scale
         scales = [float(s_) for s_ in (scale if isinstance(scale, (list, tuple)) else [scale])]
         if len(scales) != B:
@@ -314,7 +320,7 @@ def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
             for bi, s_ in enumerate(scales):
                 E.attn_fwd_pair(qb[bi:bi + 1], kb[bi:bi + 1], vb[bi:bi + 1], n_tv, n_tv, qv[bi:bi + 1], kv[bi:bi + 1],
                                 vv[bi:bi + 1], n_tv, rowmap.n_vip, bufs.attn_scatter_for_batch(bi), _bf16_scalar(s_))
-        E.attn_fwd(qv, kv, vv, out, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
+        main.wait_stream(side)
     sp.barrier()
 
 

@@ -2,7 +2,7 @@
 
   --tiny : tiny DiT (4 heads, 2 layers, with the video-IP-adapter): the P-rank forward must be bit-identical to the
            single-GPU forward on every rank; prints SEQPAR_OK.
-  --full : CogVideoX-5b shapes at the bench geometry (CFG pair, 17 550 + 226 + 480 rows): bit-identity on a 2-layer slice,
+  --full : CogVideoX-5b shapes at the bench geometry (CFG pair, 17 550 + 226 + 480 rows): bit-identity of the sharded forward,
            then the latency of the full 42-layer forward, sharded vs unsharded (CUDA events, max over ranks), one JSON line.
 """
 import argparse
@@ -102,6 +102,9 @@ def main():
             for _ in range(2):
                 call()
             ms_one = timed(call, args.steps)
+            E.profile = {}
+            call(); torch.cuda.synchronize()
+            prof_one, E.profile = E.profile, None
             m.enable_sequence_parallel()
             out = call().clone()
             same = torch.equal(out, ref)
@@ -110,12 +113,18 @@ def main():
             l0 = E.launch_count
             ms_sp = timed(call, args.steps)
             launches = (E.launch_count - l0) // args.steps
+            E.profile = {}
+            call(); torch.cuda.synchronize()
+            prof_sp, E.profile = E.profile, None
+        per = lambda prof: {k: round(sum(s_.elapsed_time(e_) for s_, e_ in v), 3) for k, v in
+                            sorted(prof.items(), key=lambda kv: -sum(s_.elapsed_time(e_) for s_, e_ in kv[1]))[:10]}
         ok = ok and same
         if rank == 0:
             line = {"what": "CogVideoX-5b DiT forward, CFG pair, 18 256 rows, sequence-parallel (Ulysses, fused peer-store all-to-alls)",
                     "layers": args.layers, "ranks": world, "bit_identical_to_single_gpu": same,
                     "ms_single_gpu": ms_one, "ms_sharded": ms_sp, "speedup": ms_one / ms_sp,
-                    "parallel_efficiency": ms_one / ms_sp / world, "launches_per_forward": launches}
+                    "parallel_efficiency": ms_one / ms_sp / world, "launches_per_forward": launches,
+                    "op_ms_single_gpu": per(prof_one), "op_ms_sharded_rank0": per(prof_sp)}
             print(json.dumps(line), flush=True)
             if args.out:
                 with open(args.out, "a") as f:
