@@ -25,7 +25,8 @@ constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int GROUP_M = 16;  // m-tiles per scheduling group (L2 reuse of the weight tile)
 
-enum { EPI_BIAS_ACT = 0, EPI_GATE_RESIDUAL = 1, EPI_QKV = 2 };
+enum { EPI_BIAS_ACT = 0, EPI_GATE_RESIDUAL = 1, EPI_QKV = 2, EPI_QKV_SP = 3 };  // _SP: heads scattered to peer ranks
+__host__ __device__ constexpr bool epi_is_qkv(int e) { return e == EPI_QKV || e == EPI_QKV_SP; }
 
 struct QkvProjDev {
     __nv_bfloat16* out;
@@ -181,6 +182,7 @@ __device__ __forceinline__ void epi_gate_residual(const GemmParams& p, float (&a
 
 // One head (64 columns) of one projection for one row: bias, LayerNorm(64), RoPE in place on `acc`; returns where the
 // row's 64 bf16 values go (nullptr: the row is not stored).
+template <bool SP>
 __device__ __forceinline__ __nv_bfloat16* epi_qkv_compute(const GemmParams& p, float (&acc)[64], int row, int n) {
     add_bias<64>(acc, p.bias, n);
     const int inner = p.heads * 64;
@@ -233,7 +235,7 @@ __device__ __forceinline__ __nv_bfloat16* epi_qkv_compute(const GemmParams& p, f
         }
     }
     __nv_bfloat16* o;
-    if (p.sp_world > 1) {  // Ulysses all-to-all fused into the store: the head's owner rank receives the row over NVLink
+    if constexpr (SP) {  // Ulysses all-to-all fused into the store: the head's owner rank receives the row over NVLink
         const int dst = head / p.sp_hpr;
         o = p.sp_peer[pi][dst] + (int64_t(ri.b * p.sp_hpr + (head - dst * p.sp_hpr)) * pr.out_rows + ri.r) * 64;
     } else {
@@ -242,8 +244,9 @@ __device__ __forceinline__ __nv_bfloat16* epi_qkv_compute(const GemmParams& p, f
     return o;
 }
 
+template <bool SP>
 __device__ __forceinline__ void epi_qkv(const GemmParams& p, float (&acc)[64], int row, int n) {
-    __nv_bfloat16* o = epi_qkv_compute(p, acc, row, n);
+    __nv_bfloat16* o = epi_qkv_compute<SP>(p, acc, row, n);
     if (o == nullptr) return;
 #pragma unroll
     for (int i = 0; i < 64; i += 8) store8_bf16(o + i, &acc[i]);
@@ -390,7 +393,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), acc_phase, 0x104);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
-            if constexpr (EPI == EPI_QKV) {
+            if constexpr (epi_is_qkv(EPI)) {
 #pragma unroll 1
                 for (int c = 0; c < BLOCK_N; c += 64) {
                     uint32_t r0[32], r1[32];
@@ -403,7 +406,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
                         accv[i] = __uint_as_float(r0[i]);
                         accv[32 + i] = __uint_as_float(r1[i]);
                     }
-                    epi_qkv(p, accv, row, nt * BLOCK_N + c);
+                    epi_qkv<EPI == EPI_QKV_SP>(p, accv, row, nt * BLOCK_N + c);
                 }
             } else {
 #pragma unroll 1
@@ -454,7 +457,9 @@ constexpr int G2_A_BYTES = 128 * BLOCK_K * 2;  // 16 KB
 constexpr int G2_B_BYTES = 128 * BLOCK_K * 2;  // 16 KB (this CTA's half of the 256 output columns)
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr int G2_XPOSE_BYTES = 4 * 32 * 128;  // EPI_QKV peer scatter: one 32-row x 128-byte transpose buffer per epilogue warp
-constexpr int G2_SMEM_BYTES = G2_STAGES * G2_STAGE_BYTES + 256 + G2_XPOSE_BYTES + 1024;
+__host__ __device__ constexpr int g2_smem_bytes(int epi) {
+    return G2_STAGES * G2_STAGE_BYTES + 256 + (epi == EPI_QKV_SP ? G2_XPOSE_BYTES : 0) + 1024;
+}
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
@@ -571,7 +576,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
             mbar_wait(tfull_bar(acc), acc_phase, 0x184);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 256);
-            if constexpr (EPI == EPI_QKV) {
+            if constexpr (epi_is_qkv(EPI)) {
 #pragma unroll 1
                 for (int c = 0; c < 256; c += 64) {
                     uint32_t r0[32], r1[32];
@@ -584,11 +589,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
                         accv[i] = __uint_as_float(r0[i]);
                         accv[32 + i] = __uint_as_float(r1[i]);
                     }
-                    if (p.sp_world > 1) {
-                        __nv_bfloat16* o = epi_qkv_compute(p, accv, row, nt * 256 + c);
+                    if constexpr (EPI == EPI_QKV_SP) {
+                        __nv_bfloat16* o = epi_qkv_compute<true>(p, accv, row, nt * 256 + c);
                         store_rows_coalesced(bar_base + 256u + uint32_t(ew) * 4096u, lane, o, accv);
                     } else {
-                        epi_qkv(p, accv, row, nt * 256 + c);
+                        epi_qkv<false>(p, accv, row, nt * 256 + c);
                     }
                 }
             } else {
@@ -632,13 +637,13 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const Gemm
     auto kern = gemm2_kernel<EPI>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES);
-        if (e != cudaSuccess) return fail(int(e), "gemm2: cudaFuncSetAttribute(smem=%d): %s", G2_SMEM_BYTES, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g2_smem_bytes(EPI));
+        if (e != cudaSuccess) return fail(int(e), "gemm2: cudaFuncSetAttribute(smem=%d): %s", g2_smem_bytes(EPI), cudaGetErrorString(e));
         attr_set = true;
     }
     const int tiles = p.m_tiles * p.n_tiles;
     const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
-    kern<<<2 * clusters, 256, G2_SMEM_BYTES, stream>>>(ta, tb, p);
+    kern<<<2 * clusters, 256, g2_smem_bytes(EPI), stream>>>(ta, tb, p);
     return check_launch("gemm2");
 }
 
@@ -681,7 +686,7 @@ static int dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
         if (rc) return rc;
         return launch_gemm2<EPI>(ta, tb, p, stream);
     }
-    const int bn = (EPI == EPI_QKV) ? 256 : (p.N % 256 == 0 ? 256 : (p.N % 128 == 0 ? 128 : 64));
+    const int bn = epi_is_qkv(EPI) ? 256 : (p.N % 256 == 0 ? 256 : (p.N % 128 == 0 ? 128 : 64));
     p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
     p.n_tiles = p.N / bn;
     CUtensorMap ta, tb;
@@ -690,7 +695,7 @@ static int dispatch(const __nv_bfloat16* A, int64_t lda, const __nv_bfloat16* W,
     rc = make_tmap_2d(&tb, W, uint64_t(p.K), uint64_t(p.N), uint64_t(p.K) * 2, BLOCK_K, uint32_t(bn));
     if (rc) return rc;
     if (bn == 256) return launch_gemm<256, EPI>(ta, tb, p, stream);
-    if constexpr (EPI != EPI_QKV) {
+    if constexpr (!epi_is_qkv(EPI)) {
         if (bn == 128) return launch_gemm<128, EPI>(ta, tb, p, stream);
         return launch_gemm<64, EPI>(ta, tb, p, stream);
     }
@@ -793,7 +798,7 @@ static int qkv_rope_gemm_impl(const tg_bf16* A, int64_t lda, const tg_bf16* W, c
             (proj[i].cos_video == nullptr) != (proj[i].sin_video == nullptr) ||
             (proj[i].cos_vip == nullptr) != (proj[i].sin_vip == nullptr))
             return fail(-19, "qkv_rope_gemm: projection %d has half of a (weight,bias) or (cos,sin) pair", i);
-        p.proj[i].out = reinterpret_cast<__nv_bfloat16*>(proj[i].out);
+        p.proj[i].out = reinterpret_cast<__nv_bfloat16*>(scatter != nullptr ? scatter->peer[i][0] : proj[i].out);  // world 1
         p.proj[i].out_rows = proj[i].out_rows;
         p.proj[i].ln_w = reinterpret_cast<const __nv_bfloat16*>(proj[i].ln_w);
         p.proj[i].ln_b = reinterpret_cast<const __nv_bfloat16*>(proj[i].ln_b);
@@ -802,6 +807,9 @@ static int qkv_rope_gemm_impl(const tg_bf16* A, int64_t lda, const tg_bf16* W, c
         p.proj[i].cos_vip = proj[i].cos_vip;
         p.proj[i].sin_vip = proj[i].sin_vip;
     }
+    if (p.sp_world > 1)
+        return dispatch<EPI_QKV_SP>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
+                                    p, static_cast<cudaStream_t>(stream));
     return dispatch<EPI_QKV>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),
                              p, static_cast<cudaStream_t>(stream));
 }

@@ -37,7 +37,7 @@ class LongVGenCogVideoXPipeline(MPFIFOVideoIPAdapterCogVideoXPipeline):
                  use_dynamic_cfg: bool = False, num_videos_per_prompt: int = 1, eta: float = 0.0, generator=None, latents=None,
                  prompt_embeds=None, negative_prompt_embeds=None, return_dict: bool = True, attention_kwargs=None,
                  callback_on_step_end=None, callback_on_step_end_tensor_inputs=("latents",), max_sequence_length: int = 226,
-                 longvgen_mean=None, longvgen_std=None, longvgen_pca=None):
+                 longvgen_mean=None, longvgen_std=None, longvgen_pca=None, sequence_parallel_group=None):
         if num_frames_per_chunk > 4:
             raise ValueError("The number of frames must equal 4 for now due to static positional embeddings.")
         if callback_on_step_end is not None:
@@ -65,6 +65,8 @@ class LongVGenCogVideoXPipeline(MPFIFOVideoIPAdapterCogVideoXPipeline):
         ts = [int(t) for t in timesteps]
         old_x0 = None
         B = 2 if do_cfg else 1
+        if sequence_parallel_group is not None:   # every rank of the group calls with identical arguments (seqpar.py)
+            self.transformer.enable_sequence_parallel(sequence_parallel_group)
         for i, t in enumerate(ts):
             model_in = torch.cat([latents] * 2) if do_cfg else latents
             noise_pred = self.transformer(hidden_states=model_in, encoder_hidden_states=prompt_embeds,
@@ -81,6 +83,8 @@ class LongVGenCogVideoXPipeline(MPFIFOVideoIPAdapterCogVideoXPipeline):
             latents, old_x0 = self.scheduler.step(noise_pred, old_x0, t, prev_t, ts[i - 1] if i > 0 else None, latents,
                                                   generator=generator, return_dict=False)
             latents = latents.to(prompt_embeds.dtype)
+        if sequence_parallel_group is not None:
+            self.transformer.disable_sequence_parallel()
         # :891-904 — un-normalise the 16 PCA coordinates, zero-pad to the PCA width, inverse transform (fp32, host)
         dtype = latents.dtype
         b, f, c, h, w = latents.shape
