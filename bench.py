@@ -272,6 +272,38 @@ def run_ours(args):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
         clocks = sampler.stop() if sampler else None
+        # N > 1, extra (not part of `value`): the SAME window step with the DiT forward sequence-parallel over all N ranks
+        # (tokensgen_b200/seqpar.py: rows sharded for LayerNorm / GEMMs, heads for attention, all-to-alls fused into the
+        # epilogues as NVLink peer stores) — the strong-scaling latency of ONE clip, which is what the serial base stage
+        # of the pipeline uses.  Every rank runs rank 0's window (same weights, same inputs).
+        seqpar = None
+        if world > 1 and 48 % world == 0 and not args.no_seqpar:
+            del model
+            torch.cuda.empty_cache()
+            model = build_random_model(device=dev, seed=0)
+            sp_in = {k: v.to(dev) for k, v in window_inputs(seed=42).items()}
+            sp_prompt = sp_in["prompt_embeds"]
+
+            def step_sp():
+                lat = sp_in["latents"]
+                noise_pred = model(hidden_states=torch.cat([lat, lat]), encoder_hidden_states=sp_prompt, timestep=ts_dev,
+                                   vip_encoder_hidden_states=sp_in["image_embeddings"], image_rotary_emb=rope,
+                                   vip_image_rotary_emb=img_rope, vip_condition_rotary_emb=cond_rope, return_dict=False)[0]
+                old = [sp_in["old_x0"][j].unsqueeze(0).unsqueeze(0) for j in range(F)]
+                return sch.window_step(noise_pred, lat, old, t, prev_t, next_t, 6.0, noise=(sp_in["noise1"], sp_in["noise2"]))[0]
+
+            import tokensgen_b200.transformer as T
+            T._FUSE_PAIR = True   # same kernel sequence (K4 + K5 in one launch) on both sides of the bit-identity check
+            ref_out = step_sp().clone()
+            model.enable_sequence_parallel()
+            for _ in range(args.warmup):
+                out_sp = step_sp()
+            same = bool(torch.equal(out_sp, ref_out))
+            ms_sp = timed(step_sp, args.steps) / args.steps
+            model.disable_sequence_parallel()
+            T._FUSE_PAIR = False
+            seqpar = {"what": "one window step (DiT forward CFG pair + DPM step) sharded over all ranks: strong scaling of a single clip",
+                      "ranks": world, "ms_per_step": ms_sp, "bit_identical_to_unsharded": same}
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = measured_peaks()
@@ -306,6 +338,9 @@ def run_ours(args):
                              "algorithmic_bytes": 4 * 2 * 48 * N * 64 * 2},
                 "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
                 "clocks": clocks}
+        if seqpar is not None:
+            seqpar["speedup_vs_this_runs_1gpu_step"] = ms_step / seqpar["ms_per_step"]
+            line["sequence_parallel"] = seqpar
         if world == 1 and not args.no_cpu_baseline:
             times, cores = cpu_block_seconds(1, 1)
             line["cpu_baseline"] = {"value": cpu_tokens_per_s(times[0]), "unit": "tokens/s", "cores": cores, "kind": "port",
@@ -324,6 +359,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-seqpar", action="store_true", help="N > 1: skip the extra sequence-parallel single-clip measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
