@@ -217,11 +217,36 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         def encode_video(video):
             video = video.to(device=device, dtype=dtype).permute(0, 2, 1, 3, 4)       # b c f h w
             video = torch.cat([video] + [video[:, :, [-1]]] * nf_per_chunk, dim=2)    # pad one chunk (:580-581)
+            n = video.shape[2] // nf_per_chunk
+            grp = getattr(self, "_clip_parallel_group", None)
+            if grp is None:
+                lat = []
+                for c in range(n):
+                    dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
+                    lat.append(dist.sample(generator=generator, scale=self.vae.config.scaling_factor))   # K19: sample * scaling fused
+                return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)                   # b f c h w
+            # clip-parallel: every rank of the group was called with the same video; the chunks are independent (the conv
+            # cache is cleared per encode call), so chunk c is encoded by group rank c % P and broadcast.  The posterior
+            # noise of the other ranks' chunks is still drawn (and dropped) so the generator stream — and with it every
+            # later draw — is the one the serial loop produces: results are identical to the single-process call.
+            import torch.distributed as tdist
+            P, r = tdist.get_world_size(grp), tdist.get_rank(grp)
+            cfg = self.vae.config
+            lshape = (video.shape[0], cfg.latent_channels, (nf_per_chunk - 1) // cfg.temporal_compression_ratio + 1,
+                      video.shape[3] // self.vae_scale_factor_spatial, video.shape[4] // self.vae_scale_factor_spatial)
             lat = []
-            for c in range(video.shape[2] // nf_per_chunk):
-                dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
-                lat.append(dist.sample(generator=generator, scale=self.vae.config.scaling_factor))   # K19: sample * scaling fused
-            return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)                       # b f c h w
+            for c in range(n):
+                if c % P == r:
+                    dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
+                    lat.append(dist.sample(generator=generator, scale=cfg.scaling_factor).contiguous())
+                    if tuple(lat[-1].shape) != lshape:
+                        raise E.TokensGenError(f"clip-parallel encode: latent shape {tuple(lat[-1].shape)} != {lshape}")
+                else:
+                    E.randn_tensor(lshape, generator, device, dtype)
+                    lat.append(torch.empty(lshape, device=device, dtype=dtype))
+            for c in range(n):
+                tdist.broadcast(lat[c], src=tdist.get_global_rank(grp, c % P), group=grp)
+            return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)
 
         def condense(lat):
             b, f, c, h, w = lat.shape
@@ -370,9 +395,13 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
             img_grid, cond_grid, rs_img, rs_smp = self._vip_grids(latents, num_chunks, compressed_nf_per_chunk,
                                                                   video_ipadapter_start_frame_idx)
             vip_nf_per_chunk = self.resampler.config.num_temporal_queries
-            image_embeddings = self.vae_encode_image(frames, device, do_cfg, use_separate_guidance, nf_per_chunk,
-                                                     compressed_nf_per_chunk, num_chunks, rs_img, rs_smp,
-                                                     image_embeddings=image_embeddings, generator=generator)
+            self._clip_parallel_group = sequence_parallel_group   # conditioning chunks are encoded one per rank (vae_encode_image)
+            try:
+                image_embeddings = self.vae_encode_image(frames, device, do_cfg, use_separate_guidance, nf_per_chunk,
+                                                         compressed_nf_per_chunk, num_chunks, rs_img, rs_smp,
+                                                         image_embeddings=image_embeddings, generator=generator)
+            finally:
+                self._clip_parallel_group = None
             n_vip_frames = min(vip_nf_per_chunk + 1, compressed_nf_per_chunk)
             cond_rope = self._prepare_vip_rotary_positional_embeddings(cond_grid[0][:n_vip_frames], cond_grid[1], cond_grid[2], device)
             img_rope = self._prepare_vip_rotary_positional_embeddings(img_grid[0][:compressed_nf_per_chunk], img_grid[1], img_grid[2], device)
