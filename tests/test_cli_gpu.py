@@ -8,6 +8,7 @@ import subprocess
 import sys
 
 import pytest
+import torch
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,3 +42,44 @@ def test_cli_runs_end_to_end_on_a_tiny_checkpoint(tmp_path):
     assert _frames(src[0]) == (36, (96, 80, 3))      # 4 chunks x 9 frames of the conditioning clip
     assert _frames(orig[0]) == (9, (96, 80, 3))      # the base clip: 3 latent frames -> 9 frames
     assert _frames(fifo[0]) == (36, (96, 80, 3))     # 12 latent frames emitted by the FIFO stage -> 4 x 9 frames
+
+
+def _all_frames(path):
+    import cv2
+    import numpy as np
+    cap = cv2.VideoCapture(path)
+    out = []
+    while True:
+        ok, img = cap.read()
+        if not ok:
+            break
+        out.append(img)
+    cap.release()
+    return np.stack(out)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("mode", ["cfg_parallel", "sequence_parallel"])
+def test_cli_two_ranks_writes_the_same_videos_as_one_rank(tmp_path, mode):
+    """1 rank vs torchrun x2 — base clip CFG-parallel (one guidance branch per rank) or sequence-parallel (every DiT
+    forward sharded over both ranks, conditioning chunks encoded one per rank), FIFO stage window-parallel, decode
+    clip-parallel: identical mp4s."""
+    import numpy as np
+    roots = [str(tmp_path / "one"), str(tmp_path / "two")]
+    for r_ in roots:
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_tiny_checkpoint.py"), r_], check=True, cwd=ROOT)
+    if mode == "sequence_parallel":
+        with open(os.path.join(roots[1], "tiny_edit.yaml"), "a") as f:
+            f.write("sequence_parallel: true\n")
+    cli = os.path.join(ROOT, "infer_cogvideo_mp_fifo.py")
+    env1 = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    r = subprocess.run([sys.executable, cli, "--config", os.path.join(roots[0], "tiny_edit.yaml")], cwd=ROOT, env=env1,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29547", cli, "--config", os.path.join(roots[1], "tiny_edit.yaml")],
+                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    for kind in ("orig", "fifo"):
+        a, b = (_all_frames(glob.glob(os.path.join(r_, "outputs", "tiny_*", f"clip1_{kind}_*.mp4"))[0]) for r_ in roots)
+        assert a.shape == b.shape and np.array_equal(a, b), kind

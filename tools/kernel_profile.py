@@ -1,5 +1,5 @@
 """Small drivers for `ncu --set full` captures of the other hot kernels at their bench shapes.
-usage: kernel_profile.py gemm_ff1 | gemm_qkv | gemm_ff2 | conv | ln | norm_act"""
+usage: kernel_profile.py gemm_ff1 | gemm_qkv | gemm_qkv_sp | gemm_ff2 | conv | ln | norm_act"""
 import os
 import sys
 
@@ -58,6 +58,35 @@ elif which == "gemm_qkv":
                 p.cos_vip, p.sin_vip = cosv.data_ptr(), sinv.data_ptr()
         projs.append(p)
     rep(lambda: E.qkv_rope_gemm(a, w, bias, B, H, rm, projs, 1e-6))
+elif which == "gemm_qkv_sp":
+    # the sequence-parallel Q/K/V GEMM of one of P = 2 ranks (rows [0, 9128) of each batch) with the head scatter going to
+    # two buffers on THIS device (the kernel only sees addresses): shows what the shared-memory transposed, full-line
+    # epilogue stores cost the tensor pipe
+    from tokensgen_b200.seqpar import shard_rows
+    P = 2
+    chunk, shards = shard_rows(rows, P)
+    row0, rl = shards[0]
+    rms = E.make_rowmap(n_text, n_video, n_vip, hw, F, row0, rl)
+    a = torch.randn(B * rl, d, device=dev).bfloat16()
+    w = (torch.randn(6 * d, d, device=dev) / d ** 0.5).bfloat16()
+    bias = torch.randn(6 * d, device=dev).bfloat16()
+    n_tv = n_text + n_video
+    bufs = [[torch.empty(B, H // P, n_tv if i < 3 else rows, 64, device=dev, dtype=torch.bfloat16) for i in range(6)] for _ in range(P)]
+    lnw, lnb = torch.ones(64, device=dev).bfloat16(), torch.zeros(64, device=dev).bfloat16()
+    cos, sin = torch.rand(n_video, 64, device=dev), torch.rand(n_video, 64, device=dev)
+    cosv, sinv = torch.rand(n_vip, 64, device=dev), torch.rand(n_vip, 64, device=dev)
+    projs = []
+    for i in range(6):
+        p = E.QkvProj()
+        p.out_rows = n_tv if i < 3 else rows
+        if i in (0, 1, 3, 4):
+            p.ln_w, p.ln_b = lnw.data_ptr(), lnb.data_ptr()
+            p.cos_video, p.sin_video = cos.data_ptr(), sin.data_ptr()
+            if i >= 3:
+                p.cos_vip, p.sin_vip = cosv.data_ptr(), sinv.data_ptr()
+        projs.append(p)
+    scat = E.make_qkv_scatter([[bufs[q][i].data_ptr() for q in range(P)] for i in range(6)])
+    rep(lambda: E.qkv_rope_gemm(a, w, bias, B, H, rms, projs, 1e-6, scatter=scat))
 elif which == "ln":
     x = torch.randn(M, d, device=dev).bfloat16()
     y = torch.empty_like(x)
