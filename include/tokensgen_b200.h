@@ -321,6 +321,13 @@ int tg_vae_posterior_sample(const tg_bf16* moments, const tg_bf16* eps, tg_bf16*
  * rounding like the reference.  a: [planes, Ha, Wa], b: [planes, Hb, Wb]; extent is clamped to the tile sizes. */
 int tg_vae_blend(const tg_bf16* a, tg_bf16* b, int64_t planes, int Ha, int Wa, int Hb, int Wb, int extent, int axis, void* stream);
 
+/* K20: decoded video planes [3, F, H, W] bf16 in [-1, 1] -> packed frames [F, H, W, 3] uint8,
+ * u = rint(clamp(x/2 + 0.5, 0, 1) * 255) in fp32 (round-half-even).  Replaces VideoProcessor.postprocess_video
+ * (longvgen/pipeline/pipeline_cogvideox_mp_fifo.py:363: denormalise, permute, float32 numpy frames) plus the exporter's
+ * float -> uint8 conversion on the host: 4x fewer bytes cross PCIe and no host float math.
+ * pixels = F*H*W; plane_stride = elements between channel planes. */
+int tg_vae_frames_to_rgb8(const tg_bf16* x, uint8_t* y, int64_t pixels, int64_t plane_stride, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

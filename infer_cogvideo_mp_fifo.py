@@ -117,7 +117,7 @@ def main(args):
             vip_scale=vip_params.scale if args.use_vip else 1.0, sampling_mode=args.get("sampling_mode"),
             sampling_params=args.get("sampling_params"), cache_idx=args.get("cache_idx"),
             video_ipadapter_start_frame_idx=vip_params.video_ipadapter_start_frame_idx if args.use_vip else 1000,
-            return_dict=False, output_type="np")
+            return_dict=False, output_type="uint8")   # reference: "np" float frames; here packed to uint8 on the GPU (same mp4 bytes)
         # two extensions of the yaml schema (absent from the shipped configs): a non-default resolution, and precomputed
         # prompt embeddings for checkpoints without the T5 encoder
         if args.get("height") is not None:

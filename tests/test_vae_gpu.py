@@ -242,3 +242,21 @@ def test_tiled_decode_and_encode_vs_oracle(env):
     print(f"tiled decode rel_l2 {rel_l2(d, ref):.3e}  tiled encode rel_l2 {rel_l2(m, refm):.3e}")
     assert d.shape == ref.shape == (1, 3, 49, 96, 80) and m.shape == refm.shape
     assert rel_l2(d, ref) < 3e-2 and rel_l2(m, refm) < 3e-2
+
+
+def test_frames_to_rgb8_matches_host_postprocess_bit_exact():
+    """K20: GPU uint8 pack == VideoProcessor.postprocess_video("np") followed by the exporter's
+    (frame * 255).round().astype(uint8), including out-of-range and half-way values."""
+    import numpy as np
+    from tokensgen_b200 import _ext as E
+    from tokensgen_b200.pipeline import VideoProcessor
+    g = torch.Generator().manual_seed(3)
+    video = (torch.randn(1, 3, 5, 24, 40, generator=g) * 0.8).bfloat16()
+    video[0, 0, 0, 0, :8] = torch.tensor([-1.5, -1.0, 1.0, 1.5, 0.0, 1 / 255, -1 / 255, 0.00390625]).bfloat16()
+    vp = VideoProcessor()
+    ref = (vp.postprocess_video(video.cuda(), "np") * 255).round().astype(np.uint8)        # [B, F, H, W, 3]
+    got = vp.postprocess_video(video.cuda(), "uint8")
+    assert got.dtype == np.uint8 and got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    planes = E.vae_frames_to_rgb8(video[0].cuda())
+    assert np.array_equal(planes.cpu().numpy(), ref[0])

@@ -106,6 +106,7 @@ SYMBOLS = {
     "tg_vae_avgpool_time": (C.c_int, [_VP, _VP, _I, _I64, _VP]),
     "tg_vae_to_channels_last": (C.c_int, [_VP, _VP, _I, _I, _I64, _I64, _VP]),
     "tg_vae_posterior_sample": (C.c_int, [_VP, _VP, _VP, _I64, _F, _VP]),
+    "tg_vae_frames_to_rgb8": (C.c_int, [_VP, _VP, _I64, _I64, _VP]),
     "tg_vae_blend": (C.c_int, [_VP, _VP, _I64, _I, _I, _I, _I, _I, _I, _VP]),
 }
 
@@ -544,3 +545,16 @@ def vae_blend(a: torch.Tensor, b: torch.Tensor, extent: int, axis: int) -> None:
     with _Timed("vae_blend", 1):
         _check(lib.tg_vae_blend(_bf16_cuda(a, "a").data_ptr(), _bf16_cuda(b, "b").data_ptr(), planes, Ha, Wa, Hb, Wb, extent, axis,
                                 _stream()), "tg_vae_blend")
+
+
+def vae_frames_to_rgb8(video: torch.Tensor) -> torch.Tensor:
+    """video [3, F, H, W] bf16 in [-1, 1] (contiguous planes) -> [F, H, W, 3] uint8 (tg_vae_frames_to_rgb8)."""
+    lib = load()
+    if video.dim() != 4 or video.shape[0] != 3 or not (video.is_cuda and video.dtype == torch.bfloat16 and video[0].is_contiguous()):
+        raise TokensGenError("vae_frames_to_rgb8: expected CUDA bf16 [3, F, H, W] with contiguous planes")
+    _, F, H, W = video.shape
+    out = torch.empty(F, H, W, 3, device=video.device, dtype=torch.uint8)
+    with _Timed("vae_frames_to_rgb8", 1):
+        _check(lib.tg_vae_frames_to_rgb8(video.data_ptr(), out.data_ptr(), F * H * W, video.stride(0), _stream()),
+               "tg_vae_frames_to_rgb8")
+    return out

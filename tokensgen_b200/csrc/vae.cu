@@ -236,6 +236,21 @@ posterior_sample_kernel(const __nv_bfloat16* __restrict__ moments, const __nv_bf
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K20
+// Decoded video planes [C = 3, F, H, W] bf16 in [-1, 1] -> packed frames [F, H, W, 3] uint8:
+//   u = rint(clamp(x / 2 + 0.5, 0, 1) * 255)   (fp32, round-half-even: exactly VideoProcessor.postprocess_video's float
+// frames followed by the exporter's `(frame * 255).round().astype(uint8)`), one thread per pixel, 3 coalesced plane reads.
+__global__ void __launch_bounds__(256)
+frames_to_rgb8_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ y, int64_t pixels, int64_t plane_stride) {
+    for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < pixels; i += int64_t(gridDim.x) * blockDim.x) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = fminf(fmaxf(__bfloat162float(x[c * plane_stride + i]) * 0.5f + 0.5f, 0.0f), 1.0f);
+            y[i * 3 + c] = uint8_t(rintf(v * 255.0f));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K18
 // b[.., k, ..] = a[.., -extent + k, ..] * (1 - k/extent) + b[.., k, ..] * (k/extent) along H (axis 0) or W (axis 1),
 // in place on b, every op rounded to bf16 like the reference's bf16 tensor expression (autoencoder_kl_cogvideox.py:1190-1204).
@@ -335,6 +350,14 @@ extern "C" int tg_vae_posterior_sample(const tg_bf16* moments, const tg_bf16* ep
         reinterpret_cast<const __nv_bfloat16*>(moments), reinterpret_cast<const __nv_bfloat16*>(eps),
         reinterpret_cast<__nv_bfloat16*>(z), n, scale);
     return check_launch("vae_posterior_sample");
+}
+
+extern "C" int tg_vae_frames_to_rgb8(const tg_bf16* x, uint8_t* y, int64_t pixels, int64_t plane_stride, void* stream) {
+    if (!x || !y) return fail(-1, "vae_frames_to_rgb8: null pointer");
+    if (pixels <= 0 || plane_stride < pixels) return fail(-2, "vae_frames_to_rgb8: pixels=%lld plane_stride=%lld", (long long)pixels, (long long)plane_stride);
+    frames_to_rgb8_kernel<<<grid_for(pixels), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), y, pixels, plane_stride);
+    return check_launch("vae_frames_to_rgb8");
 }
 
 extern "C" int tg_vae_blend(const tg_bf16* a, tg_bf16* b, int64_t planes, int Ha, int Wa, int Hb, int Wb, int extent, int axis, void* stream) {

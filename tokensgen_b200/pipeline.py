@@ -78,6 +78,10 @@ class VideoProcessor:
     def postprocess_video(self, video: torch.Tensor, output_type: str = "np"):
         if output_type == "latent":
             return video
+        if output_type == "uint8":
+            # schema extension: [B, F, H, W, 3] uint8 numpy frames packed on the GPU — bit-identical to
+            # `(postprocess_video(..., "np") * 255).round().astype(uint8)` (what export_to_video does with "np" frames)
+            return np.stack([E.vae_frames_to_rgb8(v.to(torch.bfloat16)).cpu().numpy() for v in video])
         v = (video.float() / 2 + 0.5).clamp(0, 1)          # [B, C, F, H, W]
         if output_type == "pt":
             return v.permute(0, 2, 1, 3, 4)
