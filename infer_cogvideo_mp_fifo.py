@@ -80,7 +80,7 @@ def main(args):
     # `sequence_parallel: true` (schema extension; default with more than two ranks whose count divides the head count):
     # instead, EVERY rank runs the base clip with each DiT forward sharded over all ranks (tokensgen_b200/seqpar.py).
     heads = pipe.transformer.config.num_attention_heads
-    seq_par = world > 1 and bool(args.get("sequence_parallel", world > 2)) and heads % world == 0 and not args.use_2nd_stage
+    seq_par = world > 1 and bool(args.get("sequence_parallel", world > 2)) and heads % world == 0
     cfg_group = dist.new_group([0, 1]) if world > 1 and args.get("cfg_parallel", True) and not seq_par else None
     pipe_list = [pipe]
     vip_params = args.video_ipadapter_params if args.use_vip else None
@@ -132,20 +132,28 @@ def main(args):
                 print(f"Processing {name}: [{prompt}]")
             if args.use_vip:
                 if args.use_2nd_stage:
-                    rp = vip_params.resampler_params
-                    image_embeddings = pipe_2nd(
-                        prompt=prompt, height=rp.num_height_queries, width=rp.num_width_queries,
-                        num_frames_per_chunk=rp.num_temporal_queries, num_chunks=dps.max_num_chunks, use_dynamic_cfg=True,
-                        guidance_scale=args.get("guidance_scale_2nd", args.guidance_scale),
-                        generator=torch.Generator().manual_seed(args.seed_2nd), longvgen_mean=args.longvgen_mean,
-                        longvgen_std=args.longvgen_std, longvgen_pca=args.longvgen_pca).frames
+                    # T2To stage on rank 0 (the tokens transformer is loaded there only); with a sequence-parallel base
+                    # clip its condensed tokens are then shipped to every rank (one 56 MB broadcast for gen.yaml)
+                    if rank == 0:
+                        rp = vip_params.resampler_params
+                        pe2 = {k: call[k] for k in ("prompt_embeds", "negative_prompt_embeds") if k in call}
+                        image_embeddings = pipe_2nd(
+                            prompt=None if pe2 else prompt, height=rp.num_height_queries, width=rp.num_width_queries,
+                            num_frames_per_chunk=rp.num_temporal_queries, num_chunks=dps.max_num_chunks, use_dynamic_cfg=True,
+                            guidance_scale=args.get("guidance_scale_2nd", args.guidance_scale),
+                            generator=torch.Generator().manual_seed(args.seed_2nd), longvgen_mean=args.longvgen_mean,
+                            longvgen_std=args.longvgen_std, longvgen_pca=args.longvgen_pca, **pe2).frames
+                    if seq_par:
+                        box = [image_embeddings.cpu() if rank == 0 else None]
+                        dist.broadcast_object_list(box, src=0, device=device)
+                        image_embeddings = box[0].to(device)
                 else:
                     assert item.get("video") is not None
                     video = load_video(item["video"], dps.output_res, args.num_frames_per_chunk, dps.pad_to_fit, dps.sample_fps,
                                        dps.start_t, dps.end_t, dps.max_num_chunks, dps.crop_to_fit)
             base_outputs = pipe(frames=video, image_embeddings=image_embeddings,
                                 generator=torch.Generator().manual_seed(args.seed),
-                                cfg_parallel_group=cfg_group if not args.use_2nd_stage else None,
+                                cfg_parallel_group=cfg_group if not args.use_2nd_stage else None,   # rank 1 has no T2To tokens
                                 sequence_parallel_group=dist.group.WORLD if seq_par else None, **call)
             base_outputs.condition_frames = None      # not needed by the FIFO stage; keeps the broadcast small
         else:

@@ -58,8 +58,27 @@ def _all_frames(path):
     return np.stack(out)
 
 
+def test_cli_gen_flow_t2to_then_to2v(tmp_path):
+    """config/infer/gen.yaml's flow (use_2nd_stage): T2To tokens transformer -> PCA un-projection -> condensed tokens ->
+    To2V base clip -> FIFO -> decode, on the tiny checkpoint tree."""
+    root = str(tmp_path / "ck")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_tiny_checkpoint.py"), root], check=True, cwd=ROOT)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "infer_cogvideo_mp_fifo.py"), "--config", os.path.join(root, "tiny_gen.yaml")],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    outs = glob.glob(os.path.join(root, "outputs", "tinygen_*"))
+    assert len(outs) == 1
+    emb, orig, fifo = (glob.glob(os.path.join(outs[0], f"clip1_{k}_moving gradients.*")) for k in ("embeds", "orig", "fifo"))
+    assert emb and orig and fifo and not glob.glob(os.path.join(outs[0], "clip1_source_*"))
+    e = torch.load(emb[0], weights_only=True)
+    assert tuple(e.shape) == (8, 256, 2, 3) and torch.isfinite(e.float()).all()   # 4 chunks x 2 temporal queries, 2 x 3 grid
+    assert _frames(orig[0]) == (9, (96, 80, 3))
+    assert _frames(fifo[0]) == (36, (96, 80, 3))
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("mode", ["cfg_parallel", "sequence_parallel"])
+@pytest.mark.parametrize("mode", ["cfg_parallel", "sequence_parallel", "gen_sequence_parallel"])
 def test_cli_two_ranks_writes_the_same_videos_as_one_rank(tmp_path, mode):
     """1 rank vs torchrun x2 — base clip CFG-parallel (one guidance branch per rank) or sequence-parallel (every DiT
     forward sharded over both ranks, conditioning chunks encoded one per rank), FIFO stage window-parallel, decode
@@ -68,18 +87,19 @@ def test_cli_two_ranks_writes_the_same_videos_as_one_rank(tmp_path, mode):
     roots = [str(tmp_path / "one"), str(tmp_path / "two")]
     for r_ in roots:
         subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_tiny_checkpoint.py"), r_], check=True, cwd=ROOT)
-    if mode == "sequence_parallel":
-        with open(os.path.join(roots[1], "tiny_edit.yaml"), "a") as f:
+    yaml_name = "tiny_gen.yaml" if mode.startswith("gen") else "tiny_edit.yaml"
+    if mode.endswith("sequence_parallel"):
+        with open(os.path.join(roots[1], yaml_name), "a") as f:
             f.write("sequence_parallel: true\n")
     cli = os.path.join(ROOT, "infer_cogvideo_mp_fifo.py")
     env1 = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
-    r = subprocess.run([sys.executable, cli, "--config", os.path.join(roots[0], "tiny_edit.yaml")], cwd=ROOT, env=env1,
+    r = subprocess.run([sys.executable, cli, "--config", os.path.join(roots[0], yaml_name)], cwd=ROOT, env=env1,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29547", cli, "--config", os.path.join(roots[1], "tiny_edit.yaml")],
+                        "127.0.0.1", "--master-port", "29547", cli, "--config", os.path.join(roots[1], yaml_name)],
                        cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     for kind in ("orig", "fifo"):
-        a, b = (_all_frames(glob.glob(os.path.join(r_, "outputs", "tiny_*", f"clip1_{kind}_*.mp4"))[0]) for r_ in roots)
+        a, b = (_all_frames(glob.glob(os.path.join(r_, "outputs", "tiny*", f"clip1_{kind}_*.mp4"))[0]) for r_ in roots)
         assert a.shape == b.shape and np.array_equal(a, b), kind

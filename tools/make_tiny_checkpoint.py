@@ -78,6 +78,28 @@ def main(root):
                                  clip1=dict(prompt="moving gradients", video=os.path.join(root, "clip.mp4"), params=dict(max_num_chunks=4))))
     with open(os.path.join(root, "tiny_edit.yaml"), "w") as f:
         yaml.safe_dump(cfg, f, sort_keys=False)
+
+    # ---- the T2To + To2V flow of config/infer/gen.yaml (use_2nd_stage): a patch-1 tokens transformer that generates the
+    # 16 leading PCA coordinates of the condensed tokens, the normalisation statistics and the pickled PCA object
+    from pca import PCA
+    t2to_dir = os.path.join(root, "T2To")
+    t2to_cfg = dict(dit_cfg, patch_size=1)
+    t2to = CogVideoXTransformer3DModel(**t2to_cfg)
+    for p in t2to.parameters():
+        torch.nn.init.normal_(p, std=0.02)
+    save_model(t2to, t2to_cfg, os.path.join(t2to_dir, "transformer"), "CogVideoXTransformer3DModel")
+    g2 = torch.Generator().manual_seed(2)
+    torch.save(PCA(None).fit(torch.randn(512, rp["output_dim"], generator=g2)), os.path.join(vip_dir, "pca.pt"))
+    torch.save(torch.randn(1, 16, generator=g2) * 0.1, os.path.join(vip_dir, "mean.pt"))
+    torch.save(torch.rand(1, 16, generator=g2) + 0.5, os.path.join(vip_dir, "std.pt"))
+    gen = dict(cfg, name_prefix="tinygen", use_2nd_stage=True, pretrained_2nd_stage_model_name_or_path=t2to_dir,
+               longvgen_mean=os.path.join(vip_dir, "mean.pt"), longvgen_std=os.path.join(vip_dir, "std.pt"),
+               longvgen_pca=os.path.join(vip_dir, "pca.pt"), guidance_scale_2nd=6.0)
+    gen["video_ipadapter_params"] = dict(vip_params, scale=[1.0])
+    gen["input_config"] = dict(public=cfg["input_config"]["public"],
+                               clip1=dict(prompt="moving gradients", params=dict(max_num_chunks=4)))
+    with open(os.path.join(root, "tiny_gen.yaml"), "w") as f:
+        yaml.safe_dump(gen, f, sort_keys=False)
     print("wrote", root)
 
 
