@@ -74,3 +74,77 @@ def test_sp_entry_points_validate_before_launching():
     assert rc < 0 and b"scatter is null" in lib.tg_last_error()
     rc = lib.tg_attn_fwd_sp(0x100, 12, 0, 12, 0x100, 0x100, 12, 0, 12, None, 0, 1, 2, 0.125, 0, 1.0, None)
     assert rc < 0 and b"scatter is null" in lib.tg_last_error()
+
+
+# ------------------------------------------------------------------------------------------------ clip-parallel encodes (gloo)
+class _StubDist:
+    def __init__(self, mean):
+        self.mean = mean
+
+    def sample(self, generator=None, scale=1.0):
+        from tokensgen_b200 import _ext as E
+        eps = E.randn_tensor(self.mean.shape, generator, self.mean.device, self.mean.dtype)
+        return (self.mean + eps) * scale
+
+
+class _StubVae:
+    """encode(): a deterministic 'latent mean' of the right shape (4x temporal, 8x spatial pooling of the clip)."""
+    from types import SimpleNamespace
+    config = SimpleNamespace(latent_channels=16, temporal_compression_ratio=4, scaling_factor=0.7)
+
+    def encode(self, x):
+        import torch
+        from types import SimpleNamespace
+        b, c, f, h, w = x.shape
+        t = (f - 1) // 4 + 1
+        m = torch.nn.functional.adaptive_avg_pool3d(x.float(), (t, h // 8, w // 8)).mean(1, keepdim=True).repeat(1, 16, 1, 1, 1)
+        return SimpleNamespace(latent_dist=_StubDist(m.to(x.dtype)))
+
+
+def _stub_pipe():
+    from tokensgen_b200.pipeline import MPFIFOVideoIPAdapterCogVideoXPipeline as Pipe
+    pipe = Pipe.__new__(Pipe)
+    pipe.vae, pipe.vae_scale_factor_spatial = _StubVae(), 8
+    return pipe
+
+
+def _video():
+    import torch
+    g = torch.Generator().manual_seed(11)
+    return torch.rand(1, 45, 3, 16, 24, generator=g) * 2 - 1      # 5 chunks of 9 frames (+ 1 padded chunk)
+
+
+def _encode_worker(rank, world, port, out_path):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pipe = _stub_pipe()
+        pipe._clip_parallel_group = dist.group.WORLD
+        gen = torch.Generator().manual_seed(5)
+        lat = pipe._encode_video_chunks(_video(), 9, "cpu", torch.bfloat16, gen)
+        after = torch.randn(4, generator=gen)       # the generator stream continues exactly as in the serial loop
+        torch.save((lat, after), f"{out_path}.{rank}")
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_clip_parallel_encode_equals_serial_loop(tmp_path, world):
+    import os
+    import torch
+    import torch.multiprocessing as mp
+    pipe = _stub_pipe()
+    gen = torch.Generator().manual_seed(5)
+    ref = pipe._encode_video_chunks(_video(), 9, "cpu", torch.bfloat16, gen)
+    ref_after = torch.randn(4, generator=gen)
+    assert tuple(ref.shape) == (1, 6 * 3, 16, 2, 3)
+    out = str(tmp_path / "lat.pt")
+    port = 29500 + (os.getpid() % 2000) + 10 + world
+    mp.spawn(_encode_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        lat, after = torch.load(f"{out}.{r}")
+        assert torch.equal(lat, ref) and torch.equal(after, ref_after), f"rank {r}"

@@ -212,6 +212,41 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         return prompt_embeds.to(device), (None if negative_prompt_embeds is None else negative_prompt_embeds.to(device))
 
     # ------------------------------------------------------------------ conditioning video -> condensed tokens (:562-648)
+    def _encode_video_chunks(self, video, nf_per_chunk, device, dtype, generator):
+        """pipeline_cogvideox_mp_fifo.py:576-588: pad one chunk, VAE-encode chunk by chunk, sample the posterior, scale."""
+        video = video.to(device=device, dtype=dtype).permute(0, 2, 1, 3, 4)       # b c f h w
+        video = torch.cat([video] + [video[:, :, [-1]]] * nf_per_chunk, dim=2)    # pad one chunk (:580-581)
+        n = video.shape[2] // nf_per_chunk
+        grp = getattr(self, "_clip_parallel_group", None)
+        if grp is None:
+            lat = []
+            for c in range(n):
+                dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
+                lat.append(dist.sample(generator=generator, scale=self.vae.config.scaling_factor))   # K19: sample * scaling fused
+            return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)                   # b f c h w
+        # clip-parallel: every rank of the group was called with the same video; the chunks are independent (the conv
+        # cache is cleared per encode call), so chunk c is encoded by group rank c % P and broadcast.  The posterior
+        # noise of the other ranks' chunks is still drawn (and dropped) so the generator stream — and with it every
+        # later draw — is the one the serial loop produces: results are identical to the single-process call.
+        import torch.distributed as tdist
+        P, r = tdist.get_world_size(grp), tdist.get_rank(grp)
+        cfg = self.vae.config
+        lshape = (video.shape[0], cfg.latent_channels, (nf_per_chunk - 1) // cfg.temporal_compression_ratio + 1,
+                  video.shape[3] // self.vae_scale_factor_spatial, video.shape[4] // self.vae_scale_factor_spatial)
+        lat = []
+        for c in range(n):
+            if c % P == r:
+                dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
+                lat.append(dist.sample(generator=generator, scale=cfg.scaling_factor).contiguous())
+                if tuple(lat[-1].shape) != lshape:
+                    raise E.TokensGenError(f"clip-parallel encode: latent shape {tuple(lat[-1].shape)} != {lshape}")
+            else:
+                E.randn_tensor(lshape, generator, device, dtype)
+                lat.append(torch.empty(lshape, device=device, dtype=dtype))
+        for c in range(n):
+            tdist.broadcast(lat[c], src=tdist.get_global_rank(grp, c % P), group=grp)
+        return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)
+
     def vae_encode_image(self, frames, device, do_classifier_free_guidance, use_separate_guidance, nf_per_chunk,
                          compressed_nf_per_chunk, num_chunks, resampler_image_rotary_emb, resampler_sampling_rotary_emb,
                          image_embeddings=None, generator=None):
@@ -219,38 +254,7 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         pe = self.transformer.patch_embed
 
         def encode_video(video):
-            video = video.to(device=device, dtype=dtype).permute(0, 2, 1, 3, 4)       # b c f h w
-            video = torch.cat([video] + [video[:, :, [-1]]] * nf_per_chunk, dim=2)    # pad one chunk (:580-581)
-            n = video.shape[2] // nf_per_chunk
-            grp = getattr(self, "_clip_parallel_group", None)
-            if grp is None:
-                lat = []
-                for c in range(n):
-                    dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
-                    lat.append(dist.sample(generator=generator, scale=self.vae.config.scaling_factor))   # K19: sample * scaling fused
-                return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)                   # b f c h w
-            # clip-parallel: every rank of the group was called with the same video; the chunks are independent (the conv
-            # cache is cleared per encode call), so chunk c is encoded by group rank c % P and broadcast.  The posterior
-            # noise of the other ranks' chunks is still drawn (and dropped) so the generator stream — and with it every
-            # later draw — is the one the serial loop produces: results are identical to the single-process call.
-            import torch.distributed as tdist
-            P, r = tdist.get_world_size(grp), tdist.get_rank(grp)
-            cfg = self.vae.config
-            lshape = (video.shape[0], cfg.latent_channels, (nf_per_chunk - 1) // cfg.temporal_compression_ratio + 1,
-                      video.shape[3] // self.vae_scale_factor_spatial, video.shape[4] // self.vae_scale_factor_spatial)
-            lat = []
-            for c in range(n):
-                if c % P == r:
-                    dist = self.vae.encode(video[:, :, c * nf_per_chunk:(c + 1) * nf_per_chunk].contiguous()).latent_dist
-                    lat.append(dist.sample(generator=generator, scale=cfg.scaling_factor).contiguous())
-                    if tuple(lat[-1].shape) != lshape:
-                        raise E.TokensGenError(f"clip-parallel encode: latent shape {tuple(lat[-1].shape)} != {lshape}")
-                else:
-                    E.randn_tensor(lshape, generator, device, dtype)
-                    lat.append(torch.empty(lshape, device=device, dtype=dtype))
-            for c in range(n):
-                tdist.broadcast(lat[c], src=tdist.get_global_rank(grp, c % P), group=grp)
-            return torch.cat(lat, dim=2).permute(0, 2, 1, 3, 4)
+            return self._encode_video_chunks(video, nf_per_chunk, device, dtype, generator)
 
         def condense(lat):
             b, f, c, h, w = lat.shape
