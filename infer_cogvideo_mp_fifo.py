@@ -8,8 +8,10 @@ tokensgen_b200 mirrors.  Same flag (`--config <yaml>`), same yaml schema (config
 
 Process model: the reference builds one pipeline per visible GPU inside one process and spawns a worker per GPU for every
 video; here every GPU runs this script as a persistent rank (torchrun), loads its own copy of the weights in parallel,
-rank 0 runs the serial stages (T2To, conditioning, the 52-step base clip) and broadcasts the FIFO priming state, and all
-ranks run the FIFO stage with NCCL boundary-frame exchange, then decode clip-parallel.
+the stages the reference runs serially on one GPU (T2To, conditioning encodes, the 52-step base clip) run on rank 0 — or,
+with more than two ranks / `sequence_parallel: true`, on ALL ranks with every DiT forward sharded over them
+(tokensgen_b200/seqpar.py) and the conditioning chunks encoded one per rank — then all ranks run the FIFO stage with NCCL
+boundary-frame exchange and decode clip-parallel.
 """
 from __future__ import annotations
 
@@ -86,7 +88,7 @@ def main(args):
     vip_params = args.video_ipadapter_params if args.use_vip else None
 
     pipe_2nd = None
-    if args.use_2nd_stage and rank == 0:
+    if args.use_2nd_stage and (rank == 0 or seq_par):   # sequence-parallel: every rank holds the tokens transformer too
         tokens_transformer = CogVideoXTransformer3DModel.from_pretrained(args.pretrained_2nd_stage_model_name_or_path,
                                                                          subfolder="transformer", torch_dtype=dtype)
         pipe_2nd = LongVGenCogVideoXPipeline.from_pretrained(args.pretrained_model_name_or_path, transformer=tokens_transformer,
@@ -94,6 +96,7 @@ def main(args):
                                                              tokenizer=pipe.tokenizer)
         pipe_2nd.scheduler = CogVideoXDPMScheduler.from_config(pipe_2nd.scheduler.config, timestep_spacing="trailing")
         pipe_2nd.to(device)
+    t2to_par = seq_par and pipe_2nd is not None and tokens_transformer.config.num_attention_heads % world == 0
 
     inputs = args.input_config
     public_dps = inputs.pop("public")
@@ -132,9 +135,9 @@ def main(args):
                 print(f"Processing {name}: [{prompt}]")
             if args.use_vip:
                 if args.use_2nd_stage:
-                    # T2To stage on rank 0 (the tokens transformer is loaded there only); with a sequence-parallel base
-                    # clip its condensed tokens are then shipped to every rank (one 56 MB broadcast for gen.yaml)
-                    if rank == 0:
+                    # T2To stage: serial on rank 0 in the reference; sequence-parallel over all ranks here when the base
+                    # clip is (every rank calls with the same seed and gets the same condensed tokens — nothing to ship)
+                    if rank == 0 or t2to_par:
                         rp = vip_params.resampler_params
                         pe2 = {k: call[k] for k in ("prompt_embeds", "negative_prompt_embeds") if k in call}
                         image_embeddings = pipe_2nd(
@@ -142,8 +145,9 @@ def main(args):
                             num_frames_per_chunk=rp.num_temporal_queries, num_chunks=dps.max_num_chunks, use_dynamic_cfg=True,
                             guidance_scale=args.get("guidance_scale_2nd", args.guidance_scale),
                             generator=torch.Generator().manual_seed(args.seed_2nd), longvgen_mean=args.longvgen_mean,
-                            longvgen_std=args.longvgen_std, longvgen_pca=args.longvgen_pca, **pe2).frames
-                    if seq_par:
+                            longvgen_std=args.longvgen_std, longvgen_pca=args.longvgen_pca,
+                            sequence_parallel_group=dist.group.WORLD if t2to_par else None, **pe2).frames
+                    if seq_par and not t2to_par:   # head count of the tokens transformer does not divide: ship rank 0's tokens
                         box = [image_embeddings.cpu() if rank == 0 else None]
                         dist.broadcast_object_list(box, src=0, device=device)
                         image_embeddings = box[0].to(device)
