@@ -173,7 +173,6 @@ def test_forward_virtual_ranks_bit_identical(golden_dir, world, use_vip):
                      image_rotary_emb=g["rope"], vip_image_rotary_emb=g["img_rope"] if use_vip else None,
                      vip_condition_rotary_emb=g["cond_rope"] if use_vip else None, return_dict=False)[0]
 
-    os.environ["TG_FUSE_PAIR"] = "1"
     import tokensgen_b200.transformer as T
     old = T._FUSE_PAIR
     T._FUSE_PAIR = True  # the sharded path always fuses K4 + K5; compare against the same kernel sequence
