@@ -163,7 +163,12 @@ def main(args):
         else:
             pipe.preprare_for_fifo(**call)
         base_outputs = broadcast_base_output(base_outputs, src=0, device=device)
-        orig_video_frames, video_frames, _ = cogvideo_fifo_mp_v2(pipe_list, base_outputs, seed=args.seed)
+        # `fifo_checkpoint_dir` / `fifo_checkpoint_every` (schema extension): the FIFO stage saves its queue every N iterations
+        # and a restarted job resumes from the newest state (the deterministic base stage is simply recomputed)
+        ck = args.get("fifo_checkpoint_dir")
+        orig_video_frames, video_frames, _ = cogvideo_fifo_mp_v2(
+            pipe_list, base_outputs, seed=args.seed, checkpoint_dir=os.path.join(ck, name) if ck else None,
+            checkpoint_every=args.get("fifo_checkpoint_every", 10))
         if rank == 0:
             tag = prompt[:20]
             if video is not None:

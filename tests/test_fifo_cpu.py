@@ -125,3 +125,67 @@ def test_transfers_are_neighbour_sized_at_world_8():
         assert all(abs(src - dst) == 1 for src, _ in items)
     # 7 ranks take the 5-6 frames of their left neighbour's write region they will read, 7 ranks take 1 frame from the right
     assert sum(n for items in per_dst.values() for _, n in items) == 46
+
+
+# ------------------------------------------------------------------------------------------------ checkpoint / resume
+class _Crash(Exception):
+    pass
+
+
+def _crash_at(k):
+    def progress(it):
+        if it == k:
+            raise _Crash()
+    return progress
+
+
+def test_fifo_stage_resumes_bit_identically_after_a_crash(tmp_path):
+    from tokensgen_b200.fifo import FifoCheckpoint
+    num_frames = 26
+    sched = FifoSchedule(num_frames, _timesteps())
+    ref = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3)
+    ck = FifoCheckpoint(str(tmp_path), every=7)
+    with pytest.raises(_Crash):
+        run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, checkpoint=ck, progress=_crash_at(30))
+    assert ck.available() == [21, 28]                    # the last two generations are kept
+    resumed_from = []
+    got = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, checkpoint=ck, on_resume=resumed_from.append)
+    assert resumed_from == [28] and len(got) == len(ref) == sched.num_iterations
+    assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    # a state of another geometry is refused
+    q = _make_queue()
+    q.latents = q.latents[:, :-1].contiguous()
+    with pytest.raises(ValueError):
+        ck.load(ck.available()[-1], q)
+
+
+def _resume_worker(rank, world, port, num_frames, ckdir, out_path, crash_it):
+    from tokensgen_b200.fifo import FifoCheckpoint
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sched = FifoSchedule(num_frames, _timesteps())
+        ck = FifoCheckpoint(ckdir, every=5, rank=rank)
+        try:
+            em = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, rank=rank, world=world, checkpoint=ck,
+                          progress=_crash_at(crash_it) if crash_it is not None else None)
+            if rank == 0:
+                torch.save(torch.cat(em[52 - 13:], dim=1), out_path)
+        except _Crash:
+            pass
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fifo_stage_resumes_across_two_ranks(tmp_path):
+    num_frames = 26
+    sched = FifoSchedule(num_frames, _timesteps())
+    ref = torch.cat(run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3)[52 - 13:], dim=1)
+    out, ckdir = str(tmp_path / "emitted.pt"), str(tmp_path / "ck")
+    port = 29500 + (os.getpid() % 2000) + 40
+    mp.spawn(_resume_worker, args=(2, port, num_frames, ckdir, out, 33), nprocs=2, join=True)      # both ranks stop after it 33
+    assert not os.path.exists(out)
+    os.remove(os.path.join(ckdir, "fifo_state.rank1.it000030.pt"))   # rank 1's newest save was lost: resume from 25 on both
+    mp.spawn(_resume_worker, args=(2, port + 1, num_frames, ckdir, out, None), nprocs=2, join=True)
+    assert torch.equal(torch.load(out), ref)

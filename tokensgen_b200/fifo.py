@@ -16,6 +16,7 @@ The integer index schedule is bit-identical to the reference controller (tests/g
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -123,16 +124,69 @@ class FifoQueue:
         return lat, old
 
 
+class FifoCheckpoint:
+    """Restartable FIFO stage.  The reference's run is all-or-nothing (a 2-minute video is 351 iterations — 38
+    minutes on one GPU — and a worker crash deadlocks its controller, cogvideo_sampling_mp_fifo.py:309).  Every noise draw
+    of the loop is seeded by (seed, iteration, window rank), so the whole state of the stage between two iterations is the
+    queue (58 latent frames + x0 history + validity flags, ~20 MB) and the frames emitted so far: each rank writes its own
+    replica every `every` iterations (atomic rename, the last two generations are kept) and a restarted job resumes from
+    the newest iteration present on ALL ranks with bit-identical results."""
+
+    def __init__(self, directory: str, every: int, rank: int = 0):
+        self.dir, self.every, self.rank = directory, int(every), rank
+        os.makedirs(directory, exist_ok=True)
+
+    def _path(self, it: int) -> str:
+        return os.path.join(self.dir, f"fifo_state.rank{self.rank}.it{it:06d}.pt")
+
+    def available(self) -> List[int]:
+        pre, suf = f"fifo_state.rank{self.rank}.it", ".pt"
+        return sorted(int(f[len(pre):-len(suf)]) for f in os.listdir(self.dir) if f.startswith(pre) and f.endswith(suf))
+
+    def save(self, next_it: int, queue: "FifoQueue", emitted: List[torch.Tensor]) -> None:
+        state = {"next_it": next_it, "latents": queue.latents.cpu(), "x0": queue.x0.cpu(), "x0_valid": list(queue.x0_valid),
+                 "emitted": [e.cpu() for e in emitted]}
+        tmp = self._path(next_it) + ".tmp"
+        torch.save(state, tmp)
+        os.replace(tmp, self._path(next_it))
+        for old in self.available()[:-2]:
+            os.remove(self._path(old))
+
+    def load(self, it: int, queue: "FifoQueue") -> List[torch.Tensor]:
+        state = torch.load(self._path(it), map_location="cpu", weights_only=True)
+        if state["next_it"] != it or tuple(state["latents"].shape) != tuple(queue.latents.shape):
+            raise ValueError(f"{self._path(it)} does not belong to this run (shape / iteration mismatch)")
+        queue.latents.copy_(state["latents"])
+        queue.x0.copy_(state["x0"])
+        queue.x0_valid = list(state["x0_valid"])
+        return [e.to(queue.latents.device) for e in state["emitted"]]
+
+
 def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn, seed: int = 0, rank: int = 0,
-             world: int = 1, group=None, progress: Optional[Callable[[int], None]] = None) -> List[torch.Tensor]:
+             world: int = 1, group=None, progress: Optional[Callable[[int], None]] = None,
+             checkpoint: Optional[FifoCheckpoint] = None, on_resume: Optional[Callable[[int], None]] = None) -> List[torch.Tensor]:
     """The controller loop (:230-359).  `step_fn(window, latents[1,13,...], old_x0 list, t, prev_t, next_t, generator)`
     returns (latents_out [1,13,...], x0 list); `shift_fn(queue, noise_generator)` advances the queue by one slot and
     re-noises the tail.  Returns the emitted frames (slot r_nf of every iteration) as seen by this rank; rank 0's list is
-    the video (emissions before iteration T - nf are the ramp-up the reference drops, :367)."""
+    the video (emissions before iteration T - nf are the ramp-up the reference drops, :367).
+    `checkpoint`: save the stage state every `checkpoint.every` iterations and resume from the newest state all ranks
+    hold; `on_resume(k)` lets the caller fast-forward its own per-iteration bookkeeping (VipBook.shift) by k iterations."""
     import torch.distributed as dist
     emitted = []
     dev = queue.latents.device
-    for it in range(schedule.num_iterations):
+    start_it = 0
+    if checkpoint is not None:
+        have = checkpoint.available()
+        if world > 1:   # newest iteration every rank has (a crash may have interrupted a save on some of them)
+            sets = [None] * world
+            dist.all_gather_object(sets, have, group=group)
+            have = sorted(set.intersection(*[set(x) for x in sets]))
+        if have:
+            start_it = have[-1]
+            emitted = checkpoint.load(start_it, queue)
+            if on_resume is not None:
+                on_resume(start_it)
+    for it in range(start_it, schedule.num_iterations):
         wins = schedule.windows(it)
         mine = [w for w in wins if w.rank % world == rank]
         results = []
@@ -168,6 +222,9 @@ def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn
         emitted.append(queue.latents[:, [schedule.r_nf]].clone())
         ngen = torch.Generator(device=dev).manual_seed(seed * 1000003 + it + 7919)
         shift_fn(queue, ngen)
+        if checkpoint is not None and checkpoint.every > 0 and (it + 1) % checkpoint.every == 0 \
+                and it + 1 < schedule.num_iterations:
+            checkpoint.save(it + 1, queue, emitted)
         if progress is not None:
             progress(it)
     return emitted
@@ -320,7 +377,17 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
         if vip is not None:
             vip.shift()                                                   # :351-357
 
-    emitted = run_fifo(schedule, queue, step_fn, shift, seed=seed, rank=rank, world=world, progress=progress)
+    ckpt = None
+    if kwargs.get("checkpoint_dir"):   # schema extension: restartable FIFO stage (FifoCheckpoint)
+        ckpt = FifoCheckpoint(kwargs["checkpoint_dir"], kwargs.get("checkpoint_every", 10), rank)
+
+    def fast_forward(k):               # the condensed-token bookkeeping advances once per iteration (:351-357)
+        if vip is not None:
+            for _ in range(k):
+                vip.shift()
+
+    emitted = run_fifo(schedule, queue, step_fn, shift, seed=seed, rank=rank, world=world, progress=progress,
+                       checkpoint=ckpt, on_resume=fast_forward)
     latents = torch.cat(emitted[(T - nf):], dim=1).contiguous()           # :367 (slot r_nf belongs to window rank 0 -> process 0)
     if world > 1:
         dist.broadcast(latents, src=0)
