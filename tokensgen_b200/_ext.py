@@ -118,6 +118,9 @@ launch_count = 0
 profile: Optional[dict] = None
 
 
+_NVTX = _os.environ.get("TG_NVTX", "0") != "0"
+
+
 class _Timed:
     def __init__(self, tag: str, launches: int = 1):
         self.tag, self.launches = tag, launches
@@ -125,6 +128,8 @@ class _Timed:
     def __enter__(self):
         global launch_count
         launch_count += self.launches
+        if _NVTX:   # TG_NVTX=1: one NVTX range per op tag (shows up in nsys / ncu --nvtx timelines)
+            torch.cuda.nvtx.range_push(self.tag)
         if profile is not None:
             self.s = torch.cuda.Event(enable_timing=True)
             self.e = torch.cuda.Event(enable_timing=True)
@@ -132,6 +137,8 @@ class _Timed:
         return self
 
     def __exit__(self, *exc):
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
         if profile is not None:
             self.e.record()
             profile.setdefault(self.tag, []).append((self.s, self.e))
