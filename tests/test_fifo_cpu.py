@@ -100,9 +100,8 @@ def _worker(rank, world, port, num_frames, out_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_boundary_exchange_reproduces_single_process(tmp_path, world):
-    num_frames = 26
+@pytest.mark.parametrize("world,num_frames", [(2, 26), (4, 26), (3, 39), (8, 39)])
+def test_boundary_exchange_reproduces_single_process(tmp_path, world, num_frames):
     sched = FifoSchedule(num_frames, _timesteps())
     ref = torch.cat(run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3)[52 - 13:], dim=1)
     assert ref.shape[1] == num_frames
