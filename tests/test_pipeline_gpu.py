@@ -87,3 +87,38 @@ def test_t2to_pipeline_tail():
                use_dynamic_cfg=True, generator=torch.Generator().manual_seed(5), longvgen_mean=mean, longvgen_std=std,
                longvgen_pca=pca).frames
     assert tuple(out.shape) == (1, 8, 32, 2, 3) and out.dtype == torch.bfloat16 and torch.isfinite(out.float()).all()
+
+
+def test_fifo_stage_checkpoint_resume_is_bit_identical(tmp_path):
+    """Restartable FIFO stage through the sampler entry point: crash after iteration 9, restart, resume from the state
+    saved after iteration 8 (queue + x0 history + emitted frames; the condensed-token bookkeeping is fast-forwarded) —
+    the latents equal the uninterrupted run's."""
+    import copy
+    from tokensgen_b200.fifo import cogvideo_fifo_mp_v2
+    pipe = _tiny_pipe()
+    g = torch.Generator().manual_seed(3)
+    frames = torch.rand(1, 18, 3, 64, 96, generator=g) * 2 - 1
+    pe, ne = torch.randn(1, 10, 128, generator=g), torch.randn(1, 10, 128, generator=g)
+    base = pipe(frames=frames, prompt_embeds=pe, negative_prompt_embeds=ne, height=64, width=96, num_frames_per_chunk=9,
+                max_num_chunks=2, max_num_chunks_w_fifo=25, max_num_chunks_wo_fifo=1, num_inference_steps=12, guidance_scale=6.0,
+                generator=torch.Generator().manual_seed(42), vip_scale=[0.6], sampling_mode="fifo",
+                sampling_params={"num_partitions": 4, "use_adaptive_padding": True}, cache_idx=None, output_type="latent",
+                return_dict=False)
+    _, ref, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42)
+
+    class Crash(Exception):
+        pass
+
+    def crash(it):
+        if it == 9:
+            raise Crash()
+
+    ck = str(tmp_path / "ck")
+    with pytest.raises(Crash):
+        cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, checkpoint_dir=ck, checkpoint_every=4, progress=crash)
+    import os
+    assert sorted(os.listdir(ck)) == ["fifo_state.rank0.it000004.pt", "fifo_state.rank0.it000008.pt"]
+    seen = []
+    _, got, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, checkpoint_dir=ck, checkpoint_every=4, progress=seen.append)
+    assert seen[0] == 8                      # resumed, not restarted
+    assert torch.equal(got, ref)
