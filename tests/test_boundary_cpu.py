@@ -70,3 +70,32 @@ def test_state_dict_layout_matches_reference(use_vip):
         proc = m.transformer_blocks[0].attn1.processor
         assert type(proc).__name__ == "VideoIPAdapterCogVideoXAttnProcessor2_0" and proc.scale == [0.6]
         assert torch.equal(proc.vip_to_q.weight, m.transformer_blocks[0].attn1.to_q.weight)
+
+
+def test_ctypes_struct_layouts_match_the_header(tmp_path):
+    """Every struct the binding passes by pointer has the size and field offsets `gcc` gives the header's definition."""
+    import shutil
+    import subprocess
+    from tokensgen_b200 import _ext as E
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    structs = {"tg_rowmap": E.RowMap, "tg_modvec": E.ModVec, "tg_qkv_proj": E.QkvProj, "tg_qkv_scatter": E.QkvScatter,
+               "tg_attn_scatter": E.AttnScatter, "tg_dpm_step_args": E.DpmStepArgs, "tg_conv_args": E.ConvArgs,
+               "tg_norm_args": E.NormArgs}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/tokensgen_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf(" %zu", offsetof({cname}, {fname}));')
+        lines.append('  printf("\\n");')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    subprocess.run(["gcc", "-std=c99", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.strip().splitlines()
+    assert len(out) == len(structs)
+    for line, (cname, cls) in zip(out, structs.items()):
+        parts = line.split()
+        assert parts[0] == cname
+        want = [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
+        assert [int(x) for x in parts[1:]] == want, f"{cname}: header {parts[1:]} vs ctypes {want}"
