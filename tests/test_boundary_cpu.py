@@ -99,3 +99,15 @@ def test_ctypes_struct_layouts_match_the_header(tmp_path):
         assert parts[0] == cname
         want = [ctypes.sizeof(cls)] + [getattr(cls, f).offset for f, _ in cls._fields_]
         assert [int(x) for x in parts[1:]] == want, f"{cname}: header {parts[1:]} vs ctypes {want}"
+
+
+def test_binding_argument_counts_match_the_header():
+    from tokensgen_b200 import _ext
+    header = open(os.path.join(ROOT, "include", "tokensgen_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = re.findall(r"^(?:int|const char\*)\s+(tg_\w+)\s*\((.*?)\);", header, flags=re.M | re.S)
+    assert len(protos) == len(_ext.SYMBOLS)
+    for name, params in protos:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_ext.SYMBOLS[name][1]), f"{name}: header has {n} parameters, binding {len(_ext.SYMBOLS[name][1])}"
