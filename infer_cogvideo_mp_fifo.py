@@ -45,18 +45,20 @@ def create_output_folders(output_dir, config, prefix="longvgen"):
 def init_pipeline(gpu_id, args, dtype):
     """infer_cogvideo_mp_fifo.py:138-183."""
     device = torch.device(f"cuda:{gpu_id}")
+    # `device=`: the checkpoint shards are read straight to this rank's GPU into a meta-constructed module tree
+    # (tokensgen_b200/loading.py) — no CPU-side random init, fp32 copy or staging of the 11 GB transformer
     transformer = CogVideoXTransformer3DModel.from_pretrained(args.pretrained_model_name_or_path, subfolder="transformer",
-                                                              torch_dtype=torch.bfloat16).to(device)
+                                                              torch_dtype=torch.bfloat16, device=device).to(device)
     resampler = None
     if args.use_vip:
         vip_params = args.video_ipadapter_params
         vip_path = args.pretrained_resampler_name_or_path
         transformer.set_vip_layers(vip_path, **vip_params)
         transformer = transformer.to(dtype)
-        resampler = Resampler.from_pretrained(vip_path, subfolder="resampler", torch_dtype=dtype).to(device)
+        resampler = Resampler.from_pretrained(vip_path, subfolder="resampler", torch_dtype=dtype, device=device).to(device)
         resampler.set_pca(args.get("longvgen_pca", None), device=device)
     pipe = MPFIFOVideoIPAdapterCogVideoXPipeline.from_pretrained(args.pretrained_model_name_or_path, transformer=transformer,
-                                                                 resampler=resampler, torch_dtype=dtype)
+                                                                 resampler=resampler, torch_dtype=dtype, device=device)
     pipe.scheduler = CogVideoXDPMScheduler.from_config(pipe.scheduler.config, timestep_spacing="trailing")
     pipe.to(device)
     pipe.vae.enable_slicing()
@@ -90,7 +92,7 @@ def main(args):
     pipe_2nd = None
     if args.use_2nd_stage and (rank == 0 or seq_par):   # sequence-parallel: every rank holds the tokens transformer too
         tokens_transformer = CogVideoXTransformer3DModel.from_pretrained(args.pretrained_2nd_stage_model_name_or_path,
-                                                                         subfolder="transformer", torch_dtype=dtype)
+                                                                         subfolder="transformer", torch_dtype=dtype, device=device)
         pipe_2nd = LongVGenCogVideoXPipeline.from_pretrained(args.pretrained_model_name_or_path, transformer=tokens_transformer,
                                                              torch_dtype=dtype, vae=pipe.vae, text_encoder=pipe.text_encoder,
                                                              tokenizer=pipe.tokenizer)

@@ -96,6 +96,19 @@ def test_from_pretrained_roundtrip(tmp_path):
     assert m2.dtype == torch.bfloat16 and m2.config.heads == 4
     for k, v in m.state_dict().items():
         assert torch.equal(m2.state_dict()[k], v.to(torch.bfloat16))
+    # meta construction + assignment: every tensor materialised on the requested device, nothing left on `meta`
+    m3 = Resampler.from_pretrained(str(tmp_path), subfolder="resampler", torch_dtype=torch.bfloat16, device="cpu")
+    assert all(not t.is_meta and t.device.type == "cpu" for t in list(m3.parameters()) + list(m3.buffers()))
+    # a checkpoint of another geometry is refused (assignment would otherwise accept any shape) ...
+    sd = {k: v.contiguous() for k, v in m.state_dict().items()}
+    k0 = next(k for k, v in sd.items() if v.dim() == 2)
+    save_file(dict(sd, **{k0: sd[k0][:-1].contiguous()}), str(d / "diffusion_pytorch_model.safetensors"))
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        Resampler.from_pretrained(str(tmp_path), subfolder="resampler", torch_dtype=torch.bfloat16)
+    # ... and so is one that lacks tensors
+    save_file({k: v for k, v in sd.items() if k != k0}, str(d / "diffusion_pytorch_model.safetensors"))
+    with pytest.raises(RuntimeError, match="lacks"):
+        Resampler.from_pretrained(str(tmp_path), subfolder="resampler", torch_dtype=torch.bfloat16)
 
 
 def test_scheduler_from_config_ignores_unknown_keys():

@@ -141,9 +141,10 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         from .vae import AutoencoderKLCogVideoX
         root = pretrained_model_name_or_path
         if transformer is None:
-            transformer = CogVideoXTransformer3DModel.from_pretrained(root, subfolder="transformer", torch_dtype=torch_dtype)
+            transformer = CogVideoXTransformer3DModel.from_pretrained(root, subfolder="transformer", torch_dtype=torch_dtype,
+                                                                      device=kwargs.get("device"))
         if vae is None:
-            vae = AutoencoderKLCogVideoX.from_pretrained(root, subfolder="vae", torch_dtype=torch_dtype)
+            vae = AutoencoderKLCogVideoX.from_pretrained(root, subfolder="vae", torch_dtype=torch_dtype, device=kwargs.get("device"))
         if scheduler is None:
             path = os.path.join(root, "scheduler", "scheduler_config.json")
             cfg = load_config(root, "scheduler", "scheduler_config.json") if os.path.exists(path) else {}
