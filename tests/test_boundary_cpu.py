@@ -111,3 +111,18 @@ def test_binding_argument_counts_match_the_header():
         params = params.strip()
         n = 0 if params in ("", "void") else params.count(",") + 1
         assert n == len(_ext.SYMBOLS[name][1]), f"{name}: header has {n} parameters, binding {len(_ext.SYMBOLS[name][1])}"
+
+
+def test_library_sass_is_blackwell_native():
+    """The shipped .so holds sm_100a SASS with tcgen05 tensor-core MMAs (UTCHMMA, incl. the CTA-pair form), TMEM loads/stores
+    (LDTM/STTM), TMA tile loads (UTMALDG) and tcgen05 commits (UTCBAR) — not a recompiled mma.sync / cp.async path."""
+    import shutil
+    import subprocess
+    from tokensgen_b200 import _ext
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    sass = subprocess.run(["cuobjdump", "-sass", str(_ext.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    assert "sm_100a" in sass
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMALDG.2D.2CTA", "UTCBAR", "UTCBAR.2CTA.MULTICAST"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass and "LDGSTS" not in sass      # no mma.sync tensor path, no cp.async staging
