@@ -188,3 +188,33 @@ def test_fifo_stage_resumes_across_two_ranks(tmp_path):
     os.remove(os.path.join(ckdir, "fifo_state.rank1.it000030.pt"))   # rank 1's newest save was lost: resume from 25 on both
     mp.spawn(_resume_worker, args=(2, port + 1, num_frames, ckdir, out, None), nprocs=2, join=True)
     assert torch.equal(torch.load(out), ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 5, 6, 7, 8])
+@pytest.mark.parametrize("chunks", [1, 2, 5, 24])
+def test_transfer_plan_delivers_every_slot_a_rank_reads(world, chunks):
+    """Pure-index simulation of run_fifo's data movement for every process count: each rank's queue replica carries, per
+    slot, the iteration that last wrote it (as known to that rank); a window may only read slots whose stamp equals the
+    single-process truth.  Proves `FifoSchedule.transfers` is complete without running any arithmetic."""
+    s = FifoSchedule(chunks * 13, _timesteps())
+    L = s.queue_len
+    INIT = -1
+    truth = [INIT] * L
+    rep = [[INIT] * L for _ in range(world)]
+    for it in range(s.num_iterations):
+        wins = s.windows(it)
+        for w in wins:                                         # reads: the pre-iteration queue
+            r = w.rank % world
+            assert rep[r][w.start:w.end] == truth[w.start:w.end], (it, w.rank, r)
+        for w in wins:                                         # write-back
+            for q in range(w.write_lo, w.write_hi):
+                truth[q] = it
+                rep[w.rank % world][q] = it
+        for src, dst, lo, hi in s.transfers(it, world):         # boundary exchange
+            assert all(rep[src][q] == it for q in range(lo, hi)), "a rank sends slots it did not just write"
+            rep[dst][lo:hi] = rep[src][lo:hi]
+        # rank 0 emits slot r_nf: it must hold the true frame
+        assert rep[0][s.r_nf] == truth[s.r_nf]
+        fresh = 10 ** 6 + it                                   # shift by one slot, fresh noise at the tail (generated locally)
+        truth = truth[1:] + [fresh]
+        rep = [x[1:] + [fresh] for x in rep]
