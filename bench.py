@@ -134,6 +134,42 @@ def cpu_block_seconds(repeats: int, warmup: int):
     return times, cores
 
 
+def eager_block_seconds(device, repeats: int = 5, warmup: int = 2):
+    """Second baseline: the reference's op sequence in PyTorch eager ON THE GPU — the oracle port
+    executes the same torch ops the reference modules do (18 cuBLAS Linears, three SDPA calls, unfused LayerNorm / modulation
+    / RoPE / cat / gated residual) — for ONE CogVideoX-5b block + VIP at full size (B = 1), bf16.  Not the product path."""
+    from oracle import dit as odit
+    from oracle import rope as orope
+    from oracle.synth import dit_shapes, synth_state_dict
+    dev = torch.device(device)
+    shapes = {k: v for k, v in dit_shapes(48, 64, 1, 512, 4096, 16, 16, 2, 3072, True).items()
+              if k.startswith("transformer_blocks.0.")}
+    sd = {k: v.to(dev, torch.bfloat16) for k, v in synth_state_dict(shapes, 77).items()}
+    g = torch.Generator().manual_seed(42)
+    hid = torch.randn(1, TOKENS, 3072, generator=g).bfloat16().to(dev)
+    enc = torch.randn(1, 706, 3072, generator=g).bfloat16().to(dev)
+    temb = torch.randn(1, 13, 512, generator=g).bfloat16().to(dev)
+    on = lambda pair: tuple(t.to(dev) for t in pair)
+    rope = on(orope.window_rope(64, 13, 30, 45))
+    img = on(orope.rope_3d_from_grids(64, np.arange(13, dtype=np.float32), np.arange(30, dtype=np.float32),
+                                      np.arange(45, dtype=np.float32)))
+    cond = on(orope.rope_3d_from_grids(64, np.array([1000, 1003.25, 1006.5, 1009.75, 1013], dtype=np.float32),
+                                       np.linspace(0, 30, 8, endpoint=False, dtype=np.float32),
+                                       np.linspace(0, 45, 12, endpoint=False, dtype=np.float32)))
+    cfg = odit.DitConfig()
+    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            sync()
+            t0 = time.perf_counter()
+            odit.block_forward(sd, "transformer_blocks.0", cfg, hid, enc, temb, rope, img, cond, torch.bfloat16)
+            sync()
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return float(np.median(times))
+
+
 def cpu_tokens_per_s(block_seconds: float) -> float:
     # one bench step = 42 blocks x CFG pair (B = 2) of that block (embedding/final layers are < 0.1 % and left out)
     return TOKENS / (DENOISE_STEPS * 42 * 2 * block_seconds)
@@ -341,6 +377,17 @@ def run_ours(args):
         if seqpar is not None:
             seqpar["speedup_vs_this_runs_1gpu_step"] = ms_step / seqpar["ms_per_step"]
             line["sequence_parallel"] = seqpar
+        if world == 1 and not args.no_eager_baseline:
+            # reported next to the CPU baseline, never on the product path; a failure here must not cost the bench line
+            try:
+                sec = eager_block_seconds(dev)
+                line["gpu_eager_baseline"] = {
+                    "what": "the reference's op sequence in PyTorch eager on this GPU (oracle port: cuBLAS Linears + SDPA + unfused "
+                            "elementwise), ONE CogVideoX-5b block + VIP at full size, B = 1, bf16; a step = 42 blocks x 2 CFG branches",
+                    "block_ms": sec * 1e3, "value": cpu_tokens_per_s(sec), "unit": "tokens/s",
+                    "ours_over_eager": value / cpu_tokens_per_s(sec)}
+            except Exception as e:  # noqa: BLE001
+                line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
             times, cores = cpu_block_seconds(1, 1)
             line["cpu_baseline"] = {"value": cpu_tokens_per_s(times[0]), "unit": "tokens/s", "cores": cores, "kind": "port",
@@ -359,6 +406,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline block")
     ap.add_argument("--no-seqpar", action="store_true", help="N > 1: skip the extra sequence-parallel single-clip measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -179,7 +179,7 @@ def vip_attention(sd, pre: str, cfg: DitConfig, hidden: Tensor, enc: Tensor, rop
     out = sdpa(q, k, v)                                                      # :2067
     cross = sdpa(q_tv, k_vip, v_vip)                                         # :2117
     vip_out = sdpa(q_vip, torch.cat([k_tv, k_vip], 2), torch.cat([v_tv, v_vip], 2))  # :2120
-    scale = torch.tensor(cfg.vip_scale).to(out.dtype)                        # :2126-2133 (list of one -> scalar)
+    scale = torch.tensor(cfg.vip_scale).to(device=out.device, dtype=out.dtype)  # :2126-2133 (list of one -> scalar)
     out = out + scale * cross
     out = torch.cat([out, vip_out], dim=2).transpose(1, 2).reshape(B, -1, H * D)
     out = linear(out, sd, pre + ".to_out.0", dtype)
