@@ -13,6 +13,9 @@ sys.path.insert(0, str(ROOT))
 
 
 def same(a, b) -> bool:
+    import numpy as np
+    if isinstance(a, np.ndarray):
+        return isinstance(b, np.ndarray) and a.shape == b.shape and a.dtype == b.dtype and bool(np.array_equal(a, b))
     if torch.is_tensor(a):
         return torch.is_tensor(b) and a.shape == b.shape and a.dtype == b.dtype and torch.equal(a, b)
     if isinstance(a, dict):
@@ -27,9 +30,12 @@ def main() -> int:
     from oracle import ref_import
     committed = mg.GOLDEN
     mg.GOLDEN = pathlib.Path(tempfile.mkdtemp(prefix="goldens_"))
+    import transformers  # noqa: F401  (before the stubs are on sys.path: see make_goldens._load_ref_pipeline_module)
+    from transformers import AutoImageProcessor, AutoModel, T5EncoderModel, T5Tokenizer  # noqa: F401
     ref_import.enable()
     torch.set_num_threads(8)
-    for fn in (mg.gen_rope, mg.gen_dit_tiny, mg.gen_dpm, mg.gen_fifo_trace, mg.gen_vae_tiny, mg.gen_resampler_tiny):
+    for fn in (mg.gen_rope, mg.gen_dit_tiny, mg.gen_dpm, mg.gen_fifo_trace, mg.gen_vae_tiny, mg.gen_resampler_tiny,
+               mg.gen_pipeline_tiny):
         fn()
     bad = []
     names = sorted(p.name for p in mg.GOLDEN.iterdir())

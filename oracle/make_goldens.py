@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from oracle import ref_import
-from oracle.synth import dit_shapes, state_dict_digest, synth_state_dict
+from oracle.synth import conditioning_clip, dit_shapes, state_dict_digest, synth_state_dict
 
 GOLDEN = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
@@ -344,11 +344,110 @@ def gen_resampler_tiny():
     torch.save(blob, GOLDEN / "resampler_tiny.pt")
 
 
+PIPE_TINY = dict(
+    dit=dict(num_attention_heads=4, attention_head_dim=64, in_channels=16, out_channels=16, time_embed_dim=128, text_embed_dim=128,
+             num_layers=2, patch_size=2, use_rotary_positional_embeddings=True, attention_bias=True),
+    # 480 x 720 is forced by the reference itself: its CFG branch VAE-encodes hard-coded `zeros(.., 3, 480, 720)` clips
+    # (pipeline_cogvideox_mp_fifo.py:618) and feeds them to the Resampler with the conditioning video's RoPE tables
+    resampler=dict(dim=256, depth=1, dim_head=64, heads=4, num_height_queries=2, num_width_queries=3, num_temporal_queries=2,
+                   embedding_dim=256, output_dim=256, max_height_seq_len=30, max_width_seq_len=45, max_temporal_seq_len=3),
+    vae=dict(block_out_channels=(64, 64, 64, 64), layers_per_block=1, norm_num_groups=8, sample_height=480, sample_width=720,
+             scaling_factor=0.7),
+    call=dict(height=480, width=720, num_frames_per_chunk=9, max_num_chunks=2, max_num_chunks_w_fifo=25, max_num_chunks_wo_fifo=1,
+              num_inference_steps=12, guidance_scale=6.0, vip_scale=[0.6], sampling_mode="fifo",
+              sampling_params={"num_partitions": 4, "use_adaptive_padding": True}, cache_idx=None, output_type="latent",
+              return_dict=False),
+    seeds=dict(dit=1111, resampler=2222, vae=3333, inputs=3, call=42, global_rng=777))
+
+
+def _load_ref_pipeline_module():
+    """longvgen/pipeline/__init__.py imports every pipeline of the repository (CLIP / SVD era ones included); only
+    pipeline_cogvideox_mp_fifo.py is on the reproduced path, so that file is loaded on its own.  `transformers` must be
+    imported before the stubs are on sys.path (its dependency check would otherwise trip over the accelerate stub)."""
+    import importlib.util
+    import types
+    name = "longvgen.pipeline.pipeline_cogvideox_mp_fifo"
+    if name in sys.modules:
+        return sys.modules[name]
+    import longvgen  # noqa: F401  (namespace package rooted at the reference tree)
+    if "longvgen.pipeline" not in sys.modules:
+        pkg = types.ModuleType("longvgen.pipeline")
+        pkg.__path__ = [str(ref_import.REFERENCE_ROOT / "longvgen" / "pipeline")]
+        sys.modules["longvgen.pipeline"] = pkg
+    spec = importlib.util.spec_from_file_location(name, ref_import.REFERENCE_ROOT / "longvgen" / "pipeline" / "pipeline_cogvideox_mp_fifo.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def gen_pipeline_tiny():
+    """The reference's OWN base stage end to end — MPFIFOVideoIPAdapterCogVideoXPipeline.__call__
+    (pipeline_cogvideox_mp_fifo.py:837-1344): conditioning video -> VAE encode -> patch projection -> Resampler -> 12-step
+    CFG denoising loop with the diagonal FIFO capture — on tiny reference models with deterministic weights, in bf16 on the
+    CPU (the dtype the reference runs in; a CPU generator makes every noise draw reproducible on any device)."""
+    P = _load_ref_pipeline_module()
+    import longvgen.models.autoencoder_kl_cogvideox as vae_mod
+    from longvgen.models.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from longvgen.schedulers.scheduling_dpm_cogvideox import CogVideoXDPMScheduler
+    from longvgen.video_ipadapter.resampler import Resampler
+    c = PIPE_TINY
+    dit = CogVideoXTransformer3DModel(**c["dit"], sample_width=90, sample_height=60, sample_frames=9, max_text_seq_length=10)
+    dit.set_vip_layers(None, length=18, func_type="1", scale=[0.6], resampler_params=c["resampler"])
+    res = Resampler(**c["resampler"])
+    vae = vae_mod.AutoencoderKLCogVideoX(in_channels=3, out_channels=3, latent_channels=16, **c["vae"])
+    meta, sds = {}, {}
+    for name, m in (("dit", dit), ("resampler", res), ("vae", vae)):
+        shapes = {k: list(v.shape) for k, v in m.state_dict().items() if "pos_embedding" not in k}
+        sd = synth_state_dict(shapes, seed=c["seeds"][name])
+        m.load_state_dict(sd, strict=False)
+        m.to(torch.bfloat16).eval()
+        meta[name] = {"shapes": shapes, "digest": state_dict_digest(sd), "seed": c["seeds"][name]}
+    sch = CogVideoXDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                                prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=1.0,
+                                timestep_spacing="trailing")
+    pipe = P.MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae, dit, sch, resampler=res)
+    g = torch.Generator().manual_seed(c["seeds"]["inputs"])
+    pe = torch.randn(1, 10, 128, generator=g)
+    ne = torch.randn(1, 10, 128, generator=g)
+    frames = conditioning_clip(18)
+    emb_in = torch.randn(1, 4, 256, 2, 3, generator=g).bfloat16()      # 2 chunks x 2 temporal queries, the T2To stage's output shape
+    keys = ("fifo_latents", "fifo_old_pred_original_sample", "orig_latents", "nf_per_chunk", "vip_nf_per_chunk", "num_frames",
+            "image_embeddings", "timesteps", "num_inference_steps", "do_classifier_free_guidance", "prompt_embeds",
+            "vip_image_rotary_grid", "vip_condition_rotary_grid", "guidance_scale", "video_ipadapter_start_frame_idx")
+
+    def run(**kw):
+        with torch.no_grad():
+            out = pipe(prompt_embeds=pe.to(torch.bfloat16), negative_prompt_embeds=ne.to(torch.bfloat16),
+                       generator=torch.Generator().manual_seed(c["seeds"]["call"]), **c["call"], **kw)
+        o = out[0] if isinstance(out, tuple) and len(out) == 1 else out
+        return {k: getattr(o, k) for k in keys}
+
+    # (a) To2V flow (edit.yaml): conditioning video -> VAE -> Resampler.  The reference samples the VAE posterior from the
+    #     GLOBAL generator (`latent_dist.sample()` without one, :585), so the condensed tokens are reproducible only through
+    #     the seed set here; everything downstream of them draws from `generator`.
+    torch.manual_seed(c["seeds"]["global_rng"])
+    from_video = run(frames=frames.to(torch.bfloat16))
+    # (b) T2To + To2V flow (gen.yaml): condensed tokens given -> fully determined by `generator`
+    from_tokens = run(frames=None, image_embeddings=emb_in)
+    # the To2V flow shares everything downstream of the condensed tokens with (b): keep its tokens, grids, counts and the
+    # priming frame only (the fixture stays ~6 MB)
+    from_video["fifo_latents_last"] = from_video.pop("fifo_latents")[:, -1].clone()
+    for k in ("fifo_old_pred_original_sample", "orig_latents", "prompt_embeds"):
+        from_video.pop(k)
+    torch.save({"meta": meta, "config": {k: v for k, v in c.items() if k != "seeds"}, "seeds": c["seeds"],
+                "inputs": {"frames": "oracle.synth.conditioning_clip(18)", "prompt_embeds": pe, "negative_prompt_embeds": ne,
+                           "image_embeddings": emb_in},
+                "from_video": from_video, "from_tokens": from_tokens}, GOLDEN / "pipeline_tiny.pt")
+
+
 def main():
+    import transformers  # noqa: F401  (before the stubs: see _load_ref_pipeline_module)
+    from transformers import AutoImageProcessor, AutoModel, T5EncoderModel, T5Tokenizer  # noqa: F401
     ref_import.enable()
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    fns = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny, gen_resampler_tiny)
+    fns = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny, gen_resampler_tiny, gen_pipeline_tiny)
     only = set(sys.argv[1:])
     for fn in fns:
         if only and fn.__name__ not in only:

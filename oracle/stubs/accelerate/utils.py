@@ -1,2 +1,17 @@
 def gather_object(x):
     raise NotImplementedError("accelerate is not on the reproduced path")
+
+
+class DistributedDataParallelKwargs:
+    def __init__(self, *a, **k):
+        pass
+
+
+class ProjectConfiguration:
+    def __init__(self, *a, **k):
+        pass
+
+
+def set_seed(seed):
+    import torch
+    torch.manual_seed(seed)

@@ -1,0 +1,2 @@
+class CogVideoXDDIMScheduler:  # name-only (type hint in the reference pipelines)
+    pass

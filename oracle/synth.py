@@ -79,3 +79,17 @@ def dit_shapes(heads: int, head_dim: int, layers: int, time_dim: int, text_dim: 
         s[p + "ff.net.2.weight"] = [d, 4 * d]
         s[p + "ff.net.2.bias"] = [d]
     return s
+
+
+def conditioning_clip(frames: int = 10, height: int = 480, width: int = 720) -> torch.Tensor:
+    """Deterministic [1, F, 3, H, W] conditioning video in [-1, 1] (moving gradients + a seeded low-amplitude texture),
+    generated instead of stored: 10 frames of 480 x 720 fp32 would be a 41 MB fixture."""
+    t = torch.arange(frames, dtype=torch.float32)[:, None, None]
+    y = torch.arange(height, dtype=torch.float32)[None, :, None]
+    x = torch.arange(width, dtype=torch.float32)[None, None, :]
+    r = torch.sin(0.031 * x + 0.4 * t) * torch.cos(0.017 * y)
+    g = torch.sin(0.023 * y - 0.3 * t + 1.0)
+    b = torch.cos(0.011 * (x + y) + 0.2 * t)
+    clip = torch.stack(torch.broadcast_tensors(r, g, b), dim=1)
+    noise = torch.rand(clip.shape, generator=torch.Generator().manual_seed(5)) * 0.2 - 0.1
+    return (clip * 0.9 + noise).clamp(-1, 1).unsqueeze(0)
