@@ -214,7 +214,7 @@ def run_ours(args):
     E.load()
 
     model = build_random_model(device=dev, seed=rank)
-    sch = CogVideoXDPMScheduler()
+    sch = CogVideoXDPMScheduler.cogvideox_5b()
     sch.set_timesteps(DENOISE_STEPS)
     host = window_inputs(seed=42 + rank)
     F = 13

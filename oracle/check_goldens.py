@@ -34,8 +34,7 @@ def main() -> int:
     from transformers import AutoImageProcessor, AutoModel, T5EncoderModel, T5Tokenizer  # noqa: F401
     ref_import.enable()
     torch.set_num_threads(8)
-    for fn in (mg.gen_rope, mg.gen_dit_tiny, mg.gen_dpm, mg.gen_fifo_trace, mg.gen_vae_tiny, mg.gen_resampler_tiny,
-               mg.gen_pipeline_tiny):
+    for fn in mg.ALL:
         fn()
     bad = []
     names = sorted(p.name for p in mg.GOLDEN.iterdir())

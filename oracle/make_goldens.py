@@ -441,13 +441,262 @@ def gen_pipeline_tiny():
                 "from_video": from_video, "from_tokens": from_tokens}, GOLDEN / "pipeline_tiny.pt")
 
 
+FIFO_TINY = dict(
+    dit=dict(num_attention_heads=4, attention_head_dim=64, in_channels=16, out_channels=16, time_embed_dim=128, text_embed_dim=128,
+             num_layers=2, patch_size=2, use_rotary_positional_embeddings=True, attention_bias=True),
+    resampler=dict(output_dim=256, num_height_queries=2, num_width_queries=3, num_temporal_queries=2),
+    vip=dict(length=18, func_type="1", scale=[0.6]),
+    geom=dict(nf=3, T=12, num_chunks=2, C=16, H=8, W=12, n_text=10, vip_dim=256, num_partitions=4),
+    guidance_scale=6.0, start_frame_idx=1000,
+    seeds=dict(dit=4242, inputs=11))
+
+
+def fifo_tiny_base_output(device="cpu"):
+    """The FIFO priming state of the golden (what the base stage would hand to the sampler), built from seeded tensors and
+    the SAME grid arithmetic the pipeline uses (pipeline_cogvideox_mp_fifo.py:1061-1102): shared by the generator (reference
+    side) and the tests (product side), so the fixture only carries the reference's outputs.  numpy / torch only."""
+    c = FIFO_TINY
+    G = c["geom"]
+    nf, T, nc = G["nf"], G["T"], G["num_chunks"]
+    g = torch.Generator().manual_seed(c["seeds"]["inputs"])
+    frame = (1, 1, G["C"], G["H"], G["W"])
+    fifo_latents = torch.randn(1, T, G["C"], G["H"], G["W"], generator=g).bfloat16()
+    old = [torch.randn(frame, generator=g).bfloat16() for _ in range(T - 1)] + [None]
+    prompt = torch.randn(2, G["n_text"], c["dit"]["text_embed_dim"], generator=g).bfloat16()
+    rq = c["resampler"]
+    nt = rq["num_temporal_queries"]
+    emb = torch.randn(1, (nc + 1) * nt, G["vip_dim"], rq["num_height_queries"], rq["num_width_queries"], generator=g).bfloat16()
+    emb = torch.cat([emb, emb], dim=0)
+    orig = torch.randn(1, nf, G["C"], G["H"], G["W"], generator=g).bfloat16()
+    lin = lambda a, b, n: np.linspace(a, b, n, endpoint=False, dtype=np.float32)
+    gh, gw = G["H"] // 2, G["W"] // 2
+    s0 = c["start_frame_idx"]
+    img = [lin(0, nc * nf, nc * nf), lin(0, gh, gh), lin(0, gw, gw)]
+    cond = [np.concatenate([lin(s0 + i * nf, s0 + (i + 1) * nf, nt) for i in range(nc + 1)]),
+            lin(0, gh, rq["num_height_queries"]), lin(0, gw, rq["num_width_queries"])]
+    return dict(fifo_latents=fifo_latents.to(device), fifo_old_pred_original_sample=[None if o is None else o.to(device) for o in old],
+                prompt_embeds=prompt.to(device), image_embeddings=emb.to(device), orig_latents=orig.to(device),
+                vip_image_rotary_grid=img, vip_condition_rotary_grid=cond, nf_per_chunk=nf, vip_nf_per_chunk=nt,
+                num_frames=nc * nf, num_inference_steps=T, guidance_scale=c["guidance_scale"],
+                video_ipadapter_start_frame_idx=s0, rope_grid=(nf, gh, gw))
+
+
+def gen_fifo_stage():
+    """The reference SAMPLER end to end on tensors: `cogvideo_fifo_mp_v2` (cogvideo_sampling_mp_fifo.py:27-395) driving its
+    own worker `fifo_onestep_per_gpu` (:408-579) — run in a thread instead of a spawned GPU process — with the reference
+    DiT (tiny, bf16, CPU), the reference scheduler and the reference pipeline's vip-RoPE builder.  The only substitution is
+    the NOISE: the worker's `randn_tensor` draws and the controller's `torch.randn_like` re-noise (both from the global RNG
+    in the reference, :125-128 and scheduling_dpm_cogvideox.py:449,458) return `keyed_noise((iteration, start, frame, draw))`
+    so the product path can be given the identical noise on the GPU.  Recorded: every window call's outputs (controller
+    replay on CPU, bit-exact), the inputs of iterations 0 / 7 / 14 (teacher-forced window-step parity on the GPU) and the
+    final latents."""
+    import longvgen.fifo_sampling.cogvideo_sampling_mp_fifo as mod
+    import longvgen.schedulers.scheduling_dpm_cogvideox as smod
+    from longvgen.models.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from longvgen.models.embeddings import get_3d_rotary_pos_embed, get_3d_rotary_pos_embed_v2
+    from oracle.synth import keyed_noise
+    c = FIFO_TINY
+    G = c["geom"]
+    dit = CogVideoXTransformer3DModel(**c["dit"], sample_width=G["W"], sample_height=G["H"], sample_frames=9,
+                                      max_text_seq_length=G["n_text"])
+    dit.set_vip_layers(None, **c["vip"], resampler_params=c["resampler"])
+    shapes = {k: list(v.shape) for k, v in dit.state_dict().items() if "pos_embedding" not in k}
+    sd = synth_state_dict(shapes, seed=c["seeds"]["dit"])
+    dit.load_state_dict(sd, strict=False)
+    dit.to(torch.bfloat16).eval()
+    sch = smod.CogVideoXDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                                     prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=1.0,
+                                     timestep_spacing="trailing")
+    sch.set_timesteps(G["T"])
+    b = fifo_tiny_base_output()
+    rope = get_3d_rotary_pos_embed(64, [[0, 0, 0], list(b["rope_grid"])], b["rope_grid"])
+
+    state = {"it": 0, "start": 0, "j": -1, "which": 0}
+    calls = []
+
+    def keyed_randn_tensor(shape, generator=None, device=None, dtype=None, layout=None):
+        n = keyed_noise((state["it"], state["start"], state["j"], state["which"]), shape, dtype)
+        state["which"] += 1
+        return n
+
+    orig_step = sch.step
+
+    def step(*a, **k):
+        state["j"] += 1
+        state["which"] = 0
+        return orig_step(*a, **k)
+
+    sch.step = step
+
+    class Pipe:   # the attributes fifo_onestep_per_gpu / the controller touch on the reference pipeline object
+        scheduler, transformer, device, guidance_scale = sch, dit, torch.device("cpu"), c["guidance_scale"]
+
+        @staticmethod
+        def _prepare_vip_rotary_positional_embeddings(grid_t, grid_h, grid_w, device):
+            cos, sin = get_3d_rotary_pos_embed_v2(embed_dim=64, grid_t=grid_t, grid_h=grid_h, grid_w=grid_w)  # :797-813
+            return cos.to(device), sin.to(device)
+
+    class InQ(queue.Queue):
+        def get(self, *a, **k):
+            item = super().get(*a, **k)
+            if item is not None:
+                state.update(it=int(item[0]), start=int(item[3]), j=-1, which=0)
+                calls.append(dict(it=int(item[0]), start=int(item[3]), mid=int(item[4]), end=int(item[5]), real_end=int(item[6]),
+                                  lat_in=item[10].clone(), old_in=[None if o is None else o.clone() for o in item[11]],
+                                  emb_in=item[18].clone(), img_t=np.asarray(item[12]).copy(), cond_t=np.asarray(item[15]).copy()))
+            return item
+
+    class OutQ(queue.Queue):
+        def put(self, item, *a, **k):
+            if item is not None:
+                calls[-1]["lat_out"] = item[5].clone()
+                calls[-1]["x0_out"] = torch.cat([x.clone() for x in item[6]], dim=1)
+            return super().put(item, *a, **k)
+
+    class ThreadProc:
+        def __init__(self, target, args):
+            self.th = threading.Thread(target=target, args=args, daemon=True)
+
+        def start(self):
+            self.th.start()
+
+        def join(self):
+            self.th.join()
+
+        def close(self):
+            pass
+
+    qs = iter([InQ(), OutQ()])
+    saved = (mod.mp, mod.tqdm, smod.randn_tensor, torch.randn_like)
+    mod.mp = SimpleNamespace(Queue=lambda: next(qs), Process=ThreadProc)
+    mod.tqdm = lambda *a, **k: SimpleNamespace(update=lambda: None)
+    smod.randn_tensor = keyed_randn_tensor
+    torch.randn_like = lambda x, **k: keyed_noise((state["it"], 999, 0, 0), x.shape, x.dtype)   # shift_latents (:125-128)
+    try:
+        base = SimpleNamespace(
+            sampling_params={"num_partitions": G["num_partitions"], "use_adaptive_padding": True},
+            fifo_latents=b["fifo_latents"].clone(), fifo_old_pred_original_sample=list(b["fifo_old_pred_original_sample"]),
+            nf_per_chunk=b["nf_per_chunk"], vip_nf_per_chunk=b["vip_nf_per_chunk"], num_frames=b["num_frames"],
+            image_embeddings=b["image_embeddings"], timesteps=sch.timesteps, num_inference_steps=G["T"],
+            do_classifier_free_guidance=True, use_separate_guidance=False, use_dynamic_cfg=False, prompt_embeds=b["prompt_embeds"],
+            image_rotary_emb=rope, vip_image_rotary_grid=tuple(b["vip_image_rotary_grid"]),
+            vip_condition_rotary_grid=tuple(b["vip_condition_rotary_grid"]), attention_kwargs=None,
+            guidance_scale=c["guidance_scale"], guidance_scale_img=1.0, extra_step_kwargs={}, cache_idx=[], condition_frames=None,
+            video_ipadapter_start_frame_idx=c["start_frame_idx"], output_type="latent", return_dict=False,
+            orig_latents=b["orig_latents"])
+        orig, video, cache = mod.cogvideo_fifo_mp_v2([Pipe()], base)
+    finally:
+        mod.mp, mod.tqdm, smod.randn_tensor, torch.randn_like = saved
+        sch.step = orig_step
+    keep_inputs = {0, 7, 14}
+    recs = []
+    for r in calls:
+        rec = {k: r[k] for k in ("it", "start", "mid", "end", "real_end", "lat_out", "x0_out")}
+        if r["it"] in keep_inputs:
+            rec.update(lat_in=r["lat_in"], old_in=r["old_in"], emb_in=r["emb_in"], img_t=r["img_t"], cond_t=r["cond_t"])
+        recs.append(rec)
+    torch.save({"config": {k: v for k, v in c.items() if k != "seeds"}, "seeds": c["seeds"],
+                "meta": {"shapes": shapes, "digest": state_dict_digest(sd)}, "timesteps": sch.timesteps.clone(),
+                "calls": recs, "video": video.clone(), "orig": orig.clone()}, GOLDEN / "fifo_stage_tiny.pt")
+
+
+T2TO_TINY = dict(
+    dit=dict(num_attention_heads=4, attention_head_dim=64, in_channels=16, out_channels=16, time_embed_dim=128, text_embed_dim=128,
+             num_layers=2, patch_size=1, use_rotary_positional_embeddings=True, attention_bias=True),
+    call=dict(height=2, width=3, num_frames_per_chunk=2, num_chunks=4, num_inference_steps=6, guidance_scale=6.0,
+              use_dynamic_cfg=True, return_dict=False),
+    pca_width=32, seeds=dict(dit=5151, inputs=21, call=5, pca=9))
+
+
+def t2to_tiny_stats():
+    """mean / std / PCA of the T2To tail (pipeline_cogvideox_t2to.py:891-904).  The reference hard-codes a 3072-wide PCA
+    input, so `components_` is [3072, width]; only its first 16 rows meet non-zero coordinates."""
+    c = T2TO_TINY
+    g = torch.Generator().manual_seed(c["seeds"]["pca"])
+    mean, std = torch.randn(1, 3072, generator=g), torch.rand(1, 3072, generator=g) + 0.5
+    comp = torch.randn(3072, c["pca_width"], generator=g) / 4
+    pmean = torch.randn(1, c["pca_width"], generator=g)
+    return mean, std, comp, pmean
+
+
+def gen_t2to_tiny():
+    """The reference's T2To stage end to end — LongVGenCogVideoXPipeline.__call__ (pipeline_cogvideox_t2to.py:584-912): the
+    patch_size = 1 DiT with RoPE dims 52/6/6 (:543-564), dynamic CFG (:849-858), DPM steps, un-normalisation + PCA inverse —
+    on a tiny reference model in bf16 on the CPU, plus ONE forward of that model in fp32 and bf16 and the RoPE tables."""
+    import importlib.util
+    import types
+    _load_ref_pipeline_module()          # registers the fake `longvgen.pipeline` package
+    name = "longvgen.pipeline.pipeline_cogvideox_t2to"
+    if name not in sys.modules:
+        spec = importlib.util.spec_from_file_location(name, ref_import.REFERENCE_ROOT / "longvgen" / "pipeline" / "pipeline_cogvideox_t2to.py")
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+    P = sys.modules[name]
+    sys.path.insert(0, str(ref_import.REFERENCE_ROOT))
+    import importlib
+    ref_pca = importlib.machinery.SourceFileLoader("ref_pca", str(ref_import.REFERENCE_ROOT / "pca.py")).load_module()
+    from longvgen.models.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from longvgen.models.embeddings import get_3d_rotary_pos_embed_v2
+    from longvgen.schedulers.scheduling_dpm_cogvideox import CogVideoXDPMScheduler
+    c = T2TO_TINY
+    dit = CogVideoXTransformer3DModel(**c["dit"], sample_width=3, sample_height=2, sample_frames=8, max_text_seq_length=10)
+    shapes = {k: list(v.shape) for k, v in dit.state_dict().items() if "pos_embedding" not in k}
+    sd = synth_state_dict(shapes, seed=c["seeds"]["dit"])
+    dit.load_state_dict(sd, strict=False)
+    dit.eval()
+    g = torch.Generator().manual_seed(c["seeds"]["inputs"])
+    pe, ne = torch.randn(1, 10, 128, generator=g).bfloat16(), torch.randn(1, 10, 128, generator=g).bfloat16()
+    lat = torch.randn(2, 8, 16, 2, 3, generator=g).bfloat16()
+    ts = torch.tensor([731, 731])
+    lin = lambda n: np.linspace(0, n, n, endpoint=False, dtype=np.float32)
+    rope = get_3d_rotary_pos_embed_v2(embed_dim=64, grid_t=lin(8), grid_h=lin(2), grid_w=lin(3), dim_t=52, dim_h=6, dim_w=6)
+    blob = {"config": {k: v for k, v in c.items() if k != "seeds"}, "seeds": c["seeds"],
+            "meta": {"shapes": shapes, "digest": state_dict_digest(sd)},
+            "inputs": {"prompt_embeds": pe, "negative_prompt_embeds": ne, "latents": lat, "timestep": ts},
+            "rope_cos": rope[0].clone(), "rope_sin": rope[1].clone()}
+    text = torch.cat([ne, pe])
+    for dt, tag in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        dit.load_state_dict({k: v.to(dt) for k, v in sd.items()}, strict=False)
+        dit.to(dt)
+        with torch.no_grad():
+            blob["forward_" + tag] = dit(hidden_states=lat.to(dt), encoder_hidden_states=text.to(dt), timestep=ts,
+                                         image_rotary_emb=rope, return_dict=False)[0].clone()
+    sch = CogVideoXDPMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", num_train_timesteps=1000,
+                                prediction_type="v_prediction", rescale_betas_zero_snr=True, snr_shift_scale=1.0,
+                                timestep_spacing="trailing")
+    pipe = P.LongVGenCogVideoXPipeline(None, None, dit, sch)
+    mean, std, comp, pmean = t2to_tiny_stats()
+    pca = ref_pca.PCA(None)
+    pca.register_buffer("mean_", pmean)
+    pca.register_buffer("components_", comp)
+    import tempfile
+    tmp = Path(tempfile.mkdtemp(prefix="t2to_"))
+    torch.save(mean, tmp / "mean.pt"), torch.save(std, tmp / "std.pt"), torch.save(pca, tmp / "pca.pt")
+    orig_load = torch.load                 # the reference targets torch 2.4 (weights_only defaulted to False): pca.pt is a pickled module
+    torch.load = lambda f, **k: orig_load(f, weights_only=False)
+    try:
+        with torch.no_grad():
+            out = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, generator=torch.Generator().manual_seed(c["seeds"]["call"]),
+                       longvgen_mean=str(tmp / "mean.pt"), longvgen_std=str(tmp / "std.pt"), longvgen_pca=str(tmp / "pca.pt"),
+                       **c["call"])
+    finally:
+        torch.load = orig_load
+    blob["frames"] = out[0].clone()
+    torch.save(blob, GOLDEN / "t2to_tiny.pt")
+
+
+ALL = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny, gen_resampler_tiny, gen_pipeline_tiny, gen_fifo_stage,
+       gen_t2to_tiny)
+
+
 def main():
     import transformers  # noqa: F401  (before the stubs: see _load_ref_pipeline_module)
     from transformers import AutoImageProcessor, AutoModel, T5EncoderModel, T5Tokenizer  # noqa: F401
     ref_import.enable()
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(8)
-    fns = (gen_rope, gen_dit_tiny, gen_dpm, gen_fifo_trace, gen_vae_tiny, gen_resampler_tiny, gen_pipeline_tiny)
+    fns = ALL
     only = set(sys.argv[1:])
     for fn in fns:
         if only and fn.__name__ not in only:

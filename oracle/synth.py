@@ -93,3 +93,13 @@ def conditioning_clip(frames: int = 10, height: int = 480, width: int = 720) -> 
     clip = torch.stack(torch.broadcast_tensors(r, g, b), dim=1)
     noise = torch.rand(clip.shape, generator=torch.Generator().manual_seed(5)) * 0.2 - 0.1
     return (clip * 0.9 + noise).clamp(-1, 1).unsqueeze(0)
+
+
+def keyed_noise(key, shape, dtype=torch.bfloat16) -> torch.Tensor:
+    """Deterministic N(0,1) draw identified by a tuple of small non-negative ints (iteration, window start, frame, draw...):
+    the FIFO-stage golden replaces the reference's global-RNG draws with these so that the product path can be fed the very
+    same noise on any device (tests/golden/fifo_stage_tiny.pt)."""
+    seed = 0x5EED
+    for k in key:
+        seed = (seed * 1000003 + int(k) + 1) % (1 << 62)
+    return torch.randn(tuple(shape), generator=torch.Generator().manual_seed(seed), dtype=torch.float32).to(dtype)

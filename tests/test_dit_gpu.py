@@ -189,7 +189,7 @@ def test_window_step_vs_oracle_loop():
         n1 = torch.randn(1, F, *shp, generator=gen).bfloat16()
         n2 = torch.randn(1, F, *shp, generator=gen).bfloat16()
         ref_lat, ref_x0 = odpm.window_step_bf16(tb, npred, 6.0, lat, old, t, pt, nt, n1, n2)
-        sch = CogVideoXDPMScheduler()
+        sch = CogVideoXDPMScheduler.cogvideox_5b()
         sch.set_timesteps(52)
         out_lat, out_x0 = sch.window_step(npred.cuda(), lat.cuda(), [None if o is None else o.cuda() for o in old],
                                           t, pt, nt, 6.0, noise=(n1.cuda(), n2.cuda()))

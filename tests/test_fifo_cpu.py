@@ -151,11 +151,42 @@ def test_fifo_stage_resumes_bit_identically_after_a_crash(tmp_path):
     got = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, checkpoint=ck, on_resume=resumed_from.append)
     assert resumed_from == [28] and len(got) == len(ref) == sched.num_iterations
     assert all(torch.equal(a, b) for a, b in zip(got, ref))
+    assert ck.available() == []                          # a completed run removes its own states
     # a state of another geometry is refused
+    with pytest.raises(_Crash):
+        run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, checkpoint=ck, progress=_crash_at(30))
     q = _make_queue()
     q.latents = q.latents[:, :-1].contiguous()
     with pytest.raises(ValueError):
         ck.load(ck.available()[-1], q)
+
+
+def test_checkpoints_of_another_run_are_never_resumed(tmp_path):
+    """the CLI keys the checkpoint directory by item name; a re-run of the same item with another seed,
+    prompt, guidance, world size or weights must not resume from the old run's state.  The run fingerprint is part of the file
+    name and of the file."""
+    from tokensgen_b200.fifo import FifoCheckpoint, run_fingerprint
+    sched = FifoSchedule(26, _timesteps())
+    fp_a = run_fingerprint(3, 1, 26, _timesteps(), torch.arange(8.0))
+    fp_b = run_fingerprint(4, 1, 26, _timesteps(), torch.arange(8.0))             # another seed
+    fp_c = run_fingerprint(3, 1, 26, _timesteps(), torch.arange(8.0) + 1)         # other priming latents
+    fp_d = run_fingerprint(3, 2, 26, _timesteps(), torch.arange(8.0))             # another world size
+    assert len({fp_a, fp_b, fp_c, fp_d}) == 4 and fp_a == run_fingerprint(3, 1, 26, _timesteps(), torch.arange(8.0))
+    a = FifoCheckpoint(str(tmp_path), every=7, fingerprint=fp_a)
+    with pytest.raises(_Crash):
+        run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, checkpoint=a, progress=_crash_at(30))
+    assert a.available() == [21, 28]
+    b = FifoCheckpoint(str(tmp_path), every=7, fingerprint=fp_b)
+    assert b.available() == []
+    resumed = []
+    ref_b = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=4)
+    got_b = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=4, checkpoint=b, on_resume=resumed.append)
+    assert resumed == [] and all(torch.equal(x, y) for x, y in zip(got_b, ref_b))     # started from scratch
+    assert a.available() == [21, 28]                                                  # and left run A's states alone
+    # a state file renamed into another run's namespace is refused by the fingerprint stored inside it
+    os.rename(a._path(28), b._path(28))
+    with pytest.raises(ValueError):
+        b.load(28, _make_queue())
 
 
 def _resume_worker(rank, world, port, num_frames, ckdir, out_path, crash_it):
@@ -185,7 +216,7 @@ def test_fifo_stage_resumes_across_two_ranks(tmp_path):
     port = 29500 + (os.getpid() % 2000) + 40
     mp.spawn(_resume_worker, args=(2, port, num_frames, ckdir, out, 33), nprocs=2, join=True)      # both ranks stop after it 33
     assert not os.path.exists(out)
-    os.remove(os.path.join(ckdir, "fifo_state.rank1.it000030.pt"))   # rank 1's newest save was lost: resume from 25 on both
+    os.remove(os.path.join(ckdir, f"fifo_state.{'0' * 16}.rank1.it000030.pt"))   # rank 1's newest save was lost: resume from 25 on both
     mp.spawn(_resume_worker, args=(2, port + 1, num_frames, ckdir, out, None), nprocs=2, join=True)
     assert torch.equal(torch.load(out), ref)
 
@@ -218,3 +249,42 @@ def test_transfer_plan_delivers_every_slot_a_rank_reads(world, chunks):
         fresh = 10 ** 6 + it                                   # shift by one slot, fresh noise at the tail (generated locally)
         truth = truth[1:] + [fresh]
         rep = [x[1:] + [fresh] for x in rep]
+
+
+# ------------------------------------------------------------------------------------------------ base-output broadcast
+def _bcast_worker(rank, world, port, out_dir):
+    from types import SimpleNamespace
+    from tokensgen_b200.fifo import broadcast_base_output
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        base = None
+        if rank == 0:
+            g = torch.Generator().manual_seed(1)
+            base = SimpleNamespace(fifo_latents=torch.randn(1, 5, 2, 3, 4, generator=g), num_frames=26,
+                                   fifo_old_pred_original_sample=[torch.randn(1, 1, 2, 3, 4, generator=g), None],
+                                   image_rotary_emb=(torch.randn(6, 4, generator=g), torch.randn(6, 4, generator=g)),
+                                   vip_image_rotary_grid=[np.arange(3, dtype=np.float32)] * 3,
+                                   extra_step_kwargs={"generator": torch.Generator().manual_seed(7)}, sampling_params={"a": 1})
+        got = broadcast_base_output(base, src=0, device=torch.device("cpu"))
+        if rank == 0:
+            assert got is base and base.extra_step_kwargs is not None          # the sender's object is untouched
+        torch.save({"lat": got.fifo_latents, "old0": got.fifo_old_pred_original_sample[0],
+                    "old1_is_none": got.fifo_old_pred_original_sample[1] is None, "rope1": got.image_rotary_emb[1],
+                    "grid": got.vip_image_rotary_grid[2], "extra": None if rank == 0 else got.extra_step_kwargs,
+                    "num_frames": got.num_frames, "sp": got.sampling_params}, os.path.join(out_dir, f"r{rank}.pt"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_base_output_broadcast_ships_host_tensors_and_no_generator(tmp_path):
+    """the bundle is pickled with CPU tensors (no CUDA context on the sender's device in every receiver) and
+    without the call's torch.Generator; every field arrives intact on every rank (gloo, world size 3)."""
+    port = 29500 + (os.getpid() % 2000) + 77
+    mp.spawn(_bcast_worker, args=(3, port, str(tmp_path)), nprocs=3, join=True)
+    r = [torch.load(tmp_path / f"r{i}.pt", weights_only=False) for i in range(3)]
+    for k in (1, 2):
+        assert torch.equal(r[k]["lat"], r[0]["lat"]) and torch.equal(r[k]["old0"], r[0]["old0"]) and r[k]["old1_is_none"]
+        assert torch.equal(r[k]["rope1"], r[0]["rope1"]) and np.array_equal(r[k]["grid"], r[0]["grid"])
+        assert r[k]["extra"] is None and r[k]["num_frames"] == 26 and r[k]["sp"] == {"a": 1}

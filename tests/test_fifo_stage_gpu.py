@@ -1,0 +1,129 @@
+"""FIFO stage on the GPU against the reference SAMPLER's own run (tests/golden/fifo_stage_tiny.pt, see
+tests/test_fifo_stage_golden_cpu.py for what the fixture is): (1) teacher-forced window steps — the reference worker's
+recorded inputs through the product's DiT forward + fused CFG/DPM step against the recorded outputs; (2) the whole stage
+through `cogvideo_fifo_mp_v2` with the reference's noise draws against the reference's final latents."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return torch.load(os.path.join(ROOT, "tests", "golden", "fifo_stage_tiny.pt"), weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def model(gold):
+    from oracle.synth import synth_state_dict
+    from tokensgen_b200.transformer import CogVideoXTransformer3DModel
+    c = gold["config"]
+    m = CogVideoXTransformer3DModel(**c["dit"])
+    m.set_vip_layers(None, **c["vip"], resampler_params=c["resampler"])
+    m.load_state_dict(synth_state_dict(gold["meta"]["shapes"], seed=gold["seeds"]["dit"]), strict=True)
+    return m.to("cuda", torch.bfloat16).eval()
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def test_window_steps_teacher_forced_against_the_reference_worker(gold, model):
+    """cogvideo_sampling_mp_fifo.py:408-579 on the recorded inputs of iterations 0 / 7 / 14 (ramp-up, steady state, tail)."""
+    from oracle import dpm as odpm
+    from oracle.make_goldens import fifo_tiny_base_output
+    from oracle.synth import keyed_noise
+    from tokensgen_b200.fifo import FifoSchedule
+    from tokensgen_b200.rope import get_3d_rotary_pos_embed, get_3d_rotary_pos_embed_v2
+    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+    dev = torch.device("cuda")
+    b = fifo_tiny_base_output()
+    c = gold["config"]
+    nf, gh, gw = b["rope_grid"]
+    sched = FifoSchedule(b["num_frames"], [int(t) for t in gold["timesteps"]], nf, c["geom"]["num_partitions"], True)
+    sch = CogVideoXDPMScheduler.cogvideox_5b()
+    sch.set_timesteps(c["geom"]["T"])
+    rope = get_3d_rotary_pos_embed(64, [[0, 0, 0], [nf, gh, gw]], (nf, gh, gw), device=dev)
+    tables = odpm.DpmTables()
+    worst_fwd, worst_step, n = 0.0, 0.0, 0
+    for rec in gold["calls"]:
+        if "lat_in" not in rec:
+            continue
+        it, s, e = rec["it"], rec["start"], rec["end"]
+        img = get_3d_rotary_pos_embed_v2(64, rec["img_t"], b["vip_image_rotary_grid"][1], b["vip_image_rotary_grid"][2], device=dev)
+        cond = get_3d_rotary_pos_embed_v2(64, rec["cond_t"], b["vip_condition_rotary_grid"][1], b["vip_condition_rotary_grid"][2],
+                                          device=dev)
+        lat = rec["lat_in"].to(dev)
+        ts = torch.as_tensor(sched.t[s:e].copy(), device=dev).expand(2, -1)
+        with torch.no_grad():
+            npred = model(hidden_states=torch.cat([lat, lat]), encoder_hidden_states=b["prompt_embeds"].to(dev), timestep=ts,
+                          vip_encoder_hidden_states=rec["emb_in"].to(dev).contiguous(), image_rotary_emb=rope,
+                          vip_image_rotary_emb=img, vip_condition_rotary_emb=cond, return_dict=False)[0]
+        n1 = torch.cat([keyed_noise((it, s, j, 0), lat[:, [j]].shape) for j in range(nf)], dim=1)
+        n2 = torch.cat([keyed_noise((it, s, j, 1), lat[:, [j]].shape) for j in range(nf)], dim=1)
+        t, pt, nt = sched.t[s:e], sched.prev_t[s:e], sched.next_t[s:e]
+        # (a) the product's DiT prediction pushed through the reference's own CPU scheduler arithmetic: isolates the forward
+        out_a, x0_a = odpm.window_step_bf16(tables, npred.cpu(), c["guidance_scale"], rec["lat_in"], rec["old_in"], t, pt, nt,
+                                            n1, n2, device_semantics="cpu")
+        worst_fwd = max(worst_fwd, rel(out_a, rec["lat_out"]), rel(torch.cat(x0_a, 1), rec["x0_out"]))
+        # (b) the product's own fused step (CUDA scalar semantics, which differ from the CPU run's by a bf16 rounding of the
+        # coefficients — oracle/dpm.py::_smul)
+        old = [None if o is None else o.to(dev) for o in rec["old_in"]]
+        out_b, x0_b = sch.window_step(npred, lat, old, t, pt, nt, c["guidance_scale"], noise=(n1.to(dev), n2.to(dev)))
+        worst_step = max(worst_step, rel(out_b, rec["lat_out"]), rel(torch.cat([x.reshape(1, 1, *lat.shape[2:]) for x in x0_b], 1),
+                                                                     rec["x0_out"]))
+        n += 1
+    print(f"teacher-forced window steps ({n} calls): forward-only rel_l2 {worst_fwd:.3e}, fused step rel_l2 {worst_step:.3e}")
+    assert n >= 10
+    assert worst_fwd < 1e-2 and worst_step < 1.5e-2
+
+
+def test_whole_stage_against_the_reference_sampler(gold, model):
+    """`cogvideo_fifo_mp_v2` (ours) on the golden's priming state with the reference's noise draws: 15 iterations, 77 window
+    forwards, every frame denoised through all 12 levels — final latents against the reference's."""
+    from oracle.make_goldens import fifo_tiny_base_output
+    from oracle.synth import keyed_noise
+    from tokensgen_b200.fifo import cogvideo_fifo_mp_v2
+    from tokensgen_b200.pipeline import FIFOCogVideoXPipelineOutput
+    from tokensgen_b200.rope import get_3d_rotary_pos_embed
+    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+    dev = torch.device("cuda")
+    b = fifo_tiny_base_output(dev)
+    c = gold["config"]
+    nf, gh, gw = b["rope_grid"]
+    sch = CogVideoXDPMScheduler.cogvideox_5b()
+    sch.set_timesteps(c["geom"]["T"])
+    pipe = SimpleNamespace(transformer=model, scheduler=sch)
+    base = FIFOCogVideoXPipelineOutput(
+        fifo_latents=b["fifo_latents"], fifo_old_pred_original_sample=b["fifo_old_pred_original_sample"],
+        orig_latents=b["orig_latents"], nf_per_chunk=nf, vip_nf_per_chunk=b["vip_nf_per_chunk"], num_frames=b["num_frames"],
+        image_embeddings=b["image_embeddings"], timesteps=gold["timesteps"], num_inference_steps=c["geom"]["T"],
+        do_classifier_free_guidance=True, use_separate_guidance=False, use_dynamic_cfg=False, prompt_embeds=b["prompt_embeds"],
+        image_rotary_emb=get_3d_rotary_pos_embed(64, [[0, 0, 0], [nf, gh, gw]], (nf, gh, gw), device=dev),
+        vip_image_rotary_grid=b["vip_image_rotary_grid"], vip_condition_rotary_grid=b["vip_condition_rotary_grid"], cache_idx=[],
+        guidance_scale=c["guidance_scale"], video_ipadapter_start_frame_idx=c["start_frame_idx"],
+        sampling_params={"num_partitions": c["geom"]["num_partitions"], "use_adaptive_padding": True}, output_type="latent",
+        return_dict=False)
+    frame = (1, 1) + tuple(b["fifo_latents"].shape[2:])
+    state = {"it": 0}
+
+    def window_noise(w):
+        state["it"] = w.iteration
+        mk = lambda which: torch.cat([keyed_noise((w.iteration, w.start, j, which), frame) for j in range(nf)], dim=1).to(dev)
+        return mk(0), mk(1)
+
+    def shift_noise(shape):
+        return keyed_noise((state["it"], 999, 0, 0), shape)
+
+    orig, video, _ = cogvideo_fifo_mp_v2([pipe], base, seed=0, window_noise=window_noise, shift_noise=shift_noise)
+    assert tuple(video.shape) == tuple(gold["video"].shape) and torch.equal(orig.cpu(), gold["orig"])
+    err = rel(video, gold["video"])
+    per_frame = [rel(video[:, j], gold["video"][:, j]) for j in range(video.shape[1])]
+    print(f"FIFO stage vs the reference sampler: final latents rel_l2 {err:.3e} (per frame {['%.2e' % e for e in per_frame]})")
+    assert err < 3e-2

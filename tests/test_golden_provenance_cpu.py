@@ -14,4 +14,4 @@ def test_committed_goldens_reproduce_from_the_unmodified_reference():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "check_goldens.py")], cwd=ROOT, capture_output=True,
                        text=True, timeout=1200)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert r.stdout.count("reproduced") == 8 and "DIFFERS" not in r.stdout
+    assert r.stdout.count("reproduced") == 10 and "DIFFERS" not in r.stdout

@@ -111,10 +111,23 @@ def test_from_pretrained_roundtrip(tmp_path):
         Resampler.from_pretrained(str(tmp_path), subfolder="resampler", torch_dtype=torch.bfloat16)
 
 
-def test_scheduler_from_config_ignores_unknown_keys():
-    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
-    s = CogVideoXDPMScheduler.from_config({"_class_name": "CogVideoXDDIMScheduler", "snr_shift_scale": 1.0, "beta_end": 0.012,
-                                           "timestep_spacing": "leading"}, timestep_spacing="trailing")
+def test_scheduler_from_config_and_reference_defaults():
+    """a partial config must mean what it means in the reference (scheduling_dpm_cogvideox.py:181-197 defaults:
+    epsilon / leading / no zero-SNR rescale / snr_shift_scale 3.0), diffusers bookkeeping keys are dropped, anything else
+    unknown is an error."""
+    import inspect
+    from tokensgen_b200.scheduler import COGVIDEOX_5B_CONFIG, CogVideoXDPMScheduler
+    sig = inspect.signature(CogVideoXDPMScheduler.__init__).parameters
+    assert (sig["prediction_type"].default, sig["timestep_spacing"].default, sig["rescale_betas_zero_snr"].default,
+            sig["snr_shift_scale"].default, sig["clip_sample"].default) == ("epsilon", "leading", False, 3.0, True)
+    s = CogVideoXDPMScheduler.from_config({"_class_name": "CogVideoXDDIMScheduler", "_diffusers_version": "0.31.0.dev0",
+                                           **COGVIDEOX_5B_CONFIG, "timestep_spacing": "leading"}, timestep_spacing="trailing")
     assert s.config.timestep_spacing == "trailing"
     s.set_timesteps(52)
     assert int(s.timesteps[0]) == 999 and len(s.timesteps) == 52
+    with pytest.raises(NotImplementedError, match="v_prediction"):
+        CogVideoXDPMScheduler.from_config({"beta_end": 0.012})          # prediction_type missing -> the reference's "epsilon"
+    with pytest.raises(ValueError, match="unknown keys"):
+        CogVideoXDPMScheduler.from_config({**COGVIDEOX_5B_CONFIG, "thresholding": True})
+    a, b = CogVideoXDPMScheduler.cogvideox_5b(), CogVideoXDPMScheduler.cogvideox_5b(snr_shift_scale=3.0)
+    assert not torch.equal(a.alphas_cumprod, b.alphas_cumprod)

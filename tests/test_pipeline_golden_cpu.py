@@ -27,7 +27,7 @@ def _cpu_pipe(cfg):
         dit.set_vip_layers(None, length=18, func_type="1", scale=[0.6], resampler_params=cfg["resampler"])
         res = Resampler(**cfg["resampler"])
         vae = AutoencoderKLCogVideoX(**cfg["vae"])
-    pipe = MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae, dit, CogVideoXDPMScheduler(), resampler=res)
+    pipe = MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae, dit, CogVideoXDPMScheduler.cogvideox_5b(), resampler=res)
     pipe._device = torch.device("cpu")
     return pipe, dit, res, vae
 

@@ -28,7 +28,7 @@ def _tiny_pipe():
                                  sample_width=96, scaling_factor=0.7)
     dev = torch.device("cuda")
     pipe = MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae.to(dev, torch.bfloat16).eval(), dit.to(dev, torch.bfloat16).eval(),
-                                                 CogVideoXDPMScheduler(), resampler=res.to(dev, torch.bfloat16).eval())
+                                                 CogVideoXDPMScheduler.cogvideox_5b(), resampler=res.to(dev, torch.bfloat16).eval())
     return pipe.to(dev)
 
 
@@ -78,7 +78,7 @@ def test_t2to_pipeline_tail():
                                       num_layers=2, patch_size=1, use_rotary_positional_embeddings=True, attention_bias=True)
     for p in dit.parameters():
         torch.nn.init.normal_(p, std=0.02)
-    pipe = LongVGenCogVideoXPipeline(None, None, None, dit.to("cuda", torch.bfloat16).eval(), CogVideoXDPMScheduler()).to("cuda")
+    pipe = LongVGenCogVideoXPipeline(None, None, dit.to("cuda", torch.bfloat16).eval(), CogVideoXDPMScheduler.cogvideox_5b()).to("cuda")
     g = torch.Generator().manual_seed(2)
     pca = PCA(None).fit(torch.randn(64, 32, generator=g))
     mean, std = torch.randn(1, 32, generator=g), torch.rand(1, 32, generator=g) + 0.5
@@ -117,20 +117,22 @@ def test_fifo_stage_checkpoint_resume_is_bit_identical(tmp_path):
     with pytest.raises(Crash):
         cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, checkpoint_dir=ck, checkpoint_every=4, progress=crash)
     import os
-    assert sorted(os.listdir(ck)) == ["fifo_state.rank0.it000004.pt", "fifo_state.rank0.it000008.pt"]
+    names = sorted(os.listdir(ck))
+    assert len(names) == 2 and names[0].endswith(".rank0.it000004.pt") and names[1].endswith(".rank0.it000008.pt")
     seen = []
     _, got, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, checkpoint_dir=ck, checkpoint_every=4, progress=seen.append)
     assert seen[0] == 8                      # resumed, not restarted
     assert torch.equal(got, ref)
+    assert os.listdir(ck) == []              # the completed run removed its states
+    # the same item with another seed must NOT resume from a state of the old run
+    with pytest.raises(Crash):
+        cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, checkpoint_dir=ck, checkpoint_every=4, progress=crash)
+    seen2 = []
+    cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=43, checkpoint_dir=ck, checkpoint_every=4, progress=seen2.append)
+    assert seen2[0] == 0
 
 
-@pytest.mark.skipif(__import__("os").environ.get("TG_PIPELINE_GOLDEN") != "1",
-                    reason="written after round 1's GPU budget was spent: validate once with TG_PIPELINE_GOLDEN=1, then un-gate")
-def test_base_stage_against_the_reference_pipeline_golden():
-    """The whole base stage (gen.yaml flow: condensed tokens given) against the reference's own
-    MPFIFOVideoIPAdapterCogVideoXPipeline.__call__ run on CPU in bf16 (tests/golden/pipeline_tiny.pt): same deterministic
-    weights, same prompt embeddings, same CPU generator -> identical noise draws; the 12-step CFG loop with the diagonal FIFO
-    capture must agree within the bf16 tolerance, the arithmetic-free parts exactly."""
+def _golden_pipe():
     import os
     from oracle.synth import synth_state_dict
     from tokensgen_b200.pipeline import MPFIFOVideoIPAdapterCogVideoXPipeline
@@ -148,7 +150,20 @@ def test_base_stage_against_the_reference_pipeline_golden():
     for name, m in (("dit", dit), ("resampler", res), ("vae", vae)):
         m.load_state_dict(synth_state_dict(meta[name]["shapes"], seed=meta[name]["seed"]), strict=True)
         m.to(dev, torch.bfloat16).eval()
-    pipe = MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae, dit, CogVideoXDPMScheduler(), resampler=res).to(dev)
+    pipe = MPFIFOVideoIPAdapterCogVideoXPipeline(None, None, vae, dit, CogVideoXDPMScheduler.cogvideox_5b(), resampler=res).to(dev)
+    return gold, pipe
+
+
+_rel = lambda a, b: ((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm()).item()
+
+
+def test_base_stage_against_the_reference_pipeline_golden():
+    """The whole base stage (gen.yaml flow: condensed tokens given) against the reference's own
+    MPFIFOVideoIPAdapterCogVideoXPipeline.__call__ run on CPU in bf16 (tests/golden/pipeline_tiny.pt): same deterministic
+    weights, same prompt embeddings, same CPU generator -> identical noise draws; the 12-step CFG loop with the diagonal FIFO
+    capture must agree within the bf16 tolerance, the arithmetic-free parts exactly."""
+    gold, pipe = _golden_pipe()
+    cfg = gold["config"]
     inp, ref = gold["inputs"], gold["from_tokens"]
     out = pipe(frames=None, image_embeddings=inp["image_embeddings"], prompt_embeds=inp["prompt_embeds"],
                negative_prompt_embeds=inp["negative_prompt_embeds"],
@@ -156,10 +171,35 @@ def test_base_stage_against_the_reference_pipeline_golden():
     out = out[0] if isinstance(out, tuple) else out
     assert torch.equal(out.image_embeddings.cpu(), ref["image_embeddings"])
     assert torch.equal(out.fifo_latents[:, -1].cpu(), ref["fifo_latents"][:, -1])          # priming frame: pure noise draw
-    rel = lambda a, b: ((a.double().cpu() - b.double()).norm() / b.double().norm()).item()
-    e_fifo, e_orig = rel(out.fifo_latents, ref["fifo_latents"]), rel(out.orig_latents, ref["orig_latents"])
+    e_fifo, e_orig = _rel(out.fifo_latents, ref["fifo_latents"]), _rel(out.orig_latents, ref["orig_latents"])
     print(f"base stage vs reference pipeline (bf16 CPU): fifo_latents rel_l2 {e_fifo:.3e}, orig_latents rel_l2 {e_orig:.3e}")
     assert e_fifo < 2e-2 and e_orig < 3e-2
     old = out.fifo_old_pred_original_sample
     assert len(old) == 12 and old[-1] is None
-    assert rel(old[0].reshape(ref["fifo_old_pred_original_sample"][0].shape), ref["fifo_old_pred_original_sample"][0]) < 3e-2
+    assert _rel(old[0].reshape(ref["fifo_old_pred_original_sample"][0].shape), ref["fifo_old_pred_original_sample"][0]) < 3e-2
+
+
+def test_from_video_flow_against_the_reference_pipeline_golden():
+    """edit.yaml flow (pipeline_cogvideox_mp_fifo.py:562-648): conditioning video -> VAE encode (3 chunks of 9 frames at
+    480 x 720, posterior SAMPLE x scaling) -> patch_embed.proj -> Resampler -> padding / CFG layout, against the condensed
+    tokens of the reference's own run.  The reference draws the posterior noise from the global RNG (seeded in the generator
+    script); the same CPU stream is replayed through `vae_posterior_generator`.  The call's `generator` must stay untouched by
+    the encode: the priming frame (first draw of prepare_latents) and the grids are exact."""
+    from oracle.synth import conditioning_clip
+    gold, pipe = _golden_pipe()
+    cfg, ref = gold["config"], gold["from_video"]
+    pipe.vae_posterior_generator = torch.Generator().manual_seed(gold["seeds"]["global_rng"])
+    inp = gold["inputs"]
+    out = pipe(frames=conditioning_clip(18).to(torch.bfloat16), prompt_embeds=inp["prompt_embeds"],
+               negative_prompt_embeds=inp["negative_prompt_embeds"],
+               generator=torch.Generator().manual_seed(gold["seeds"]["call"]), **cfg["call"])
+    out = out[0] if isinstance(out, tuple) else out
+    ie = out.image_embeddings
+    assert tuple(ie.shape) == tuple(ref["image_embeddings"].shape) and torch.equal(ie[0], ie[1])
+    err = _rel(ie, ref["image_embeddings"])
+    print(f"from-video flow: condensed tokens (VAE encode -> proj -> Resampler) vs the reference pipeline rel_l2 {err:.3e}")
+    assert err < 3e-2
+    assert torch.equal(out.fifo_latents[:, -1].cpu(), ref["fifo_latents_last"])
+    assert (out.nf_per_chunk, out.vip_nf_per_chunk, out.num_frames) == (ref["nf_per_chunk"], ref["vip_nf_per_chunk"], ref["num_frames"])
+    for mine, want in zip(out.vip_condition_rotary_grid, ref["vip_condition_rotary_grid"]):
+        assert np.array_equal(np.asarray(mine, np.float32), np.asarray(want, np.float32))

@@ -163,11 +163,14 @@ def test_forward_virtual_ranks_bit_identical(golden_dir, world, use_vip):
     from oracle.synth import dit_shapes, synth_state_dict
     from test_dit_gpu import TINY, tiny_model
     g = torch.load(os.path.join(golden_dir, "dit_tiny.pt"))
-    tag = ("vip" if use_vip else "plain") + "_pf"
-    lat, text, vip, ts = g[tag + "_inputs"]
+    base = "vip" if use_vip else "plain"
     sd = synth_state_dict(dit_shapes(use_vip=use_vip, **TINY), 1234)
+    # per-frame timesteps, then per-sample ones at the SAME (B, rows) geometry, then per-frame again: the sharded workspaces
+    # freeze a rowmap (frames / hw) and must not be reused across the two (transformer.py workspace key)
+    order = ("pf", "ps", "pf")
 
-    def run(m):
+    def run(m, kind="pf"):
+        lat, text, vip, ts = g[f"{base}_{kind}_inputs"]
         with torch.no_grad():
             return m(lat.cuda(), text.cuda(), ts.cuda(), vip_encoder_hidden_states=vip.cuda() if use_vip else None,
                      image_rotary_emb=g["rope"], vip_image_rotary_emb=g["img_rope"] if use_vip else None,
@@ -177,10 +180,12 @@ def test_forward_virtual_ranks_bit_identical(golden_dir, world, use_vip):
     old = T._FUSE_PAIR
     T._FUSE_PAIR = True  # the sharded path always fuses K4 + K5; compare against the same kernel sequence
     try:
-        ref = run(tiny_model(use_vip, sd))
+        ref_model = tiny_model(use_vip, sd)
+        ref = {k: run(ref_model, k).clone() for k in ("pf", "ps")}
     finally:
         T._FUSE_PAIR = old
     torch.cuda.synchronize()
+    assert not torch.equal(ref["pf"], ref["ps"])
     shared = {"base": [None] * world, "rows": [None] * world, "bar": threading.Barrier(world)}
     outs, errs = [None] * world, []
 
@@ -189,8 +194,11 @@ def test_forward_virtual_ranks_bit_identical(golden_dir, world, use_vip):
             torch.cuda.set_device(0)
             m = tiny_model(use_vip, sd)
             m.__dict__["_tg_sp"] = _VirtualPeers(world, r, shared)
-            for _ in range(2):  # twice: buffer reuse across forwards
-                outs[r] = run(m)
+            outs[r] = []
+            for kind in order:
+                for _ in range(2):  # twice: buffer reuse across forwards
+                    y = run(m, kind)
+                outs[r].append(y.clone())
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
             errs.append(e)
@@ -201,7 +209,9 @@ def test_forward_virtual_ranks_bit_identical(golden_dir, world, use_vip):
     [t.join(timeout=120) for t in th]
     assert not errs, errs
     for r in range(world):
-        assert outs[r] is not None and torch.equal(outs[r], ref), f"rank {r} differs"
+        assert outs[r] is not None and len(outs[r]) == len(order)
+        for kind, y in zip(order, outs[r]):
+            assert torch.equal(y, ref[kind]), f"rank {r} differs on the {kind} forward"
 
 
 # ------------------------------------------------------------------------------------------------ real peers

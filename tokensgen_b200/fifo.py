@@ -124,28 +124,54 @@ class FifoQueue:
         return lat, old
 
 
+def run_fingerprint(*parts) -> str:
+    """Identity of one FIFO run for checkpoint matching: ints / floats / strings / lists are hashed by repr, tensors by their
+    bytes (CPU copy).  Two runs share checkpoints only if every part agrees."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in parts:
+        if torch.is_tensor(p):
+            t = p.detach().to("cpu").contiguous()
+            h.update(str((tuple(t.shape), str(t.dtype))).encode())
+            h.update(t.view(torch.uint8).numpy().tobytes())
+        elif isinstance(p, np.ndarray):
+            h.update(str((p.shape, str(p.dtype))).encode())
+            h.update(np.ascontiguousarray(p).tobytes())
+        else:
+            h.update(repr(p).encode())
+        h.update(b"|")
+    return h.hexdigest()[:16]
+
+
 class FifoCheckpoint:
     """Restartable FIFO stage.  The reference's run is all-or-nothing (a 2-minute video is 351 iterations — 38
     minutes on one GPU — and a worker crash deadlocks its controller, cogvideo_sampling_mp_fifo.py:309).  Every noise draw
     of the loop is seeded by (seed, iteration, window rank), so the whole state of the stage between two iterations is the
     queue (58 latent frames + x0 history + validity flags, ~20 MB) and the frames emitted so far: each rank writes its own
     replica every `every` iterations (atomic rename, the last two generations are kept) and a restarted job resumes from
-    the newest iteration present on ALL ranks with bit-identical results."""
+    the newest iteration present on ALL ranks with bit-identical results.
 
-    def __init__(self, directory: str, every: int, rank: int = 0):
-        self.dir, self.every, self.rank = directory, int(every), rank
+    A state only ever resumes the run that wrote it: `fingerprint` (seed, world size, schedule, and a hash of the priming
+    latents / prompt / condensed-token embeddings / a weight probe — `run_fingerprint`) is part of the file name AND stored
+    inside the file; states of other runs in the same directory are ignored, and a run that completes removes its own."""
+
+    def __init__(self, directory: str, every: int, rank: int = 0, fingerprint: str = "0" * 16):
+        self.dir, self.every, self.rank, self.fingerprint = directory, int(every), rank, str(fingerprint)
         os.makedirs(directory, exist_ok=True)
 
+    def _prefix(self) -> str:
+        return f"fifo_state.{self.fingerprint}.rank{self.rank}.it"
+
     def _path(self, it: int) -> str:
-        return os.path.join(self.dir, f"fifo_state.rank{self.rank}.it{it:06d}.pt")
+        return os.path.join(self.dir, f"{self._prefix()}{it:06d}.pt")
 
     def available(self) -> List[int]:
-        pre, suf = f"fifo_state.rank{self.rank}.it", ".pt"
+        pre, suf = self._prefix(), ".pt"
         return sorted(int(f[len(pre):-len(suf)]) for f in os.listdir(self.dir) if f.startswith(pre) and f.endswith(suf))
 
     def save(self, next_it: int, queue: "FifoQueue", emitted: List[torch.Tensor]) -> None:
-        state = {"next_it": next_it, "latents": queue.latents.cpu(), "x0": queue.x0.cpu(), "x0_valid": list(queue.x0_valid),
-                 "emitted": [e.cpu() for e in emitted]}
+        state = {"next_it": next_it, "fingerprint": self.fingerprint, "latents": queue.latents.cpu(), "x0": queue.x0.cpu(),
+                 "x0_valid": list(queue.x0_valid), "emitted": [e.cpu() for e in emitted]}
         tmp = self._path(next_it) + ".tmp"
         torch.save(state, tmp)
         os.replace(tmp, self._path(next_it))
@@ -154,12 +180,19 @@ class FifoCheckpoint:
 
     def load(self, it: int, queue: "FifoQueue") -> List[torch.Tensor]:
         state = torch.load(self._path(it), map_location="cpu", weights_only=True)
+        if state.get("fingerprint") != self.fingerprint:
+            raise ValueError(f"{self._path(it)} was written by a different run (fingerprint mismatch)")
         if state["next_it"] != it or tuple(state["latents"].shape) != tuple(queue.latents.shape):
             raise ValueError(f"{self._path(it)} does not belong to this run (shape / iteration mismatch)")
         queue.latents.copy_(state["latents"])
         queue.x0.copy_(state["x0"])
         queue.x0_valid = list(state["x0_valid"])
         return [e.to(queue.latents.device) for e in state["emitted"]]
+
+    def clear(self) -> None:
+        """The run completed: its states must not resume a later run of the same item."""
+        for it in self.available():
+            os.remove(self._path(it))
 
 
 def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn, seed: int = 0, rank: int = 0,
@@ -227,17 +260,23 @@ def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn
             checkpoint.save(it + 1, queue, emitted)
         if progress is not None:
             progress(it)
+    if checkpoint is not None:
+        checkpoint.clear()
     return emitted
 
 
-def make_shift_fn(scheduler):
-    """shift_latents (:117-131) on the GPU: one tg_queue_shift_renoise launch for the latent queue and its x0 history."""
+def make_shift_fn(scheduler, noise_override=None):
+    """shift_latents (:117-131) on the GPU: one tg_queue_shift_renoise launch for the latent queue and its x0 history.
+    `noise_override(shape)` supplies the re-noise draw instead of the (seed, iteration) generator (parity tests)."""
     from . import _ext as E
     b = scheduler.betas[999].double()
     s1, s2 = float((1 - b) ** 0.5), float(b ** 0.5)
 
     def shift(queue: FifoQueue, gen: torch.Generator):
-        noise = torch.randn(queue.x0.shape[1:], generator=gen, device=queue.x0.device, dtype=torch.bfloat16)
+        if noise_override is not None:
+            noise = noise_override(tuple(queue.x0.shape[1:])).to(device=queue.x0.device, dtype=torch.bfloat16).contiguous()
+        else:
+            noise = torch.randn(queue.x0.shape[1:], generator=gen, device=queue.x0.device, dtype=torch.bfloat16)
         E.queue_shift_renoise(queue.latents[0], queue.x0, noise, s1, s2)
         queue.x0_valid = queue.x0_valid[1:] + [False]
 
@@ -301,19 +340,35 @@ def broadcast_base_output(base_output, src: int = 0, device=None, group=None):
     """Ships the FIFO priming state of the base stage from rank `src` to every rank (one object broadcast of ~0.2 GB for
     gen.yaml: 52 + 52 latent frames, prompt and condensed-token embeddings, grids).  The reference hands the same bundle
     to its worker processes through mp.Queue on every window (cogvideo_sampling_mp_fifo.py:284-305); here it crosses
-    NVLink once per video."""
+    NVLink once per video.  The bundle is pickled with its tensors on the HOST (a pickled CUDA tensor is rebuilt on the
+    sender's device index by every receiver: a context + ~0.2 GB on GPU 0 per rank) and without the call's
+    torch.Generator (`extra_step_kwargs`, unused by the FIFO stage); receivers move the tensors to their own `device`."""
+    import copy
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return base_output
-    box = [base_output if dist.get_rank(group) == src else None]
+
+    def convert(v, fn):
+        if torch.is_tensor(v):
+            return fn(v)
+        if isinstance(v, (list, tuple)) and v and all(torch.is_tensor(x) or x is None for x in v):
+            return type(v)(None if x is None else fn(x) for x in v)
+        return v
+
+    box = [None]
+    if dist.get_rank(group) == src:
+        host = copy.copy(base_output)
+        for name, v in list(vars(host).items()):
+            setattr(host, name, convert(v, lambda t: t.detach().cpu()))
+        host.extra_step_kwargs = None
+        box = [host]
     dist.broadcast_object_list(box, src=src, group=group, device=device)
+    if dist.get_rank(group) == src:
+        return base_output
     out = box[0]
     if device is not None:
         for name, v in list(vars(out).items()):
-            if torch.is_tensor(v):
-                setattr(out, name, v.to(device))
-            elif isinstance(v, (list, tuple)) and v and all(torch.is_tensor(x) or x is None for x in v):
-                setattr(out, name, type(v)(None if x is None else x.to(device) for x in v))
+            setattr(out, name, convert(v, lambda t: t.to(device)))
     return out
 
 
@@ -368,9 +423,12 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
     if base_output.image_embeddings is not None:
         vip = VipBook(base_output.vip_image_rotary_grid, base_output.vip_condition_rotary_grid, base_output.image_embeddings,
                       nf, base_output.vip_nf_per_chunk, T, base_output.video_ipadapter_start_frame_idx)
+    # `window_noise(window) -> (n1, n2)` / `shift_noise(shape)`: supply the noise the reference would draw from its global RNG
+    # (tests/test_fifo_stage_gpu.py feeds the draws of the reference-sampler golden); default: the (seed, iteration, rank) streams
     step_fn = make_step_fn(pipe.transformer, pipe.scheduler, base_output.prompt_embeds, base_output.image_rotary_emb, vip,
-                           base_output.guidance_scale if base_output.do_classifier_free_guidance else 1.0)
-    shift_latents = make_shift_fn(pipe.scheduler)
+                           base_output.guidance_scale if base_output.do_classifier_free_guidance else 1.0,
+                           noise_override=kwargs.get("window_noise"))
+    shift_latents = make_shift_fn(pipe.scheduler, noise_override=kwargs.get("shift_noise"))
 
     def shift(q, gen):
         shift_latents(q, gen)
@@ -379,7 +437,14 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
 
     ckpt = None
     if kwargs.get("checkpoint_dir"):   # schema extension: restartable FIFO stage (FifoCheckpoint)
-        ckpt = FifoCheckpoint(kwargs["checkpoint_dir"], kwargs.get("checkpoint_every", 10), rank)
+        probe = [p.detach().reshape(-1)[:4096] for p in (pipe.transformer.proj_out.weight,
+                                                          pipe.transformer.transformer_blocks[0].attn1.to_q.weight)]
+        vip_scale = [getattr(b.attn1.processor, "scale", None) for b in pipe.transformer.transformer_blocks[:1]]
+        fp = run_fingerprint(seed, world, base_output.num_frames, [int(t) for t in base_output.timesteps], nf,
+                             base_output.guidance_scale, sp.get("num_partitions", 4), sp.get("use_adaptive_padding", True),
+                             vip_scale, base_output.fifo_latents, base_output.prompt_embeds,
+                             base_output.image_embeddings if base_output.image_embeddings is not None else "no-vip", *probe)
+        ckpt = FifoCheckpoint(kwargs["checkpoint_dir"], kwargs.get("checkpoint_every", 10), rank, fingerprint=fp)
 
     def fast_forward(k):               # the condensed-token bookkeeping advances once per iteration (:351-357)
         if vip is not None:

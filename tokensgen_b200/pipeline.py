@@ -129,6 +129,11 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         self.video_processor = VideoProcessor(vae_scale_factor=self.vae_scale_factor_spatial)
         self._device = transformer.device if transformer is not None else torch.device("cpu")
         self._guidance_scale, self._attention_kwargs, self._interrupt, self._num_timesteps = 6.0, None, False, 0
+        # The reference samples the VAE posterior of the conditioning clips WITHOUT a generator (`latent_dist.sample()`,
+        # pipeline_cogvideox_mp_fifo.py:585): the device's global RNG, not the call's `generator`, whose stream is consumed
+        # only by prepare_latents and the scheduler steps.  None keeps exactly that; a generator here makes the condensed
+        # tokens reproducible (schema extension; the parity test replays the reference's CPU global stream through it).
+        self.vae_posterior_generator = None
 
     # ------------------------------------------------------------------ construction / placement
     @classmethod
@@ -143,12 +148,16 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         if transformer is None:
             transformer = CogVideoXTransformer3DModel.from_pretrained(root, subfolder="transformer", torch_dtype=torch_dtype,
                                                                       device=kwargs.get("device"))
-        if vae is None:
+        if vae is False:       # LongVGenCogVideoXPipeline (T2To): no VAE in that stage
+            vae = None
+        elif vae is None:
             vae = AutoencoderKLCogVideoX.from_pretrained(root, subfolder="vae", torch_dtype=torch_dtype, device=kwargs.get("device"))
         if scheduler is None:
             path = os.path.join(root, "scheduler", "scheduler_config.json")
-            cfg = load_config(root, "scheduler", "scheduler_config.json") if os.path.exists(path) else {}
-            scheduler = CogVideoXDPMScheduler.from_config(cfg, timestep_spacing="trailing")
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"{path} is missing: the noise schedule comes from the checkpoint tree, there is no default")
+            scheduler = CogVideoXDPMScheduler.from_config(load_config(root, "scheduler", "scheduler_config.json"),
+                                                          timestep_spacing="trailing")
         if text_encoder is None and os.path.isdir(os.path.join(root, "text_encoder")):
             try:
                 from transformers import T5EncoderModel, T5Tokenizer
@@ -156,6 +165,8 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
                 text_encoder = T5EncoderModel.from_pretrained(root, subfolder="text_encoder", torch_dtype=torch_dtype)
             except Exception as e:  # third-party encoder is optional: prompt_embeds can be passed instead
                 print(f"tokensgen_b200: T5 text encoder not loaded ({e}); pass prompt_embeds")
+        if vae is None:
+            return cls(tokenizer, text_encoder, transformer, scheduler)
         return cls(tokenizer, text_encoder, vae, transformer, scheduler, resampler=resampler)
 
     def to(self, device):
@@ -255,7 +266,7 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         pe = self.transformer.patch_embed
 
         def encode_video(video):
-            return self._encode_video_chunks(video, nf_per_chunk, device, dtype, generator)
+            return self._encode_video_chunks(video, nf_per_chunk, device, dtype, self.vae_posterior_generator)
 
         def condense(lat):
             b, f, c, h, w = lat.shape

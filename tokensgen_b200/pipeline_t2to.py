@@ -18,8 +18,17 @@ from .rope import get_3d_rotary_pos_embed_v2
 
 
 class LongVGenCogVideoXPipeline(MPFIFOVideoIPAdapterCogVideoXPipeline):
-    def __init__(self, tokenizer, text_encoder, vae, transformer, scheduler, **_unused):
-        super().__init__(tokenizer, text_encoder, vae, transformer, scheduler, resampler=None)
+    def __init__(self, tokenizer, text_encoder, transformer, scheduler, **_unused):
+        """Same positional signature as the reference (pipeline_cogvideox_t2to.py:297-311): this stage has no VAE."""
+        super().__init__(tokenizer, text_encoder, None, transformer, scheduler, resampler=None)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, transformer=None, torch_dtype=torch.bfloat16, text_encoder=None,
+                        tokenizer=None, scheduler=None, **kwargs):
+        """infer_cogvideo_mp_fifo.py:225-229: the T2To stage shares the checkpoint tree's scheduler / T5 with the To2V one."""
+        kwargs.pop("vae", None), kwargs.pop("resampler", None)
+        return super().from_pretrained(pretrained_model_name_or_path, transformer=transformer, torch_dtype=torch_dtype,
+                                       vae=False, text_encoder=text_encoder, tokenizer=tokenizer, scheduler=scheduler, **kwargs)
 
     def prepare_latents(self, batch_size, num_channels_latents, num_chunks, num_frames_per_chunk, height, width, dtype, device,
                         generator, latents=None):

@@ -19,18 +19,29 @@ import torch
 from . import _ext as E
 
 
+# scheduler/scheduler_config.json of THUDM/CogVideoX-5b (SURVEY §8 [HF config]); timestep_spacing is overridden to
+# "trailing" by the CLI (infer_cogvideo_mp_fifo.py:177-178)
+COGVIDEOX_5B_CONFIG = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                           clip_sample=False, set_alpha_to_one=True, steps_offset=0, prediction_type="v_prediction",
+                           clip_sample_range=1.0, sample_max_value=1.0, timestep_spacing="trailing",
+                           rescale_betas_zero_snr=True, snr_shift_scale=1.0)
+
+
 class CogVideoXDPMScheduler:
     order = 1
 
     def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.00085, beta_end: float = 0.0120,
                  beta_schedule: str = "scaled_linear", trained_betas=None, clip_sample: bool = True,
-                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "v_prediction",
-                 clip_sample_range: float = 1.0, sample_max_value: float = 1.0, timestep_spacing: str = "trailing",
-                 rescale_betas_zero_snr: bool = True, snr_shift_scale: float = 1.0):
+                 set_alpha_to_one: bool = True, steps_offset: int = 0, prediction_type: str = "epsilon",
+                 clip_sample_range: float = 1.0, sample_max_value: float = 1.0, timestep_spacing: str = "leading",
+                 rescale_betas_zero_snr: bool = False, snr_shift_scale: float = 3.0):
+        """Defaults are the reference's own (scheduling_dpm_cogvideox.py:181-197), so a partial scheduler_config.json means
+        the same schedule here as there; the CogVideoX-5b checkpoint's values are `COGVIDEOX_5B_CONFIG` / `.cogvideox_5b()`."""
         cfg = {k: v for k, v in locals().items() if k != "self"}
         self.config = SimpleNamespace(**cfg)
         if prediction_type != "v_prediction":
-            raise NotImplementedError("CogVideoX-5b uses v_prediction; other prediction types are not on this path")
+            raise NotImplementedError("the CogVideoX-5b path steps with prediction_type='v_prediction' (scheduler_config.json); "
+                                      f"got {prediction_type!r} — pass the checkpoint's scheduler config or use .cogvideox_5b()")
         if trained_betas is not None:
             self.betas = torch.tensor(trained_betas, dtype=torch.float32)
         elif beta_schedule == "linear":
@@ -54,13 +65,23 @@ class CogVideoXDPMScheduler:
         self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
 
     @classmethod
+    def cogvideox_5b(cls, **overrides):
+        """The scheduler of the CogVideoX-5b checkpoint as the CLI configures it (trailing spacing)."""
+        return cls(**{**COGVIDEOX_5B_CONFIG, **overrides})
+
+    @classmethod
     def from_config(cls, config=None, **overrides):
         """`CogVideoXDPMScheduler.from_config(pipe.scheduler.config, timestep_spacing="trailing")`
-        (infer_cogvideo_mp_fifo.py:177-178): a dict / namespace of constructor arguments, unknown keys dropped."""
+        (infer_cogvideo_mp_fifo.py:177-178): a dict / namespace of constructor arguments.  Missing keys take the REFERENCE's
+        defaults; keys this class does not know are dropped only if they are diffusers bookkeeping (`_class_name`, ...) —
+        anything else is an error rather than a silently different schedule."""
         import inspect
         cfg = dict(vars(config)) if hasattr(config, "__dict__") and not isinstance(config, dict) else dict(config or {})
         cfg.update(overrides)
         names = set(inspect.signature(cls.__init__).parameters) - {"self"}
+        unknown = [k for k in cfg if k not in names and not k.startswith("_")]
+        if unknown:
+            raise ValueError(f"CogVideoXDPMScheduler.from_config: unknown keys {unknown}")
         return cls(**{k: v for k, v in cfg.items() if k in names})
 
     # ------------------------------------------------------------------ reference API

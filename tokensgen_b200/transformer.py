@@ -557,13 +557,19 @@ class CogVideoXTransformer3DModel(nn.Module):
     def enable_sequence_parallel(self, group=None) -> None:
         """Runs every later forward sequence-parallel (Ulysses) over `group` (default: all ranks): all ranks must call
         forward with identical inputs and all get the full output.  See tokensgen_b200/seqpar.py."""
+        import torch.distributed as dist
         from .seqpar import SeqParallel
-        self.__dict__["_tg_sp"] = SeqParallel(group)
-        self._tg_bufs.clear()
+        # one SeqParallel (and, below, one set of peer-mapped workspaces per geometry) per group for the life of the model:
+        # the pipelines switch this on and off around every base stage, and a symmetric-memory segment + rendezvous per
+        # video would never be freed
+        cache = self.__dict__.setdefault("_tg_sp_cache", {})
+        g = group if group is not None else dist.group.WORLD
+        if g not in cache:
+            cache[g] = SeqParallel(group)
+        self.__dict__["_tg_sp"] = cache[g]
 
     def disable_sequence_parallel(self) -> None:
         self.__dict__.pop("_tg_sp", None)
-        self._tg_bufs.clear()
 
     def save_vip_layers(self, vip_ckpt_dir=None):
         assert self.use_vip
@@ -625,16 +631,24 @@ class CogVideoXTransformer3DModel(nn.Module):
 
         rowmap = E.make_rowmap(n_text, n_video, n_vip, n_video // frames, frames)
         sp = self.__dict__.get("_tg_sp")
-        key = (B, n_text, n_video, n_vip, str(dev), sp is not None)
-        if key not in self._tg_bufs:
-            self._tg_bufs.clear()
-            ff_dim = self.transformer_blocks[0].ff.net[0].proj.out_features
-            if sp is None:
+        # `frames` is part of the key: the sharded workspaces freeze their rowmap (frames / hw decide which AdaLN row a video
+        # row reads), so a per-frame-timestep forward must never reuse the buffers of a per-sample one
+        key = (B, n_text, n_video, n_vip, frames, str(dev))
+        ff_dim = self.transformer_blocks[0].ff.net[0].proj.out_features
+        if sp is None:
+            if key not in self._tg_bufs:
+                self._tg_bufs.clear()
                 self._tg_bufs[key] = _Buffers(B, rowmap, d, cfg.num_attention_heads, ff_dim, use_vip, dev)
-            else:
-                from .seqpar import ShardedBuffers
-                self._tg_bufs[key] = ShardedBuffers(sp, B, rowmap, d, cfg.num_attention_heads, ff_dim, use_vip, dev)
-        bufs = self._tg_bufs[key]
+            bufs = self._tg_bufs[key]
+        else:
+            from .seqpar import ShardedBuffers
+            spc = self.__dict__.setdefault("_tg_bufs_sp", {})
+            skey = key + (id(sp),)
+            if skey not in spc:
+                while len(spc) >= 2:          # base stage + T2To geometries; older ones are dropped
+                    spc.pop(next(iter(spc)))
+                spc[skey] = ShardedBuffers(sp, B, rowmap, d, cfg.num_attention_heads, ff_dim, use_vip, dev)
+            bufs = spc[skey]
         x_full = bufs.X if sp is None else bufs.Xfull  # sequence parallel: every rank embeds all rows, keeps its shard
 
         # 2. patch embedding (K9) straight into the resident stream [text | video | vip]

@@ -7,14 +7,16 @@ import torch
 
 
 def _center_crop_resize(frames: torch.Tensor, out_hw) -> torch.Tensor:
-    """resize_for_rectangle_crop(..., reshape_mode="center"): scale so the clip covers the target, then centre crop."""
+    """resize_for_rectangle_crop(..., reshape_mode="center") (longvgen/data/utils.py:112-141): scale so the clip covers the
+    target — BICUBIC, the resized side TRUNCATED with int() exactly as the reference computes it, antialiased as
+    torchvision's tensor `resize` does (0.19: antialias defaults to True; float tensors are not clamped) — then centre crop."""
     th, tw = out_hw
     _, _, h, w = frames.shape
     if w / h > tw / th:
-        nh, nw = th, int(round(w * th / h))
+        nh, nw = th, int(w * th / h)
     else:
-        nh, nw = int(round(h * tw / w)), tw
-    frames = torch.nn.functional.interpolate(frames, size=(nh, nw), mode="bilinear", align_corners=False, antialias=True)
+        nh, nw = int(h * tw / w), tw
+    frames = torch.nn.functional.interpolate(frames, size=(nh, nw), mode="bicubic", align_corners=False, antialias=True)
     top, left = (nh - th) // 2, (nw - tw) // 2
     return frames[:, :, top:top + th, left:left + tw]
 
@@ -41,6 +43,10 @@ def load_video(video_path, output_res, nf_per_chunk, pad_to_fit, sample_fps, sta
             frames[pos] = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
         pos += 1
     cap.release()
+    missing = [i for i in idx.tolist() if i not in frames]
+    if missing:
+        raise IOError(f"{video_path}: the decoder ended at frame {pos} but frame {missing[0]} was requested "
+                      f"(container reports {total} frames at {fps:.3f} fps)")
     video = torch.from_numpy(np.stack([frames[i] for i in idx.tolist()])).float().permute(0, 3, 1, 2)   # f c h w
     if crop_to_fit:
         px = _center_crop_resize(video / 255.0, tuple(output_res)) * 2 - 1

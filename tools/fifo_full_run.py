@@ -32,7 +32,7 @@ if world > 1:
 E.load()
 nf, T = 13, 52
 model = build_random_model(device=dev, seed=0)          # same weights on every rank (as after loading one checkpoint)
-sch = CogVideoXDPMScheduler()
+sch = CogVideoXDPMScheduler.cogvideox_5b()
 sch.set_timesteps(T)
 g = torch.Generator(device=dev).manual_seed(1)
 mk = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.bfloat16)
