@@ -3,8 +3,12 @@
 tokensgen_b200 mirrors.  Same flag (`--config <yaml>`), same yaml schema (config/infer/{edit,gen}.yaml), same outputs
 (`<name>_{source,embeds,orig,fifo}_<prompt[:20]>` under `<output_dir>/<prefix>_<timestamp>/`).
 
-    python infer_cogvideo_mp_fifo.py --config config/infer/edit.yaml                              # one GPU
-    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 infer_cogvideo_mp_fifo.py --config ...     # one process per GPU
+    python infer_cogvideo_mp_fifo.py --config config/infer/edit.yaml     # every GPU in CUDA_VISIBLE_DEVICES, like the reference
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 infer_cogvideo_mp_fifo.py --config ...     # or under a launcher
+
+The plain `python` command is the reference's invocation (its infer_cogvideo_mp_fifo.py:191 takes the GPU list from
+CUDA_VISIBLE_DEVICES and :384-389 runs main() once): with more than one visible GPU and no launcher environment it starts
+one rank per GPU itself (`launch_plan` / `torch.multiprocessing.spawn`, 127.0.0.1 rendezvous).
 
 Process model: the reference builds one pipeline per visible GPU inside one process and spawns a worker per GPU for every
 video; here every GPU runs this script as a persistent rank (torchrun), loads its own copy of the weights in parallel,
@@ -94,7 +98,7 @@ def main(args):
         tokens_transformer = CogVideoXTransformer3DModel.from_pretrained(args.pretrained_2nd_stage_model_name_or_path,
                                                                          subfolder="transformer", torch_dtype=dtype, device=device)
         pipe_2nd = LongVGenCogVideoXPipeline.from_pretrained(args.pretrained_model_name_or_path, transformer=tokens_transformer,
-                                                             torch_dtype=dtype, vae=pipe.vae, text_encoder=pipe.text_encoder,
+                                                             torch_dtype=dtype, text_encoder=pipe.text_encoder,
                                                              tokenizer=pipe.tokenizer)
         pipe_2nd.scheduler = CogVideoXDPMScheduler.from_config(pipe_2nd.scheduler.config, timestep_spacing="trailing")
         pipe_2nd.to(device)
@@ -164,7 +168,8 @@ def main(args):
             base_outputs.condition_frames = None      # not needed by the FIFO stage; keeps the broadcast small
         else:
             pipe.preprare_for_fifo(**call)
-        base_outputs = broadcast_base_output(base_outputs, src=0, device=device)
+        if not seq_par:     # sequence-parallel: every rank ran the base stage and already holds the identical bundle
+            base_outputs = broadcast_base_output(base_outputs, src=0, device=device)
         # `fifo_checkpoint_dir` / `fifo_checkpoint_every` (schema extension): the FIFO stage saves its queue every N iterations
         # and a restarted job resumes from the newest state (the deterministic base stage is simply recomputed)
         ck = args.get("fifo_checkpoint_dir")
@@ -184,7 +189,32 @@ def main(args):
         dist.destroy_process_group()
 
 
+def launch_plan(env, visible_gpus: int) -> int:
+    """How many ranks this command must start itself: 0 = run main() in this process (one GPU, an existing launcher
+    environment, or TG_SINGLE_PROCESS=1), else one rank per visible GPU (TG_NPROC caps it)."""
+    if "WORLD_SIZE" in env or "RANK" in env or env.get("TG_SINGLE_PROCESS", "0") == "1":
+        return 0
+    n = min(visible_gpus, int(env.get("TG_NPROC", visible_gpus)))
+    return n if n > 1 else 0
+
+
+def _rank_entry(rank: int, world: int, port: int, config_path: str):
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    main(cfgmod.load(config_path))
+
+
 if __name__ == "__main__":
     parser = argparse.ArgumentParser()
     parser.add_argument("--config", type=str, default="./config/infer/edit.yaml")
-    main(cfgmod.load(parser.parse_args().config))
+    cli = parser.parse_args()
+    nproc = launch_plan(os.environ, torch.cuda.device_count())   # device_count honours CUDA_VISIBLE_DEVICES (reference :191)
+    if nproc:
+        import socket
+        import torch.multiprocessing as mp
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        print(f"Running on gpus: {list(range(nproc))}")
+        mp.spawn(_rank_entry, args=(nproc, port, cli.config), nprocs=nproc, join=True)   # start method "spawn", like the reference
+    else:
+        main(cfgmod.load(cli.config))

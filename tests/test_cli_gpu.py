@@ -96,9 +96,18 @@ def test_cli_two_ranks_writes_the_same_videos_as_one_rank(tmp_path, mode):
     r = subprocess.run([sys.executable, cli, "--config", os.path.join(roots[0], yaml_name)], cwd=ROOT, env=env1,
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-                        "127.0.0.1", "--master-port", "29547", cli, "--config", os.path.join(roots[1], yaml_name)],
-                       cwd=ROOT, capture_output=True, text=True, timeout=600)
+    if mode == "cfg_parallel":
+        # the REFERENCE's invocation: one plain `python` command, GPUs from CUDA_VISIBLE_DEVICES (its :191,:384-389) — the
+        # CLI starts one rank per visible GPU itself (launch_plan)
+        two = ",".join((os.environ.get("CUDA_VISIBLE_DEVICES") or "0,1").split(",")[:2])
+        env2 = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+        r = subprocess.run([sys.executable, cli, "--config", os.path.join(roots[1], yaml_name)], cwd=ROOT,
+                           env=dict(env2, CUDA_VISIBLE_DEVICES=two), capture_output=True, text=True, timeout=600)
+        assert "Running on gpus: [0, 1]" in r.stdout
+    else:
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                            "127.0.0.1", "--master-port", "29547", cli, "--config", os.path.join(roots[1], yaml_name)],
+                           cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     for kind in ("orig", "fifo"):
         a, b = (_all_frames(glob.glob(os.path.join(r_, "outputs", "tiny*", f"clip1_{kind}_*.mp4"))[0]) for r_ in roots)
