@@ -101,50 +101,10 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_block_seconds(repeats: int, warmup: int):
-    """The reference's algorithm on the host cores: ONE CogVideoX-5b block + VIP at full size (B = 1, 17 550 video + 226
-    text + 480 vip tokens) through the oracle port (PyTorch CPU eager, bf16 like the reference), all cores."""
-    from oracle import dit as odit
+# ------------------------------------------------------------------------------------------------------ reference block
+def _block_inputs(dev):
+    """one CogVideoX-5b block + VIP at full size, B = 1, 17 550 video + 226 text + 480 vip tokens."""
     from oracle import rope as orope
-    from oracle.synth import dit_shapes, synth_state_dict
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    shapes = {k: v for k, v in dit_shapes(48, 64, 1, 512, 4096, 16, 16, 2, 3072, True).items()
-              if k.startswith("transformer_blocks.0.")}
-    sd = synth_state_dict(shapes, 77)
-    g = torch.Generator().manual_seed(42)
-    hid = torch.randn(1, TOKENS, 3072, generator=g).bfloat16()
-    enc = torch.randn(1, 706, 3072, generator=g).bfloat16()
-    temb = torch.randn(1, 13, 512, generator=g).bfloat16()
-    rope = orope.window_rope(64, 13, 30, 45)
-    img = orope.rope_3d_from_grids(64, np.arange(13, dtype=np.float32), np.arange(30, dtype=np.float32), np.arange(45, dtype=np.float32))
-    cond = orope.rope_3d_from_grids(64, np.array([1000, 1003.25, 1006.5, 1009.75, 1013], dtype=np.float32),
-                                    np.linspace(0, 30, 8, endpoint=False, dtype=np.float32),
-                                    np.linspace(0, 45, 12, endpoint=False, dtype=np.float32))
-    cfg = odit.DitConfig()
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + repeats):
-            t0 = time.perf_counter()
-            odit.block_forward(sd, "transformer_blocks.0", cfg, hid, enc, temb, rope, img, cond, torch.bfloat16)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    return times, cores
-
-
-def eager_block_seconds(device, repeats: int = 5, warmup: int = 2):
-    """Second baseline: the reference's op sequence in PyTorch eager ON THE GPU — the oracle port
-    executes the same torch ops the reference modules do (18 cuBLAS Linears, three SDPA calls, unfused LayerNorm / modulation
-    / RoPE / cat / gated residual) — for ONE CogVideoX-5b block + VIP at full size (B = 1), bf16.  Not the product path."""
-    from oracle import dit as odit
-    from oracle import rope as orope
-    from oracle.synth import dit_shapes, synth_state_dict
-    dev = torch.device(device)
-    shapes = {k: v for k, v in dit_shapes(48, 64, 1, 512, 4096, 16, 16, 2, 3072, True).items()
-              if k.startswith("transformer_blocks.0.")}
-    sd = {k: v.to(dev, torch.bfloat16) for k, v in synth_state_dict(shapes, 77).items()}
     g = torch.Generator().manual_seed(42)
     hid = torch.randn(1, TOKENS, 3072, generator=g).bfloat16().to(dev)
     enc = torch.randn(1, 706, 3072, generator=g).bfloat16().to(dev)
@@ -156,18 +116,72 @@ def eager_block_seconds(device, repeats: int = 5, warmup: int = 2):
     cond = on(orope.rope_3d_from_grids(64, np.array([1000, 1003.25, 1006.5, 1009.75, 1013], dtype=np.float32),
                                        np.linspace(0, 30, 8, endpoint=False, dtype=np.float32),
                                        np.linspace(0, 45, 12, endpoint=False, dtype=np.float32)))
+    return hid, enc, temb, rope, img, cond
+
+
+def reference_block_runner(device):
+    """A callable running ONE forward of the reference's CogVideoXBlock + video-IP-adapter (func_type "1") at full size in bf16
+    on `device`, and which implementation it is:
+      "reference" — the reference's OWN module (cogvideox_transformer_3d.py:54-332 + attention_processor.py:1955-2155),
+                    unmodified, from baseline/_ref (built by oracle/vendor_reference.py; imports through the stubs);
+      "port"      — the oracle restatement (oracle/dit.py::block_forward), only when baseline/_ref is absent.
+    Both get the same seeded weights (oracle.synth.synth_state_dict(shapes, 77)) and inputs."""
+    from oracle import vendor_reference as vr
+    from oracle.synth import dit_shapes, synth_state_dict
+    dev = torch.device(device)
+    shapes = {k: v for k, v in dit_shapes(48, 64, 1, 512, 4096, 16, 16, 2, 3072, True).items()
+              if k.startswith("transformer_blocks.0.")}
+    sd = synth_state_dict(shapes, 77)
+    hid, enc, temb, rope, img, cond = _block_inputs(dev)
+    if vr.enable():
+        from longvgen.models.cogvideox_transformer_3d import CogVideoXBlock
+        blk = CogVideoXBlock(dim=3072, num_attention_heads=48, attention_head_dim=64, time_embed_dim=512, attention_bias=True)
+        blk.set_vip_layers(length=480, func_type="1", scale=[0.6])
+        missing = blk.load_state_dict({k[len("transformer_blocks.0."):]: v for k, v in sd.items()}, strict=True)
+        blk = blk.to(dev, torch.bfloat16).eval()
+
+        def run():
+            return blk(hid, enc, temb, image_rotary_emb=rope, vip_image_rotary_emb=img, vip_condition_rotary_emb=cond)
+        return run, "reference"
+    from oracle import dit as odit
+    sd = {k: v.to(dev, torch.bfloat16) for k, v in sd.items()}
     cfg = odit.DitConfig()
-    sync = torch.cuda.synchronize if dev.type == "cuda" else (lambda: None)
+
+    def run_port():
+        return odit.block_forward(sd, "transformer_blocks.0", cfg, hid, enc, temb, rope, img, cond, torch.bfloat16)
+    return run_port, "port"
+
+
+def cpu_block_seconds(repeats: int, warmup: int):
+    """The reference's CPU implementation of the path on the host cores: ONE block forward per sample, all cores."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    run, kind = reference_block_runner("cpu")
     times = []
     with torch.no_grad():
         for i in range(warmup + repeats):
-            sync()
             t0 = time.perf_counter()
-            odit.block_forward(sd, "transformer_blocks.0", cfg, hid, enc, temb, rope, img, cond, torch.bfloat16)
-            sync()
+            run()
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, cores, kind
+
+
+def eager_block_seconds(device, repeats: int = 5, warmup: int = 2):
+    """Second baseline: the same reference block in PyTorch eager ON THE GPU (cuBLAS Linears, three
+    SDPA-flash calls, unfused LayerNorm / modulation / RoPE / cat / gated residual), bf16.  Not the product path."""
+    run, kind = reference_block_runner(device)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run()
+            torch.cuda.synchronize()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
-    return float(np.median(times))
+    return float(np.median(times)), kind
 
 
 def cpu_tokens_per_s(block_seconds: float) -> float:
@@ -175,24 +189,94 @@ def cpu_tokens_per_s(block_seconds: float) -> float:
     return TOKENS / (DENOISE_STEPS * 42 * 2 * block_seconds)
 
 
+def make_config(world: int, value: float, ms_step: float):
+    """`config` of the JSON line — the same keys on both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "denoise_steps_per_clip": DENOISE_STEPS, "token_steps_per_s": value * DENOISE_STEPS,
+            "model_tflops_per_step": 775.9, "achieved_model_tflops": 775.9 / (ms_step / 1e3),
+            "l2": "inputs larger than L2: 14.3 GB of weights + 3 GB of activations stream through every step",
+            "parallelism": f"window-parallel x{world}" + (" + NCCL boundary-frame exchange" if world > 1 else "")}
+
+
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores.  One STEP of this arm
+    is a bounded SAMPLE of a bench step — one of its 42 x 2 block forwards (a whole step is ~2.5 min of CPU): `ms_per_step`
+    is the measured time of that sample, `value` the metric it implies for the whole step (x 84), `sample_fraction` says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    times, cores = cpu_block_seconds(args.steps, args.warmup)
+    times, cores, kind = cpu_block_seconds(args.steps, args.warmup)
     sec = float(np.mean(times))
     val = cpu_tokens_per_s(sec)
-    sample = (f"{args.steps} timed + {args.warmup} warm-up forwards of ONE CogVideoX-5b block + VIP at full size (B=1) through the "
-              f"oracle port (PyTorch CPU eager bf16); a step = 42 blocks x 2 CFG branches, extrapolated")
+    what = ("the reference's own CogVideoXBlock + VideoIPAdapterCogVideoXAttnProcessor2_0 (unmodified, baseline/_ref)" if kind == "reference"
+            else "the oracle port of the reference block (baseline/_ref absent)")
+    sample = (f"{args.steps} timed + {args.warmup} warm-up forwards of ONE CogVideoX-5b block + VIP at full size (B=1), {what}, PyTorch "
+              f"CPU eager bf16, {cores} threads; a bench step = 42 blocks x 2 CFG branches = 84 such samples")
     line = {"impl": "reference", "metric": "denoised latent tokens/sec", "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 84 * 1e3, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "denoise_steps_per_clip": DENOISE_STEPS},
-            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": make_config(1, val, sec * 84 * 1e3),
+            "sample_fraction": 1.0 / 84, "ms_per_whole_step_extrapolated": sec * 84 * 1e3,
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
+
+
+# ------------------------------------------------------------------------------------------------------ real FIFO stage
+def fifo_schedule_stats(chunks: int, world: int):
+    """Pure index arithmetic of the FIFO stage of a `chunks`-chunk video (gen.yaml: 24): iterations, window forwards, the
+    rounds a P-rank job needs (max windows on one rank, per iteration) and the speed-up bound that follows."""
+    from tokensgen_b200.fifo import FifoSchedule
+    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+    sch = CogVideoXDPMScheduler.cogvideox_5b()
+    sch.set_timesteps(DENOISE_STEPS)
+    s = FifoSchedule(chunks * 13, [int(t) for t in sch.timesteps], 13, 4, True)
+    wins = [s.windows(i) for i in range(s.num_iterations)]
+    forwards = sum(len(w) for w in wins)
+    rounds = sum(max(sum(1 for x in w if x.rank % world == r) for r in range(world)) for w in wins)
+    ramp = sum(1 for w in wins if len(w) < 8)
+    return {"iterations": s.num_iterations, "window_forwards": forwards, "rounds": rounds, "ramp_iterations": ramp,
+            "schedule_bound_speedup": forwards / rounds}
+
+
+def run_fifo_stage(model, sch, dev, world, rank, chunks: int, barrier):
+    """BASELINE.json configs[2]/[3] for real: the FIFO stage of a `chunks`-chunk gen.yaml video (CogVideoX-5b shapes, 52-step
+    diagonal queue, 13 x 30 x 45 windows, CFG pair, video-IP-adapter, lookahead write-back) through the product's own
+    `cogvideo_fifo_mp_v2` controller — window rank w on process w % P, NCCL boundary-frame exchange every iteration.  The
+    priming bundle is synthetic (random latents / embeddings of the true shapes).  Timed on the device, max over ranks."""
+    import torch.distributed as dist
+    from types import SimpleNamespace
+    from tokensgen_b200.fifo import cogvideo_fifo_mp_v2
+    from tokensgen_b200.pipeline import FIFOCogVideoXPipelineOutput
+    from tokensgen_b200.rope import get_3d_rotary_pos_embed, vip_position_grids
+    nf, T = 13, DENOISE_STEPS
+    g = torch.Generator(device=dev).manual_seed(1)
+    mk = lambda *s_: torch.randn(*s_, generator=g, device=dev, dtype=torch.bfloat16)
+    img_grid, cond_grid = vip_position_grids(60, 90, 2, chunks, nf, 4, 8, 12, 1000)
+    base = FIFOCogVideoXPipelineOutput(
+        fifo_latents=mk(1, T, 16, 60, 90), fifo_old_pred_original_sample=[mk(1, 1, 16, 60, 90) for _ in range(T - 1)] + [None],
+        orig_latents=mk(1, nf, 16, 60, 90), nf_per_chunk=nf, vip_nf_per_chunk=4, num_frames=chunks * nf,
+        image_embeddings=mk(2, 4 * (chunks + 1), 3072, 8, 12), timesteps=sch.timesteps, num_inference_steps=T,
+        do_classifier_free_guidance=True, use_separate_guidance=False, use_dynamic_cfg=False, prompt_embeds=mk(2, 226, 4096),
+        image_rotary_emb=get_3d_rotary_pos_embed(64, [[0, 0, 0], [nf, 30, 45]], (nf, 30, 45), device=dev),
+        vip_image_rotary_grid=list(img_grid), vip_condition_rotary_grid=list(cond_grid), cache_idx=[], guidance_scale=6.0,
+        guidance_scale_img=6.0, extra_step_kwargs={}, video_ipadapter_start_frame_idx=1000, sampling_params={"num_partitions": 4},
+        output_type="latent", return_dict=False)
+    pipe = SimpleNamespace(transformer=model, scheduler=sch)
+    barrier()
+    s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_ev.record()
+    with torch.no_grad():
+        _, latents, _ = cogvideo_fifo_mp_v2([pipe], base, seed=7)
+    e_ev.record()
+    barrier()
+    ms = s_ev.elapsed_time(e_ev)
+    if world > 1:
+        tt = torch.tensor([ms], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = tt.item()
+    return ms / 1e3, int(latents.shape[1]), bool(torch.isfinite(latents.float()).all())
 
 # ------------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
@@ -341,6 +425,30 @@ def run_ours(args):
             seqpar = {"what": "one window step (DiT forward CFG pair + DPM step) sharded over all ranks: strong scaling of a single clip",
                       "ranks": world, "ms_per_step": ms_sp, "bit_identical_to_unsharded": same}
 
+        # N > 1: the REAL FIFO stage (configs[2]/[3]) through the controller — ramp-up (fewer active windows than GPUs for the
+        # first 40 iterations), steady state, boundary exchange, emit / shift / re-noise — on a short video
+        fifo = None
+        if world > 1 and not args.no_fifo_stage:
+            chunks = args.fifo_chunks
+            est = lambda c: fifo_schedule_stats(c, world)["rounds"] * (ms_total / args.steps) / 1e3
+            while chunks > 1 and est(chunks) > args.fifo_budget_s:
+                chunks -= 1
+            wall, emitted, finite = run_fifo_stage(model, sch, dev, world, rank, chunks, barrier)
+            st = fifo_schedule_stats(chunks, world)
+            one_gpu = st["window_forwards"] * (ms_total / args.steps) / 1e3
+            gen = fifo_schedule_stats(24, world)
+            fifo = {"what": f"FIFO stage of a {chunks}-chunk gen.yaml video ({chunks * 13} latent frames = {chunks * 49} video frames of "
+                            "480x720) through cogvideo_fifo_mp_v2: real controller, NCCL boundary exchange, device-timed, max over ranks",
+                    "chunks": chunks, **st, "wall_s": wall, "emitted_latent_frames": emitted, "latents_finite": finite,
+                    "emitted_tokens_per_s": 1350 * emitted / wall, "s_per_round": wall / st["rounds"],
+                    "one_gpu_counterpart_s": one_gpu,
+                    "one_gpu_counterpart_is": "window_forwards x this run's measured single-window step time (one GPU runs the windows "
+                                              "of an iteration back to back); profiles/ holds a measured 1-GPU run of the same stage",
+                    "speedup_vs_one_gpu": one_gpu / wall, "efficiency_vs_schedule_bound": (one_gpu / wall) / st["schedule_bound_speedup"],
+                    "gen_yaml_24_chunks": {**gen, "projected_wall_s": gen["rounds"] * wall / st["rounds"],
+                                           "projected_speedup_vs_one_gpu": gen["window_forwards"] / gen["rounds"] * (one_gpu / wall)
+                                           / st["schedule_bound_speedup"]}}
+
     if rank == 0:
         hbm, tf_burst, tf_sust, src = measured_peaks()
         per = {k: sum(s.elapsed_time(e) for s, e in v) / args.steps for k, v in prof.items()}  # ms per step per op tag
@@ -358,10 +466,7 @@ def run_ours(args):
         line = {"metric": "denoised latent tokens/sec", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "denoise_steps_per_clip": DENOISE_STEPS, "token_steps_per_s": value * DENOISE_STEPS,
-                           "model_tflops_per_step": 775.9, "achieved_model_tflops": 775.9 / (ms_step / 1e3) ,
-                           "l2": "inputs larger than L2: 14.3 GB of weights + 3 GB of activations stream through every step",
-                           "parallelism": f"window-parallel x{world}" + (" + NCCL boundary-frame exchange" if world > 1 else "")},
+                "config": make_config(world, value, ms_step),
                 "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": launches,
@@ -377,23 +482,52 @@ def run_ours(args):
         if seqpar is not None:
             seqpar["speedup_vs_this_runs_1gpu_step"] = ms_step / seqpar["ms_per_step"]
             line["sequence_parallel"] = seqpar
+        if fifo is not None:
+            line["fifo_stage"] = fifo
+        line["value_definition"] = ("17 550 tokens x steps / (52 x seconds): every window step advances 13 latent frames by one of the 52 "
+                                    "denoise levels (the To2V base stage, configs[1]); in the FIFO stage a window step FINALISES only its "
+                                    "second half (lookahead), so emitted tokens/s there is fifo_stage.emitted_tokens_per_s (N > 1 lines)")
         if world == 1 and not args.no_eager_baseline:
             # reported next to the CPU baseline, never on the product path; a failure here must not cost the bench line
             try:
-                sec = eager_block_seconds(dev)
+                sec, kind = eager_block_seconds(dev)
                 line["gpu_eager_baseline"] = {
-                    "what": "the reference's op sequence in PyTorch eager on this GPU (oracle port: cuBLAS Linears + SDPA + unfused "
-                            "elementwise), ONE CogVideoX-5b block + VIP at full size, B = 1, bf16; a step = 42 blocks x 2 CFG branches",
-                    "block_ms": sec * 1e3, "value": cpu_tokens_per_s(sec), "unit": "tokens/s",
+                    "what": "the reference block in PyTorch eager on this GPU (cuBLAS Linears + SDPA-flash + unfused elementwise), ONE "
+                            "CogVideoX-5b block + VIP at full size, B = 1, bf16; a step = 42 blocks x 2 CFG branches",
+                    "kind": kind, "block_ms": sec * 1e3, "value": cpu_tokens_per_s(sec), "unit": "tokens/s",
                     "ours_over_eager": value / cpu_tokens_per_s(sec)}
             except Exception as e:  # noqa: BLE001
                 line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if world == 1 and not args.no_vae:
+            # configs[4] + the VAE bookends of configs[1]: full-size CogVideoX VAE, random-init weights, this GPU (guarded like the
+            # eager baseline: a failure is recorded, not raised)
+            try:
+                del model
+                torch.cuda.empty_cache()
+                from tools import vae_bench as vb
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+                vae = vb.build_vae()
+                pts = [vb.point(vae, "decode", 13, False, peaks), vb.point(vae, "decode", 13, True, peaks),
+                       vb.point(vae, "encode", 49, False, peaks), vb.point(vae, "encode", 49, True, peaks)]
+                sweep = [vb.point(vae, "decode", T, False, peaks) for T in args.vae_sweep]
+                line["vae"] = {"what": "3D causal VAE, full CogVideoX-5b widths (128,256,256,512), 480x720: decode of one 13-latent-frame "
+                                       "clip (49 frames) untiled and tiled 3x3 (the reference CLI's default), encode of 49 frames; "
+                                       "`sweep`: configs[4] decode of T latent frames as ONE causal stream",
+                               "points": pts, "sweep": [{k: p[k] for k in ("latent_frames", "pixel_frames", "ms", "pixel_frames_per_s",
+                                                                              "tflops_whole_pass", "frac_of_sustained_peak")} for p in sweep]}
+                del vae
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                line["vae"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_block_seconds(1, 1)
-            line["cpu_baseline"] = {"value": cpu_tokens_per_s(times[0]), "unit": "tokens/s", "cores": cores, "kind": "port",
-                                    "sample": "1 timed + 1 warm-up forward of ONE CogVideoX-5b block + VIP at full size (B=1) through "
-                                              "the oracle port (PyTorch CPU eager bf16), extrapolated x42 blocks x2 CFG branches",
-                                    "block_seconds": times[0]}
+            times, cores, kind = cpu_block_seconds(3, 1)
+            sec = float(np.median(times))
+            line["cpu_baseline"] = {"value": cpu_tokens_per_s(sec), "unit": "tokens/s", "cores": cores, "kind": kind,
+                                    "sample": "3 timed (median) + 1 warm-up forward of ONE CogVideoX-5b block + VIP at full size (B=1): "
+                                              + ("the reference's own module from baseline/_ref" if kind == "reference" else "the oracle port")
+                                              + ", PyTorch CPU eager bf16, all host threads; a step = 84 such forwards (42 blocks x 2 "
+                                                "CFG branches), extrapolated",
+                                    "block_seconds": sec}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -408,6 +542,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline block")
     ap.add_argument("--no-seqpar", action="store_true", help="N > 1: skip the extra sequence-parallel single-clip measurement")
+    ap.add_argument("--no-fifo-stage", action="store_true", help="N > 1: skip the real FIFO-stage run")
+    ap.add_argument("--fifo-chunks", type=int, default=3, help="N > 1: length of the FIFO-stage video in 13-frame chunks")
+    ap.add_argument("--fifo-budget-s", type=float, default=320.0, help="N > 1: shorten the FIFO video until it fits this many seconds")
+    ap.add_argument("--no-vae", action="store_true", help="N = 1: skip the VAE block")
+    ap.add_argument("--vae-sweep", type=int, nargs="*", default=[25, 49], help="N = 1: extra decode points (latent frames, one stream)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -51,7 +51,7 @@ def test_window_steps_teacher_forced_against_the_reference_worker(gold, model):
     sch.set_timesteps(c["geom"]["T"])
     rope = get_3d_rotary_pos_embed(64, [[0, 0, 0], [nf, gh, gw]], (nf, gh, gw), device=dev)
     tables = odpm.DpmTables()
-    worst_fwd, worst_step, n = 0.0, 0.0, 0
+    rows, n = [], 0
     for rec in gold["calls"]:
         if "lat_in" not in rec:
             continue
@@ -68,20 +68,23 @@ def test_window_steps_teacher_forced_against_the_reference_worker(gold, model):
         n1 = torch.cat([keyed_noise((it, s, j, 0), lat[:, [j]].shape) for j in range(nf)], dim=1)
         n2 = torch.cat([keyed_noise((it, s, j, 1), lat[:, [j]].shape) for j in range(nf)], dim=1)
         t, pt, nt = sched.t[s:e], sched.prev_t[s:e], sched.next_t[s:e]
-        # (a) the product's DiT prediction pushed through the reference's own CPU scheduler arithmetic: isolates the forward
-        out_a, x0_a = odpm.window_step_bf16(tables, npred.cpu(), c["guidance_scale"], rec["lat_in"], rec["old_in"], t, pt, nt,
-                                            n1, n2, device_semantics="cpu")
-        worst_fwd = max(worst_fwd, rel(out_a, rec["lat_out"]), rel(torch.cat(x0_a, 1), rec["x0_out"]))
-        # (b) the product's own fused step (CUDA scalar semantics, which differ from the CPU run's by a bf16 rounding of the
-        # coefficients — oracle/dpm.py::_smul)
         old = [None if o is None else o.to(dev) for o in rec["old_in"]]
-        out_b, x0_b = sch.window_step(npred, lat, old, t, pt, nt, c["guidance_scale"], noise=(n1.to(dev), n2.to(dev)))
-        worst_step = max(worst_step, rel(out_b, rec["lat_out"]), rel(torch.cat([x.reshape(1, 1, *lat.shape[2:]) for x in x0_b], 1),
-                                                                     rec["x0_out"]))
+        out, x0s = sch.window_step(npred, lat, old, t, pt, nt, c["guidance_scale"], noise=(n1.to(dev), n2.to(dev)))
+        x0 = torch.cat([x.reshape(1, 1, *lat.shape[2:]) for x in x0s], 1)
+        # yardstick: the reference worker re-run in fp32 on the same inputs (lat_out_f32 / x0_out_f32).  Classifier-free
+        # guidance (u + 6 (c - u)) amplifies the bf16 error of the two branches, so the reference's own bf16 run is 0.5-3.4e-2
+        # away from it depending on the noise level; the product path must sit in the same band, call by call.
+        ours = max(rel(out, rec["lat_out_f32"]), rel(x0, rec["x0_out_f32"]))
+        ref = max(rel(rec["lat_out"], rec["lat_out_f32"]), rel(rec["x0_out"], rec["x0_out_f32"]))
+        rows.append((it, s, ours, ref, max(rel(out, rec["lat_out"]), rel(x0, rec["x0_out"]))))
         n += 1
-    print(f"teacher-forced window steps ({n} calls): forward-only rel_l2 {worst_fwd:.3e}, fused step rel_l2 {worst_step:.3e}")
+    print(f"teacher-forced window steps ({n} calls), rel_l2 of (latents, x0) worst of the two:")
+    for it, s, ours, ref, vs_bf16 in rows:
+        print(f"  it {it:2d} start {s:2d}: CUDA vs reference fp32 {ours:.3e} | reference bf16 vs its fp32 {ref:.3e} | CUDA vs reference bf16 {vs_bf16:.3e}")
     assert n >= 10
-    assert worst_fwd < 1e-2 and worst_step < 1.5e-2
+    for it, s, ours, ref, vs_bf16 in rows:
+        assert ours < 1.25 * ref + 2e-3, (it, s, ours, ref)
+        assert vs_bf16 < 2.0 * ref + 2e-3, (it, s, vs_bf16, ref)
 
 
 def test_whole_stage_against_the_reference_sampler(gold, model):
@@ -126,4 +129,6 @@ def test_whole_stage_against_the_reference_sampler(gold, model):
     err = rel(video, gold["video"])
     per_frame = [rel(video[:, j], gold["video"][:, j]) for j in range(video.shape[1])]
     print(f"FIFO stage vs the reference sampler: final latents rel_l2 {err:.3e} (per frame {['%.2e' % e for e in per_frame]})")
-    assert err < 3e-2
+    # two bf16 runs of 12 guided denoise steps per frame: each is ~1-3e-2 from the fp32 trajectory per step (see the
+    # teacher-forced test); measured 2.3e-2 between them on B200
+    assert err < 4e-2

@@ -38,6 +38,9 @@ def _run(pipe, seed):
     frames = torch.rand(1, 18, 3, 64, 96, generator=g) * 2 - 1
     pe = torch.randn(1, 10, 128, generator=g)
     ne = torch.randn(1, 10, 128, generator=g)
+    # the conditioning clip's VAE posterior is sampled from the GLOBAL RNG in the reference (pipeline_cogvideox_mp_fifo.py:585), not
+    # from the call's generator: pin it here so that reruns are comparable
+    pipe.vae_posterior_generator = torch.Generator().manual_seed(1000 + seed)
     base = pipe(frames=frames, prompt_embeds=pe, negative_prompt_embeds=ne, height=64, width=96, num_frames_per_chunk=9,
                 max_num_chunks=2, max_num_chunks_w_fifo=25, max_num_chunks_wo_fifo=1, num_inference_steps=12, guidance_scale=6.0,
                 generator=torch.Generator().manual_seed(seed), vip_scale=[0.6], sampling_mode="fifo",

@@ -59,36 +59,59 @@ def run(fn, tiled):
     return ms, flops, out
 
 
+def build_vae(seed: int = 0):
+    torch.manual_seed(seed)
+    with torch.device("meta"):
+        vae = AutoencoderKLCogVideoX(scaling_factor=0.7)
+    vae = vae.to_empty(device="cuda").to(torch.bfloat16)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    with torch.no_grad():
+        for name, p in vae.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0.0, 0.02, generator=g)
+            elif name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.normal_(0.0, 0.02, generator=g)
+    return vae.eval()
+
+
+def point(vae, op: str, T: int, tiled: bool, peaks: dict, g=None):
+    """One measured point: op = "decode" (T latent frames of 60 x 90, ONE causal stream: frame batches 3, 2, 2, ... with the
+    conv cache carried, autoencoder_kl_cogvideox.py:1144-1157) or "encode" (T pixel frames of 480 x 720)."""
+    g = g or torch.Generator().manual_seed(42)
+    tf_peak, hbm_peak = peaks.get("bf16_tflops_sustained", 1400.0), peaks.get("hbm_gbs", 6650.0)
+    vae.enable_tiling() if tiled else vae.disable_tiling()
+    with torch.no_grad():
+        if op == "decode":
+            z = torch.randn(1, 16, T, 60, 90, generator=g).cuda().bfloat16()
+            ms, fl, per = run(lambda: vae.decode(z).sample, tiled)
+            px = (T - 1) * 4 + 1
+        else:
+            x = (torch.rand(1, 3, T, 480, 720, generator=g) * 2 - 1).cuda().bfloat16()
+            ms, fl, per = run(lambda: vae.encode(x).latent_dist.parameters, tiled)
+            px = T
+    vae.disable_tiling()
+    out = {"op": op, "tiled": tiled, "latent_frames": T if op == "decode" else (T - 1) // 4 + 1, "pixel_frames": px, "ms": round(ms, 1),
+           "pixel_frames_per_s": round(px / ms * 1e3, 1), "conv_tflop": round(fl / 1e12, 1),
+           "tflops_whole_pass": round(fl / ms / 1e9, 1), "frac_of_sustained_peak": round(fl / ms / 1e9 / tf_peak, 3),
+           "conv_kernel_tflops": round(fl / per.get("vae_conv", ms) / 1e9, 1),
+           "conv_kernel_frac_of_sustained_peak": round(fl / per.get("vae_conv", ms) / 1e9 / tf_peak, 3), "ms_by_op": per}
+    for name in ("vae_norm_act", "vae_group_stats"):
+        if name + "_GBps" in per:
+            out[name + "_frac_of_hbm_peak"] = round(per[name + "_GBps"] / hbm_peak, 3)
+    return out
+
+
 def main():
     frames = [int(a) for a in sys.argv[1:]] or [13, 25, 49]
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-    tf_peak = peaks.get("bf16_tflops_sustained", 1400.0)
-    torch.manual_seed(0)
-    vae = AutoencoderKLCogVideoX(scaling_factor=0.7)
-    for p in vae.parameters():
-        torch.nn.init.normal_(p, std=0.02)
-    vae = vae.to("cuda", torch.bfloat16).eval()
-    g = torch.Generator().manual_seed(42)
-    with torch.no_grad():
-        for tiled in (False, True):
-            vae.enable_tiling() if tiled else vae.disable_tiling()
-            for T in frames:
-                z = torch.randn(1, 16, T, 60, 90, generator=g).cuda().bfloat16()
-                ms, fl, per = run(lambda: vae.decode(z).sample, tiled)
-                px = (T - 1) * 4 + 1
-                print(json.dumps({"op": "decode", "tiled": tiled, "latent_frames": T, "pixel_frames": px, "ms": round(ms, 1),
-                                  "pixel_frames_per_s": round(px / ms * 1e3, 1), "conv_tflop": round(fl / 1e12, 1),
-                                  "tflops_whole_pass": round(fl / ms / 1e9, 1), "frac_of_sustained_peak": round(fl / ms / 1e9 / tf_peak, 3),
-                                  "conv_kernel_tflops": round(fl / per.get("vae_conv", ms) / 1e9, 1), "ms_by_op": per}), flush=True)
-                del z
-                if tiled:
-                    break
-        vae.disable_tiling()
-        x = (torch.rand(1, 3, 49, 480, 720, generator=g) * 2 - 1).cuda().bfloat16()
-        ms, fl, per = run(lambda: vae.encode(x).latent_dist.parameters, False)
-        print(json.dumps({"op": "encode", "tiled": False, "pixel_frames": 49, "ms": round(ms, 1), "conv_tflop": round(fl / 1e12, 1),
-                          "tflops_whole_pass": round(fl / ms / 1e9, 1), "conv_kernel_tflops": round(fl / per.get("vae_conv", ms) / 1e9, 1),
-                          "ms_by_op": per}), flush=True)
+    vae = build_vae()
+    for T in frames:
+        print(json.dumps(point(vae, "decode", T, False, peaks)), flush=True)
+    print(json.dumps(point(vae, "decode", 13, True, peaks)), flush=True)
+    print(json.dumps(point(vae, "encode", 49, False, peaks)), flush=True)
+    print(json.dumps(point(vae, "encode", 49, True, peaks)), flush=True)
 
 
 if __name__ == "__main__":
