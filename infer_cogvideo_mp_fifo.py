@@ -175,7 +175,10 @@ def main(args):
         ck = args.get("fifo_checkpoint_dir")
         orig_video_frames, video_frames, _ = cogvideo_fifo_mp_v2(
             pipe_list, base_outputs, seed=args.seed, checkpoint_dir=os.path.join(ck, name) if ck else None,
-            checkpoint_every=args.get("fifo_checkpoint_every", 10))
+            checkpoint_every=args.get("fifo_checkpoint_every", 10),
+            # `streaming_decode` (schema extension, default on): every 13-frame chunk is decoded on a side stream of rank
+            # chunk % P as soon as it has left the queue, instead of all chunks after the loop — same frames, no decode tail
+            streaming_decode=bool(args.get("streaming_decode", True)))
         if rank == 0:
             tag = prompt[:20]
             if video is not None:

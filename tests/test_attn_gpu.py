@@ -63,3 +63,92 @@ def test_attn_fwd_pair_equals_two_launches(n_tv, n_vip):
     ref = ref_attn(q, k, v) + scale2 * ref_attn(q2[:, :, :n_tv], k2[:, :, n_tv:], v2[:, :, n_tv:])
     assert rel_l2(b[:, :n_tv].float(), ref) < 5e-3
     assert torch.count_nonzero(b[:, n_tv:]) == 0   # rows beyond q_rows untouched
+
+
+# ------------------------------------------------------------------------------------------------ speculative reference + exact redo
+def _steep(B, H, nq, nkv, top, seed):
+    """Scores whose row max keeps climbing along kv by far more than 2^100: the speculative reference (block 0's row max)
+    overflows and the CTA must redo its passes with the exact running-max path."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    q = torch.randn(B, H, nq, 64, generator=g, device="cuda").bfloat16()
+    k = torch.randn(B, H, nkv, 64, generator=g, device="cuda")
+    k = (k * torch.linspace(0.05, top, nkv, device="cuda").view(1, 1, -1, 1)).bfloat16()
+    v = torch.randn(B, H, nkv, 64, generator=g, device="cuda").bfloat16()
+    return q, k, v
+
+
+@pytest.mark.parametrize("nq,nkv,top", [(300, 3000, 60.0), (700, 1500, 200.0), (129, 257, 500.0)])
+def test_speculative_reference_overflow_takes_the_exact_redo(nq, nkv, top):
+    """tg_attn_fwd with the speculative softmax reference on (default): rows whose later scores exceed block 0's max by
+    hundreds of log2 units are recomputed exactly inside the same launch — the result equals the exact mode's bit for bit
+    (same code path the second time) and the fp32 reference within the usual tolerance."""
+    from tokensgen_b200 import _ext as E
+    q, k, v = _steep(1, 2, nq, nkv, top, seed=nq)
+    ref = ref_attn(q, k, v)
+    outs = {}
+    try:
+        for spec in (1, 0):
+            E.set_tuning("attn_spec", spec)
+            out = torch.full((1, nq, 128), 7.0, device="cuda", dtype=torch.bfloat16)
+            E.attn_fwd(q, k, v, out)
+            torch.cuda.synchronize()
+            outs[spec] = out
+    finally:
+        E.set_tuning("attn_spec", 1)
+    assert torch.isfinite(outs[1].float()).all()
+    assert torch.equal(outs[1], outs[0])
+    assert rel_l2(outs[1].float(), ref) < 5e-3
+
+
+def test_speculative_redo_in_accumulate_and_pair_modes():
+    """The redo must not double-add: accumulate-mode launches and both passes of the fused pair store nothing until the CTA's
+    vote is clean, then run every pass again.  Overflow only in the SECOND problem of the pair (benign self-attention)."""
+    from tokensgen_b200 import _ext as E
+    B, H, n_tv, n_vip = 1, 2, 500, 300
+    rows = n_tv + n_vip
+    g = torch.Generator(device="cuda").manual_seed(77)
+    mk = lambda n: torch.randn(B, H, n, 64, generator=g, device="cuda").bfloat16()
+    q, k, v = mk(n_tv), mk(n_tv), mk(n_tv)
+    q2, v2 = mk(rows), mk(rows)
+    k2 = torch.randn(B, H, rows, 64, generator=g, device="cuda")
+    k2[:, :, n_tv:] *= torch.linspace(0.05, 300.0, n_vip, device="cuda").view(1, 1, -1, 1)
+    k2 = k2.bfloat16()
+    scale2 = 0.6015625
+    res = {}
+    try:
+        for spec in (1, 0):
+            E.set_tuning("attn_spec", spec)
+            a = torch.zeros(B, rows, H * 64, device="cuda", dtype=torch.bfloat16)
+            E.attn_fwd(q, k, v, a, out_row0=0)
+            E.attn_fwd(q2, k2, v2, a, q_row0=0, q_rows=n_tv, kv_row0=n_tv, kv_rows=n_vip, out_row0=0, accumulate=True, out_scale=scale2)
+            b = torch.zeros_like(a)
+            E.attn_fwd_pair(q, k, v, n_tv, n_tv, q2, k2, v2, n_tv, n_vip, b, scale2)
+            torch.cuda.synchronize()
+            res[spec] = (a, b)
+    finally:
+        E.set_tuning("attn_spec", 1)
+    ref = ref_attn(q, k, v) + scale2 * ref_attn(q2[:, :, :n_tv], k2[:, :, n_tv:], v2[:, :, n_tv:])
+    for spec in (1, 0):
+        a, b = res[spec]
+        assert torch.equal(a, b), spec
+        assert rel_l2(b[:, :n_tv].float(), ref) < 5e-3, spec
+    # pass 0 (benign) ran speculatively the first time and exactly in the redo: the two modes differ only by rounding there
+    assert rel_l2(res[1][1][:, :n_tv].float(), res[0][1][:, :n_tv].float()) < 5e-3
+
+
+def test_speculative_and_exact_modes_agree_on_ordinary_inputs():
+    from tokensgen_b200 import _ext as E
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q, k, v = (torch.randn(2, 4, 1000, 64, generator=g, device="cuda").bfloat16() for _ in range(3))
+    ref = ref_attn(q, k, v)
+    errs = {}
+    try:
+        for spec in (1, 0):
+            E.set_tuning("attn_spec", spec)
+            out = torch.zeros(2, 1000, 256, device="cuda", dtype=torch.bfloat16)
+            E.attn_fwd(q, k, v, out)
+            torch.cuda.synchronize()
+            errs[spec] = rel_l2(out.float(), ref)
+    finally:
+        E.set_tuning("attn_spec", 1)
+    assert errs[1] < 5e-3 and errs[0] < 5e-3 and abs(errs[1] - errs[0]) < 1e-3

@@ -288,3 +288,46 @@ def test_base_output_broadcast_ships_host_tensors_and_no_generator(tmp_path):
         assert torch.equal(r[k]["lat"], r[0]["lat"]) and torch.equal(r[k]["old0"], r[0]["old0"]) and r[k]["old1_is_none"]
         assert torch.equal(r[k]["rope1"], r[0]["rope1"]) and np.array_equal(r[k]["grid"], r[0]["grid"])
         assert r[k]["extra"] is None and r[k]["num_frames"] == 26 and r[k]["sp"] == {"a": 1}
+
+
+# ------------------------------------------------------------------------------------------------ streaming decode hand-off
+class _ToyPipe:
+    """decode_latents stand-in: a deterministic function of the chunk (each latent frame -> 4 'video' frames)."""
+
+    @staticmethod
+    def decode_latents(latents, nf):
+        x = latents.permute(0, 2, 1, 3, 4)                       # b c f h w
+        return torch.cat([x * (i + 1) for i in range(4)], dim=2).contiguous()
+
+
+def _stream_worker(rank, world, port, num_frames, out_dir):
+    from tokensgen_b200.fifo import StreamingDecoder
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sched = FifoSchedule(num_frames, _timesteps())
+        sd = StreamingDecoder(_ToyPipe(), 13, 52 - 13, rank, world)
+        em = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, rank=rank, world=world, on_emit=sd.on_emit)
+        video = sd.finish()
+        if rank == 0:
+            torch.save({"video": video, "latents": torch.cat(em[52 - 13:], dim=1), "ready_it": dict(sd.ready_it)},
+                       os.path.join(out_dir, "stream.pt"))
+        else:
+            assert video is None
+            assert sorted(sd.frames) == list(range(rank, num_frames // 13, world))      # this rank decoded exactly its chunks
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 3])
+def test_streaming_decode_hands_every_chunk_to_its_owner_as_soon_as_it_is_complete(tmp_path, world):
+    """chunk c is decoded in iteration (T - nf) + nf (c + 1) - 1 on rank c % P, and the assembled video equals
+    decoding the final latents after the loop (what cogvideo_sampling_mp_fifo.py:367-385 does)."""
+    num_frames = 5 * 13
+    port = 29500 + (os.getpid() % 2000) + 90 + world
+    mp.spawn(_stream_worker, args=(world, port, num_frames, str(tmp_path)), nprocs=world, join=True)
+    r = torch.load(tmp_path / "stream.pt", weights_only=False)
+    assert r["ready_it"] == {c: 39 + 13 * (c + 1) - 1 for c in range(5)}
+    after = torch.cat([_ToyPipe.decode_latents(r["latents"][:, c * 13:(c + 1) * 13], 13) for c in range(5)], dim=2)
+    assert torch.equal(r["video"], after)

@@ -71,6 +71,29 @@ def test_base_stage_fifo_stage_and_decode():
     assert not np.array_equal(video, video3)
 
 
+def test_streaming_decode_under_the_fifo_loop_is_bit_identical():
+    """SURVEY §8-f2: `streaming_decode=True` decodes every chunk on a side stream as soon as its frames have left the queue;
+    the video equals the decode-after-the-loop path bit for bit, and each chunk was dispatched in its own iteration."""
+    from tokensgen_b200.fifo import cogvideo_fifo_mp_v2
+    pipe = _tiny_pipe()
+    g = torch.Generator().manual_seed(3)
+    frames = torch.rand(1, 27, 3, 64, 96, generator=g) * 2 - 1
+    pe, ne = torch.randn(1, 10, 128, generator=g), torch.randn(1, 10, 128, generator=g)
+    pipe.vae_posterior_generator = torch.Generator().manual_seed(5)
+    base = pipe(frames=frames, prompt_embeds=pe, negative_prompt_embeds=ne, height=64, width=96, num_frames_per_chunk=9,
+                max_num_chunks=3, max_num_chunks_w_fifo=25, max_num_chunks_wo_fifo=1, num_inference_steps=12, guidance_scale=6.0,
+                generator=torch.Generator().manual_seed(42), vip_scale=[0.6], sampling_mode="fifo",
+                sampling_params={"num_partitions": 4, "use_adaptive_padding": True}, cache_idx=None, output_type="np",
+                return_dict=False)
+    import copy
+    _, ref, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42)
+    log = {}
+    _, got, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, streaming_decode=True, stream_log=log)
+    assert got.shape == ref.shape == (1, 27, 64, 96, 3)
+    assert np.array_equal(got, ref)
+    assert log == {c: (12 - 3) + 3 * (c + 1) - 1 for c in range(3)}      # T = 12, nf = 3
+
+
 def test_t2to_pipeline_tail():
     from pca import PCA
     from tokensgen_b200.pipeline_t2to import LongVGenCogVideoXPipeline

@@ -43,6 +43,7 @@ struct AttnParams {
     int n_pass;        // v3: 1, or 2 = a second (Q2, K2, V2) problem over the same query rows, accumulated into the same output
     int kv_rows2;      // v3 pass 1
     float out_scale2;  // v3 pass 1: out += out_scale2 * attn2
+    int spec;          // v3: speculative softmax reference (block 0's row max, never updated) with an exact in-kernel redo
     int mutex;    // v2: the two tiles take turns on the MUFU pipe (named-barrier hand-off) instead of sharing it
     int stagger;  // v2: cycles by which tile 1 starts after tile 0 (keeps the two tiles' softmax phases interleaved)
     // sequence-parallel scatter of the output rows (tg_attn_fwd_sp): sp_world > 0 -> row g of a batch goes to its owner rank
@@ -762,6 +763,16 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     const uint32_t tmem_slot = bar_base + 8u * (18 + 2 * AT_STAGES);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    // Speculative reference (p.spec): the row max of key block 0 stays the softmax reference for the whole pass — no per-block
+    // row max, no exchange between the two threads of a row, no rescale.  Exact as long as no exponential leaves the fp32 /
+    // bf16 range (powers of two scale exactly): a row whose sum reaches 2^100 (or is not finite) sets `redo_flag`, the CTA
+    // stores nothing, and when the regular passes are over every role runs them AGAIN with the exact running-max path
+    // (`verdict`: one arrival per softmax warp; producer and MMA issuers wait for it at the end of their last pass, when they
+    // would be idle anyway).  With LayerNormed q / k (|s| <= |q||k|/8) the redo never runs; it is what keeps the result exact.
+    const uint32_t verdict = bar_base + 8u * (19 + 2 * AT_STAGES);
+    const uint32_t redo_flag = bar_base + 8u * (20 + 2 * AT_STAGES);
+    volatile uint32_t* redo_flag_ptr =
+        reinterpret_cast<volatile uint32_t*>(smem_raw + (redo_flag - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -772,6 +783,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     // video-IP-adapter processor.  TMEM, barriers and the K/V ring are set up once; barrier parities run on the cumulative
     // block index g.
     const int n_pass = p.n_pass;
+    const int total_pass = p.spec ? 2 * n_pass : n_pass;  // pass indices >= n_pass are the exact redo
     auto pass_blocks = [&](int pass) { return ((pass == 0 ? p.kv_rows : p.kv_rows2) + AT_BLOCK_KV - 1) / AT_BLOCK_KV; };
 
     if (warp == 0 && lane == 0) {
@@ -787,6 +799,8 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
         mbar_init(q_empty, 2);
+        mbar_init(verdict, 16);
+        *redo_flag_ptr = 0u;
         for (int s = 0; s < AT_STAGES; ++s) {
             mbar_init(kv_full(s), 1);
             mbar_init(kv_empty(s), 2);
@@ -816,11 +830,16 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (lane == 0) {
                 int stage = 0;
                 uint32_t phase = 0;
-                for (int pass = 0; pass < n_pass; ++pass) {
+                for (int pi = 0; pi < total_pass; ++pi) {
+                    if (pi == n_pass) {
+                        mbar_wait_fast(verdict, 0u);
+                        if (*redo_flag_ptr == 0u) break;
+                    }
+                    const int pass = pi >= n_pass ? pi - n_pass : pi;
                     const CUtensorMap* mq = pass == 0 ? &tmap_q : &tmap_q2;
                     const CUtensorMap* mk = pass == 0 ? &tmap_k : &tmap_k2;
                     const CUtensorMap* mv = pass == 0 ? &tmap_v : &tmap_v2;
-                    if (pass > 0) mbar_wait_fast(q_empty, uint32_t((pass - 1) & 1));
+                    if (pi > 0) mbar_wait_fast(q_empty, uint32_t((pi - 1) & 1));
                     mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
                     tma_load_3d(q_smem, mq, q_full, 0, q0, bh);
                     tma_load_3d(q_smem + AT_TILE_BYTES, mq, q_full, 0, q0 + AT_BLOCK_Q, bh);
@@ -868,9 +887,14 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 int stage = 0;
                 uint32_t phase = 0;
                 int g = 0;  // cumulative block index over the passes
-                for (int pass = 0; pass < n_pass; ++pass) {
+                for (int pi = 0; pi < total_pass; ++pi) {
+                    if (pi == n_pass) {
+                        mbar_wait_fast(verdict, 0u);
+                        if (*redo_flag_ptr == 0u) break;
+                    }
+                    const int pass = pi >= n_pass ? pi - n_pass : pi;
                     const int nb = pass_blocks(pass);
-                    mbar_wait_fast(q_full, uint32_t(pass & 1));
+                    mbar_wait_fast(q_full, uint32_t(pi & 1));
                     if (g > 0) mbar_wait_fast(bar_sfree, uint32_t((g - 1) & 1));  // the previous pass's last S_t is in registers
                     mbar_wait_fast(kv_full(stage), phase);
                     tc_fence_after();
@@ -935,7 +959,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
         int g = 0;   // cumulative block index over the passes (mbarrier parities)
         int xg = 0;  // exchange-slot parity: advances with every use of the pair's shared-memory slots
-        for (int pass = 0; pass < n_pass; ++pass) {
+        for (int pi = 0; pi < total_pass; ++pi) {
+        if (pi == n_pass && *redo_flag_ptr == 0u) break;   // every softmax thread read the final flag after the last vote
+        const int pass = pi >= n_pass ? pi - n_pass : pi;
+        const bool exact = p.spec == 0 || pi >= n_pass;
         const int n_blocks = pass_blocks(pass);
         const int kv_rows = pass == 0 ? p.kv_rows : p.kv_rows2;
         float mc = 0.f;    // reference max in log2 units, integer-valued
@@ -966,6 +993,8 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             bool waited = false;
             if (j == 0) { mc = float(A3_FIXED_TEST); smin = (mc - 126.0f) * inv_c; }
 #else
+            bool waited = false;
+            if (exact || j == 0) {
             float pm[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) pm[k] = fmaxf(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
@@ -981,7 +1010,6 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                 named_bar_sync(pair_bar, 64);
                 mx = fmaxf(mx, lds_f32(xs_other + par));
             }
-            bool waited = false;
             if (j == 0) {
                 mc = ceilf(mx * c);
                 smin = (mc - 126.0f) * inv_c;
@@ -1007,6 +1035,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     tmem_st32(o_addr, ro);
                 }
             }
+            }  // exact || j == 0
 #endif
             const uint64_t nmc2 = pack_f32x2(-mc, -mc);
             const float Kf = MAGIC - mc;
@@ -1071,12 +1100,23 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             named_bar_sync(pair_bar, 64);
             l += lds_f32(xs_other + par);
         }
+        bool skip = false;
+        if (!exact) {
+            // CTA-wide vote on this pass's speculative result (sticky across the passes of a pair launch)
+            if (!(l < 1.2676506e30f)) *redo_flag_ptr = 1u;  // 2^100; also catches inf / NaN
+            named_bar_sync(9, 512);
+            skip = *redo_flag_ptr != 0u;
+            if (pi == n_pass - 1) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(verdict);
+            }
+        }
         mbar_wait_fast(bar_odone, uint32_t((g - 1) & 1));
         tc_fence_after();
         const float inv_l = 1.0f / l;
         const bool accumulate = pass == 0 ? (p.accumulate != 0) : true;
         const float out_scale = pass == 0 ? p.out_scale : p.out_scale2;
-        const bool store = q_row < p.q_rows;
+        const bool store = q_row < p.q_rows && !skip;
         const int b = bh / p.H, h = bh - b * p.H;
         __nv_bfloat16* o_ptr =
             attn_out_row(p, b, h, q_row) + half * 32;
@@ -1126,6 +1166,7 @@ static long long* g_attn_trace = nullptr;
 static int g_attn_mutex = 0;
 static int g_attn_packed = 1;
 static int g_attn_alt = 0;   // v3: the two query tiles take turns on the MUFU pipe
+static int g_attn_spec = 1;  // v3: speculative softmax reference + exact in-kernel redo (see attn3_fwd_kernel)
 
 template <int EMU, bool MUTEX, bool TRACE, bool PACKED>
 static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -1218,6 +1259,7 @@ static int attn_fwd_impl(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0,
     p.accumulate = accumulate;
     p.out_scale = out_scale;
     p.n_pass = 1;
+    p.spec = g_attn_spec;
     p.stagger = g_attn_stagger;
     p.trace = g_attn_trace;
     p.mutex = g_attn_mutex;
@@ -1313,6 +1355,7 @@ static int attn_fwd_pair_impl(const tg_bf16* q, const tg_bf16* k, const tg_bf16*
     p.accumulate = 0;
     p.out_scale = 1.0f;
     p.n_pass = 2;
+    p.spec = g_attn_spec;
     p.kv_rows2 = kv_rows2;
     p.out_scale2 = out_scale2;
     if (scatter != nullptr) {
@@ -1354,5 +1397,6 @@ extern "C" int tg_set_tuning(const char* key, int value) {
     if (k == "attn_mutex") { g_attn_mutex = value; return 0; }
     if (k == "attn_packed") { g_attn_packed = value; return 0; }
     if (k == "attn_alt") { g_attn_alt = value; return 0; }
+    if (k == "attn_spec") { g_attn_spec = value; return 0; }
     return fail(-2, "set_tuning: unknown key %s", key);
 }

@@ -197,13 +197,16 @@ class FifoCheckpoint:
 
 def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn, seed: int = 0, rank: int = 0,
              world: int = 1, group=None, progress: Optional[Callable[[int], None]] = None,
-             checkpoint: Optional[FifoCheckpoint] = None, on_resume: Optional[Callable[[int], None]] = None) -> List[torch.Tensor]:
+             checkpoint: Optional[FifoCheckpoint] = None, on_resume: Optional[Callable[[int], None]] = None,
+             on_emit: Optional[Callable[[int, List[torch.Tensor]], None]] = None) -> List[torch.Tensor]:
     """The controller loop (:230-359).  `step_fn(window, latents[1,13,...], old_x0 list, t, prev_t, next_t, generator)`
     returns (latents_out [1,13,...], x0 list); `shift_fn(queue, noise_generator)` advances the queue by one slot and
     re-noises the tail.  Returns the emitted frames (slot r_nf of every iteration) as seen by this rank; rank 0's list is
     the video (emissions before iteration T - nf are the ramp-up the reference drops, :367).
     `checkpoint`: save the stage state every `checkpoint.every` iterations and resume from the newest state all ranks
-    hold; `on_resume(k)` lets the caller fast-forward its own per-iteration bookkeeping (VipBook.shift) by k iterations."""
+    hold; `on_resume(k)` lets the caller fast-forward its own per-iteration bookkeeping (VipBook.shift) by k iterations.
+    `on_emit(it, emitted)`: called on EVERY rank right after iteration `it` appended its frame (the list is complete on
+    rank 0 only) and before the queue shifts — the hook of the streaming decode (`StreamingDecoder`)."""
     import torch.distributed as dist
     emitted = []
     dev = queue.latents.device
@@ -253,6 +256,8 @@ def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn
                 for s in range(lo, hi):
                     queue.x0_valid[s] = True
         emitted.append(queue.latents[:, [schedule.r_nf]].clone())
+        if on_emit is not None:
+            on_emit(it, emitted)
         ngen = torch.Generator(device=dev).manual_seed(seed * 1000003 + it + 7919)
         shift_fn(queue, ngen)
         if checkpoint is not None and checkpoint.every > 0 and (it + 1) % checkpoint.every == 0 \
@@ -395,6 +400,82 @@ def decode_latents_parallel(pipe, latents: torch.Tensor, nf: int, rank: int = 0,
     return None if rank != 0 else torch.cat([outs[c] for c in range(chunks)], dim=2)
 
 
+class StreamingDecoder:
+    """Streaming decode under the FIFO loop.  The reference decodes all chunks serially on GPU 0 AFTER the
+    loop (cogvideo_sampling_mp_fifo.py:367-385); `decode_latents_parallel` already spreads that tail over the ranks.  Here
+    chunk c is decoded as soon as its `nf` latent frames have left the queue — iteration (T - nf) + nf (c + 1) - 1 — on
+    rank c % P, on a SIDE stream, while the main stream goes on denoising: the first 49 frames are available after 52 + 13
+    iterations instead of after the whole stage, and no decode is left for the end except the last chunk's.
+
+    Every rank runs the same deterministic loop, so the owner knows in which iteration to post its receive: rank 0 (the
+    emitting rank: slot r_nf belongs to window rank 0) sends the chunk's latents (2.25 MB) to the owner inside the
+    iteration, the owner decodes (clip-local: the VAE's conv cache is cleared per chunk, autoencoder_kl_cogvideox.py:1157),
+    and `finish()` collects the frames on rank 0.  The arithmetic is `pipe.decode_latents` on the same latents, so the video
+    is bit-identical to the decode-after-the-loop path."""
+
+    def __init__(self, pipe, nf: int, first_it: int, rank: int = 0, world: int = 1, group=None):
+        self.pipe, self.nf, self.first_it, self.rank, self.world, self.group = pipe, nf, first_it, rank, world, group
+        self.done = 0                       # chunks dispatched so far
+        self.frames: Dict[int, torch.Tensor] = {}
+        self.ready_it: Dict[int, int] = {}  # chunk -> iteration in which its decode was enqueued
+        self.side = None
+
+    def _decode(self, c: int, latents: torch.Tensor):
+        dev = latents.device
+        if dev.type != "cuda":      # host tensors (the gloo tests of the hand-off logic): no streams, decode in line
+            self.frames[c] = self.pipe.decode_latents(latents, self.nf)
+            return
+        if self.side is None:
+            self.side = torch.cuda.Stream(device=dev)
+        self.side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(self.side):
+            self.frames[c] = self.pipe.decode_latents(latents, self.nf)
+        latents.record_stream(self.side)
+
+    def on_emit(self, it: int, emitted: List[torch.Tensor]) -> None:
+        import torch.distributed as dist
+        n_video = len(emitted) - self.first_it          # frames of the video emitted so far (negative during the ramp-up)
+        while n_video >= (self.done + 1) * self.nf:
+            c = self.done
+            owner = c % self.world
+            lo = self.first_it + c * self.nf
+            if self.rank == 0:
+                chunk = torch.cat(emitted[lo:lo + self.nf], dim=1).contiguous()
+                if owner != 0:
+                    dist.send(chunk, dst=owner if self.group is None else dist.get_global_rank(self.group, owner), group=self.group)
+                else:
+                    self._decode(c, chunk)
+            elif self.rank == owner:
+                like = emitted[0]
+                chunk = torch.empty((like.shape[0], self.nf) + tuple(like.shape[2:]), device=like.device, dtype=like.dtype)
+                dist.recv(chunk, src=0 if self.group is None else dist.get_global_rank(self.group, 0), group=self.group)
+                self._decode(c, chunk)
+            self.ready_it[c] = it
+            self.done += 1
+
+    def finish(self) -> Optional[torch.Tensor]:
+        """Frames [B, 3, F, H, W] on rank 0 (None elsewhere), chunks in order."""
+        import torch.distributed as dist
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+        chunks = self.done
+        if self.world == 1:
+            return torch.cat([self.frames[c] for c in range(chunks)], dim=2)
+        ops = []
+        if self.rank != 0:
+            ops = [dist.P2POp(dist.isend, self.frames[c].contiguous(), 0, group=self.group) for c in sorted(self.frames)]
+        else:
+            like = self.frames[0]
+            for c in range(chunks):
+                if c % self.world:
+                    self.frames[c] = torch.empty_like(like)
+                    ops.append(dist.P2POp(dist.irecv, self.frames[c], c % self.world, group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        return None if self.rank != 0 else torch.cat([self.frames[c] for c in range(chunks)], dim=2)
+
+
 def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **kwargs):
     """Drop-in for the reference sampler entry point (cogvideo_sampling_mp_fifo.py:27-395): same arguments
     (`pipe_list`, `base_output`) and the same return value — `(orig_video, video, cache_video)` or a
@@ -451,14 +532,27 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
             for _ in range(k):
                 vip.shift()
 
+    # `streaming_decode` (schema extension): decode every chunk under the loop as soon as it is complete
+    streamer = None
+    if kwargs.get("streaming_decode") and base_output.output_type != "latent":
+        streamer = StreamingDecoder(pipe, nf, T - nf, rank, world)
     emitted = run_fifo(schedule, queue, step_fn, shift, seed=seed, rank=rank, world=world, progress=progress,
-                       checkpoint=ckpt, on_resume=fast_forward)
+                       checkpoint=ckpt, on_resume=fast_forward, on_emit=None if streamer is None else streamer.on_emit)
     latents = torch.cat(emitted[(T - nf):], dim=1).contiguous()           # :367 (slot r_nf belongs to window rank 0 -> process 0)
-    if world > 1:
+    if world > 1 and streamer is None:
         dist.broadcast(latents, src=0)
     orig_latents = base_output.orig_latents
     if base_output.output_type == "latent":
         video, orig_video = latents, orig_latents
+    elif streamer is not None:
+        decoded = streamer.finish()
+        video = None if decoded is None else pipe.video_processor.postprocess_video(video=decoded, output_type=base_output.output_type)
+        orig_video = None
+        if rank == 0:
+            orig_video = pipe.video_processor.postprocess_video(video=pipe.decode_latents(orig_latents, nf),
+                                                                output_type=base_output.output_type)
+        if kwargs.get("stream_log") is not None:
+            kwargs["stream_log"].update(streamer.ready_it)
     else:
         # decode is clip-parallel with no communication inside a clip (the conv cache is cleared per 13-frame chunk,
         # autoencoder_kl_cogvideox.py:1157): chunk c is decoded by process c % P and collected on process 0.
