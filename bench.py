@@ -296,6 +296,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E.load()
+    for key in ("attn_spec", "attn_emu"):      # developer A/B knobs (dev builds of the library only; see profiles/r02_ab_*.md)
+        if os.environ.get("TG_" + key.upper()) is not None:
+            E.set_tuning(key, int(os.environ["TG_" + key.upper()]))
 
     model = build_random_model(device=dev, seed=rank)
     sch = CogVideoXDPMScheduler.cogvideox_5b()

@@ -200,7 +200,10 @@ int tg_unpatchify(const tg_bf16* rows, tg_bf16* latents, int B, int F, int C, in
  * K12: classifier-free guidance + per-frame DPM-Solver++(2M) SDE step for one window, one launch.
  * Replaces cogvideo_sampling_mp_fifo.py:527-550 + scheduling_dpm_cogvideox.py:424-463 (13 Python iterations of
  * ~15 elementwise launches each), and pipeline_cogvideox_mp_fifo.py:1247-1290 for the base stage.
- *   noise_pred : bf16 [n_branches, F, chw]; n_branches = 2 -> (uncond, cond) combined as u + g*(c-u); 1 -> used as is.
+ *   noise_pred : bf16 [n_branches, F, chw]; n_branches = 2 -> (uncond, cond) combined as u + g*(c-u); 1 -> used as is;
+ *                3 (BF16_CHAIN only) -> `use_separate_guidance` (:528-530): (uncond_txt, uncond_img, txt_img) combined as
+ *                a + guidance_scale * (a - ut) + guidance_scale2 * (a - ui) with a = txt_img, where guidance_scale /
+ *                guidance_scale2 are the reference's (guidance_scale - 1) / (guidance_scale_img - 1).
  *   coef       : fp32 [F, 8] per frame {sqrt_alpha_t, sqrt_beta_t, mult0, mult1, mult2, mult3, mult_noise, flags};
  *                flags (as float) 1.0 = second-order frame (old x0 valid and prev_timestep >= 0), else 0.0.
  *                The host computes them in fp64 exactly as CogVideoXDPMScheduler.get_variables/get_mult and casts.
@@ -228,6 +231,7 @@ typedef struct {
     int F;
     int64_t chw;
     int mode;
+    float guidance_scale2;     /* n_branches = 3 only */
 } tg_dpm_step_args;
 int tg_cfg_dpm_step(const tg_dpm_step_args* args, void* stream);
 
@@ -275,6 +279,13 @@ typedef struct {
     int64_t ldy;
     int64_t plane_stride;
     int layout;
+    /* GroupNorm statistics of the OUTPUT accumulated in the epilogue (layout 0 only): stats[g] += sum, stats[stat_groups + g] +=
+     * sum of squares of the stored (bf16-rounded) outputs of group g — the `sums` tg_vae_norm_act reads, so the statistics pass
+     * over the tensor (tg_vae_group_stats) is not needed for tensors a convolution produced.  The caller zeroes `stats`
+     * (2 * stat_groups doubles); NULL = off.  Needs Cout % 32 == 0, stat_groups <= 64 and Cout / stat_groups in {4, 8, 16} or a
+     * multiple of 32. */
+    double* stats;
+    int stat_groups;
 } tg_conv_args;
 int tg_vae_conv(const tg_conv_args* args, void* stream);
 

@@ -81,11 +81,17 @@ def step(tables: DpmTables, model_output, old_x0, timestep, prev_timestep, times
 
 
 def window_step_bf16(tables: DpmTables, noise_pred, guidance_scale, latents, old_x0: List, t, prev_t, next_t, noise1, noise2,
-                     device_semantics: str = "cuda"):
+                     device_semantics: str = "cuda", guidance_scale_img=None):
     """The FIFO worker's CFG + per-frame scheduler loop, cogvideo_sampling_mp_fifo.py:527-550 (all tensors bf16).
-    noise_pred [2,F,...], latents [1,F,...], old_x0 list of F (tensor [1,1,...] or None); t/prev_t/next_t int arrays [F]."""
-    u, c = noise_pred.chunk(2)
-    npred = u + guidance_scale * (c - u)
+    noise_pred [2,F,...] — or [3,F,...] (uncond_txt, uncond_img, txt_img) with `guidance_scale_img`, the
+    use_separate_guidance branch (:528-530) — latents [1,F,...], old_x0 list of F (tensor [1,1,...] or None);
+    t/prev_t/next_t int arrays [F]."""
+    if noise_pred.shape[0] == 3:
+        ut, ui, a = noise_pred.chunk(3)
+        npred = a + (guidance_scale - 1) * (a - ut) + (guidance_scale_img - 1) * (a - ui)
+    else:
+        u, c = noise_pred.chunk(2)
+        npred = u + guidance_scale * (c - u)
     out = latents.clone()
     x0s = []
     for j in range(latents.shape[1]):

@@ -468,6 +468,8 @@ def fifo_tiny_base_output(device="cpu"):
     emb = torch.randn(1, (nc + 1) * nt, G["vip_dim"], rq["num_height_queries"], rq["num_width_queries"], generator=g).bfloat16()
     emb = torch.cat([emb, emb], dim=0)
     orig = torch.randn(1, nf, G["C"], G["H"], G["W"], generator=g).bfloat16()
+    # use_separate_guidance bundle (pipeline_cogvideox_mp_fifo.py:642-644): [cond | uncond (zero-clip tokens) | cond]
+    uncond = torch.randn(1, (nc + 1) * nt, G["vip_dim"], rq["num_height_queries"], rq["num_width_queries"], generator=g).bfloat16()
     lin = lambda a, b, n: np.linspace(a, b, n, endpoint=False, dtype=np.float32)
     gh, gw = G["H"] // 2, G["W"] // 2
     s0 = c["start_frame_idx"]
@@ -476,6 +478,9 @@ def fifo_tiny_base_output(device="cpu"):
             lin(0, gh, rq["num_height_queries"]), lin(0, gw, rq["num_width_queries"])]
     return dict(fifo_latents=fifo_latents.to(device), fifo_old_pred_original_sample=[None if o is None else o.to(device) for o in old],
                 prompt_embeds=prompt.to(device), image_embeddings=emb.to(device), orig_latents=orig.to(device),
+                image_embeddings_sep=torch.cat([emb[:1], uncond, emb[:1]], dim=0).to(device),
+                prompt_embeds_sep=torch.cat([prompt[:1], prompt[1:], prompt[1:]], dim=0).to(device),
+                guidance_scale_img=4.0,
                 vip_image_rotary_grid=img, vip_condition_rotary_grid=cond, nf_per_chunk=nf, vip_nf_per_chunk=nt,
                 num_frames=nc * nf, num_inference_steps=T, guidance_scale=c["guidance_scale"],
                 video_ipadapter_start_frame_idx=s0, rope_grid=(nf, gh, gw))
@@ -609,6 +614,29 @@ def gen_fifo_stage():
             f32_out[(r["it"], r["start"])] = (o[5].clone(), torch.cat([x.clone() for x in o[6]], dim=1))
         del calls[len(main_calls):]
         dit.to(torch.bfloat16)
+        # use_separate_guidance (three branches: uncond_txt, uncond_img, txt_img; :493-497, :528-530): the same worker, bf16,
+        # teacher-forced on the steady-state windows of iteration 7
+        sep_out = {}
+        for r in main_calls:
+            if r["it"] != 7:
+                continue
+            it_ = list(r["item"])
+            n_emb = r["emb_in"].shape[1]
+            full = b["image_embeddings_sep"]
+            ext = torch.cat([full] + [full[:, -b["vip_nf_per_chunk"]:]] * (G["T"] // b["nf_per_chunk"] + 1), dim=1)   # :101-108
+            grid = np.concatenate([b["vip_condition_rotary_grid"][0]] + [b["vip_condition_rotary_grid"][0][-b["vip_nf_per_chunk"]:]
+                                  + (i + 1) * b["nf_per_chunk"] for i in range(G["T"] // b["nf_per_chunk"] + 1)])             # :95-99
+            idx = int(np.where(grid == r["cond_t"][0])[0][0])
+            assert torch.equal(ext[:1, idx:idx + n_emb], r["emb_in"][:1])
+            it_[18] = ext[:, idx:idx + n_emb].clone()
+            iq, oq = InQ(), queue.Queue()
+            iq.put(tuple(it_))
+            iq.put(None)
+            mod.fifo_onestep_per_gpu(0, iq, oq, Pipe(), b["prompt_embeds_sep"], rope, G["T"], True, True, c["guidance_scale"],
+                                     b["guidance_scale_img"], False, None)
+            o = oq.get()
+            sep_out[(r["it"], r["start"])] = (it_[18], o[5].clone(), torch.cat([x.clone() for x in o[6]], dim=1))
+        del calls[len(main_calls):]
     finally:
         mod.mp, mod.tqdm, smod.randn_tensor, torch.randn_like = saved
         sch.step = orig_step
@@ -618,6 +646,9 @@ def gen_fifo_stage():
         if r["it"] in keep_inputs:
             rec.update(lat_in=r["lat_in"], old_in=r["old_in"], emb_in=r["emb_in"], img_t=r["img_t"], cond_t=r["cond_t"],
                        lat_out_f32=f32_out[(r["it"], r["start"])][0], x0_out_f32=f32_out[(r["it"], r["start"])][1])
+            if (r["it"], r["start"]) in sep_out:
+                e3, l3, x3 = sep_out[(r["it"], r["start"])]
+                rec.update(sep_emb_in=e3, sep_lat_out=l3, sep_x0_out=x3)
         recs.append(rec)
     torch.save({"config": {k: v for k, v in c.items() if k != "seeds"}, "seeds": c["seeds"],
                 "meta": {"shapes": shapes, "digest": state_dict_digest(sd)}, "timesteps": sch.timesteps.clone(),

@@ -196,3 +196,74 @@ def test_window_step_vs_oracle_loop():
         assert torch.equal(out_lat.cpu(), ref_lat)
         for j in range(F):
             assert torch.equal(out_x0[j].cpu(), ref_x0[j]), (start, j)
+
+
+def test_dit_forward_is_cuda_graph_capturable_and_replays_bit_identically(golden_dir):
+    """INTEGRATION.md's claim about the C ABI (no allocation, no synchronisation, every launch on the caller's stream): one
+    whole DiT forward with the video-IP-adapter — time embedding, AdaLN table GEMM, patchify, 2 blocks of LN-modulate / fused
+    QKV+RoPE GEMM / three attentions / gated-residual and GELU GEMMs, final double LayerNorm, unpatchify — is captured in a
+    CUDA graph and replayed with NEW inputs copied into the captured tensors: every replay equals the eager result bit for
+    bit."""
+    from oracle.synth import dit_shapes, synth_state_dict
+    g = torch.load(os.path.join(golden_dir, "dit_tiny.pt"))
+    sd = synth_state_dict(dit_shapes(use_vip=True, **TINY), 1234)
+    m = tiny_model(True, sd)
+    dev = torch.device("cuda")
+    on = lambda pair: tuple(t.to(dev) for t in pair)
+    rope, img, cond = on(g["rope"]), on(g["img_rope"]), on(g["cond_rope"])
+    inputs = {k: [t.cuda() for t in g[f"vip_{k}_inputs"]] for k in ("pf",)}
+    lat, text, vip, ts = inputs["pf"]
+    s_lat, s_text, s_vip, s_ts = lat.clone(), text.clone(), vip.clone(), ts.clone()
+
+    def fwd():
+        return m(s_lat, s_text, s_ts, vip_encoder_hidden_states=s_vip, image_rotary_emb=rope, vip_image_rotary_emb=img,
+                 vip_condition_rotary_emb=cond, return_dict=False)[0]
+
+    with torch.no_grad():
+        eager = fwd().clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):        # warm-up on the capture stream (workspaces, packed weights, tensor maps)
+            fwd()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = fwd()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, eager)
+        # new inputs through the same graph
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        lat2 = torch.randn(lat.shape, generator=gen, device="cuda").bfloat16()
+        s_lat.copy_(lat2)
+        graph.replay()
+        torch.cuda.synchronize()
+        replayed = out.clone()
+        s_lat.copy_(lat2)
+        eager2 = fwd()
+        torch.cuda.synchronize()
+        assert torch.equal(replayed, eager2) and not torch.equal(replayed, eager)
+
+
+def test_a_foreign_attention_processor_is_not_silently_ignored(golden_dir):
+    """`Attention.set_processor` (attention_processor.py:423-441) with a processor the fused engine does not know must not
+    be bypassed by the model's fast path: the forward raises and says how to run it."""
+    from oracle.synth import dit_shapes, synth_state_dict
+    from tokensgen_b200 import _ext as E
+    g = torch.load(os.path.join(golden_dir, "dit_tiny.pt"))
+    m = tiny_model(False, synth_state_dict(dit_shapes(use_vip=False, **TINY), 1234))
+    lat, text, vip, ts = g["plain_ps_inputs"]
+
+    class Mine:
+        def __call__(self, attn, hidden_states, encoder_hidden_states, attention_mask=None, image_rotary_emb=None):
+            return hidden_states, encoder_hidden_states
+
+    m.transformer_blocks[1].attn1.set_processor(Mine())
+    with pytest.raises(E.TokensGenError, match="processor"):
+        with torch.no_grad():
+            m(lat.cuda(), text.cuda(), ts.cuda(), image_rotary_emb=g["rope"], return_dict=False)
+    # the module-level plugin API still dispatches to it (Attention.forward filters kwargs by the processor's signature)
+    h = torch.zeros(1, 4, 256, device="cuda", dtype=torch.bfloat16)
+    e = torch.zeros(1, 2, 256, device="cuda", dtype=torch.bfloat16)
+    oh, oe = m.transformer_blocks[1].attn1(h, encoder_hidden_states=e, image_rotary_emb=g["rope"], vip_image_rotary_emb=None)
+    assert oh is h and oe is e

@@ -108,3 +108,41 @@ def test_reference_worker_agrees_with_the_oracle_window_step(gold):
         ex0 = ((torch.cat(x0s, 1).float() - rec["x0_out"].float()).norm() / rec["x0_out"].float().norm()).item()
         worst = max(worst, err, ex0)
     assert worst < 1e-2, worst
+
+
+def test_separate_guidance_worker_agrees_with_the_oracle(gold):
+    """use_separate_guidance (three branches uncond_txt / uncond_img / txt_img, cogvideo_sampling_mp_fifo.py:493-497,528-530):
+    the reference worker's recorded outputs on the windows of iteration 7 against the oracle's B = 3 forward + 3-branch CFG."""
+    from oracle import dit as odit
+    from oracle import dpm as odpm
+    from oracle import rope as orope
+    from oracle.make_goldens import fifo_tiny_base_output
+    from oracle.synth import keyed_noise, synth_state_dict
+    from tokensgen_b200.fifo import FifoSchedule
+    b = fifo_tiny_base_output()
+    c = gold["config"]
+    sd = synth_state_dict(gold["meta"]["shapes"], seed=gold["seeds"]["dit"])
+    cfg = odit.DitConfig(num_attention_heads=4, attention_head_dim=64, time_embed_dim=128, text_embed_dim=128, num_layers=2,
+                         vip_length=c["vip"]["length"], vip_embed_dim=c["geom"]["vip_dim"], use_vip=True)
+    nf, gh, gw = b["rope_grid"]
+    rope = orope.rope_3d(64, [[0, 0, 0], [nf, gh, gw]], (nf, gh, gw))
+    sched = FifoSchedule(b["num_frames"], [int(t) for t in gold["timesteps"]], nf, c["geom"]["num_partitions"], True)
+    tables = odpm.DpmTables()
+    recs = [r for r in gold["calls"] if "sep_lat_out" in r]
+    assert len(recs) >= 4
+    for rec in recs[:2]:
+        s, e = rec["start"], rec["end"]
+        img = orope.rope_3d_from_grids(64, rec["img_t"], b["vip_image_rotary_grid"][1], b["vip_image_rotary_grid"][2])
+        cond = orope.rope_3d_from_grids(64, rec["cond_t"], b["vip_condition_rotary_grid"][1], b["vip_condition_rotary_grid"][2])
+        ts = torch.as_tensor(sched.t[s:e].copy()).expand(3, -1)
+        lat = rec["lat_in"]
+        npred = odit.dit_forward(sd, cfg, torch.cat([lat] * 3), b["prompt_embeds_sep"], ts, rec["sep_emb_in"], rope, img, cond,
+                                 torch.bfloat16)
+        n1 = torch.cat([keyed_noise((7, s, j, 0), lat[:, [j]].shape) for j in range(nf)], dim=1)
+        n2 = torch.cat([keyed_noise((7, s, j, 1), lat[:, [j]].shape) for j in range(nf)], dim=1)
+        out, x0s = odpm.window_step_bf16(tables, npred.bfloat16(), c["guidance_scale"], lat, rec["old_in"], sched.t[s:e],
+                                         sched.prev_t[s:e], sched.next_t[s:e], n1, n2, device_semantics="cpu",
+                                         guidance_scale_img=b["guidance_scale_img"])
+        rel = lambda a, r: ((a.float() - r.float()).norm() / r.float().norm()).item()
+        assert rel(out, rec["sep_lat_out"]) < 1e-2 and rel(torch.cat(x0s, 1), rec["sep_x0_out"]) < 1e-2
+        assert rel(rec["sep_x0_out"], rec["x0_out"]) > 5e-2            # the three-branch result is a different one

@@ -87,6 +87,57 @@ def test_window_steps_teacher_forced_against_the_reference_worker(gold, model):
         assert vs_bf16 < 2.0 * ref + 2e-3, (it, s, vs_bf16, ref)
 
 
+def test_separate_guidance_window_steps_against_the_reference_worker(gold, model):
+    """use_separate_guidance (B = 3: uncond_txt, uncond_img, txt_img; cogvideo_sampling_mp_fifo.py:493-497,528-530): the DiT
+    forward for three branches + the fused three-branch CFG / DPM step against the reference worker's bf16 run on the same
+    window inputs, and the fused step bit for bit against the oracle's op-by-op chain on the product's own prediction."""
+    from oracle import dpm as odpm
+    from oracle.make_goldens import fifo_tiny_base_output
+    from oracle.synth import keyed_noise
+    from tokensgen_b200.fifo import FifoSchedule
+    from tokensgen_b200.rope import get_3d_rotary_pos_embed, get_3d_rotary_pos_embed_v2
+    from tokensgen_b200.scheduler import CogVideoXDPMScheduler
+    dev = torch.device("cuda")
+    b = fifo_tiny_base_output()
+    c = gold["config"]
+    nf, gh, gw = b["rope_grid"]
+    sched = FifoSchedule(b["num_frames"], [int(t) for t in gold["timesteps"]], nf, c["geom"]["num_partitions"], True)
+    sch = CogVideoXDPMScheduler.cogvideox_5b()
+    sch.set_timesteps(c["geom"]["T"])
+    rope = get_3d_rotary_pos_embed(64, [[0, 0, 0], [nf, gh, gw]], (nf, gh, gw), device=dev)
+    tables = odpm.DpmTables()
+    recs = [r for r in gold["calls"] if "sep_lat_out" in r]
+    assert len(recs) >= 4
+    for rec in recs:
+        s, e = rec["start"], rec["end"]
+        img = get_3d_rotary_pos_embed_v2(64, rec["img_t"], b["vip_image_rotary_grid"][1], b["vip_image_rotary_grid"][2], device=dev)
+        cond = get_3d_rotary_pos_embed_v2(64, rec["cond_t"], b["vip_condition_rotary_grid"][1], b["vip_condition_rotary_grid"][2],
+                                          device=dev)
+        lat = rec["lat_in"].to(dev)
+        ts = torch.as_tensor(sched.t[s:e].copy(), device=dev).expand(3, -1)
+        with torch.no_grad():
+            npred = model(hidden_states=torch.cat([lat] * 3), encoder_hidden_states=b["prompt_embeds_sep"].to(dev), timestep=ts,
+                          vip_encoder_hidden_states=rec["sep_emb_in"].to(dev).contiguous(), image_rotary_emb=rope,
+                          vip_image_rotary_emb=img, vip_condition_rotary_emb=cond, return_dict=False)[0]
+        assert npred.shape[0] == 3
+        n1 = torch.cat([keyed_noise((7, s, j, 0), lat[:, [j]].shape) for j in range(nf)], dim=1)
+        n2 = torch.cat([keyed_noise((7, s, j, 1), lat[:, [j]].shape) for j in range(nf)], dim=1)
+        t, pt, nt = sched.t[s:e], sched.prev_t[s:e], sched.next_t[s:e]
+        old = [None if o is None else o.to(dev) for o in rec["old_in"]]
+        out, x0s = sch.window_step(npred, lat, old, t, pt, nt, c["guidance_scale"], noise=(n1.to(dev), n2.to(dev)),
+                                   guidance_scale_img=b["guidance_scale_img"])
+        x0 = torch.cat([x.reshape(1, 1, *lat.shape[2:]) for x in x0s], 1)
+        # the fused kernel reproduces the reference's op-by-op bf16 chain (CUDA scalar semantics) exactly
+        ref_out, ref_x0 = odpm.window_step_bf16(tables, npred.cpu(), c["guidance_scale"], rec["lat_in"], rec["old_in"], t, pt, nt,
+                                                n1, n2, guidance_scale_img=b["guidance_scale_img"])
+        assert torch.equal(out.cpu(), ref_out) and torch.equal(x0.cpu(), torch.cat(ref_x0, 1))
+        # and the whole step sits in the reference's own bf16 band (see the two-branch test for the yardstick)
+        band = max(rel(rec["lat_out"], rec["lat_out_f32"]), rel(rec["x0_out"], rec["x0_out_f32"]))
+        got = max(rel(out, rec["sep_lat_out"]), rel(x0, rec["sep_x0_out"]))
+        print(f"  separate guidance, start {s:2d}: CUDA vs reference bf16 {got:.3e} (two-branch bf16-vs-fp32 band {band:.3e})")
+        assert got < 2.5 * band + 2e-3, (s, got, band)
+
+
 def test_whole_stage_against_the_reference_sampler(gold, model):
     """`cogvideo_fifo_mp_v2` (ours) on the golden's priming state with the reference's noise draws: 15 iterations, 77 window
     forwards, every frame denoised through all 12 levels — final latents against the reference's."""

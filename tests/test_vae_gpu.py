@@ -311,7 +311,7 @@ def test_full_width_mid_block_resnet_on_a_60x90_latent_tile(full_env):
         f = torch.randn(1, 512, T, 60, 90, generator=g).bfloat16()
         zq = torch.randn(1, 16, T, 60, 90, generator=g).bfloat16()
         ref = ov.resnet_block(sd, name, f.float(), zq.float(), cfg, cache)
-        out = V._resnet(blk, cl(f), _zq_tables(zq))
+        out = V._resnet(blk, cl(f), _zq_tables(zq)).x
         e = rel_l2(cf(out), ref)
         print(f"full-width mid-block resnet (512 ch, {T}x60x90): rel_l2 {e:.3e}")
         assert e < 5e-3, (T, e)
@@ -338,7 +338,9 @@ def test_full_width_last_up_block(full_env):
         zt = _zq_tables(zq)
         h = cl(f)
         for r in blk.resnets:
-            h = V._resnet(r, h, zt)
+            h = V._resnet(r, h, zt, 32)      # the epilogue of every conv2 hands its output's group sums to the next norm1
+        assert h.sums is not None and h.groups == 32
+        h = h.x
         e = rel_l2(cf(h), ref)
         print(f"full-width up_blocks[3] (256->128->128->128->128, {T}x64x96): rel_l2 {e:.3e}")
         assert e < 1e-2, (T, e)          # 8 convolutions deep
@@ -361,3 +363,62 @@ def test_full_width_decode_and_encode_vs_oracle(full_env):
     print(f"full-width decode rel_l2 {ed:.3e} PSNR {p:.1f} dB; encode rel_l2 {em:.3e}")
     assert d.shape == refd.shape == (1, 3, 9, 64, 96) and m.shape == refm.shape
     assert ed < 1.5e-2 and em < 1.5e-2 and p >= 40.0
+
+
+@pytest.mark.parametrize("cin,cout,groups,T,H,W,res", [
+    (128, 128, 32, 2, 160, 250, True),     # tap-reuse pair kernel, 4 channels per group, ragged width, residual
+    (128, 256, 32, 1, 150, 300, False),    # pair kernel with two channel tiles, 8 channels per group
+    (256, 512, 32, 2, 9, 33, False),       # CTA-pair 256-wide tiles, 16 channels per group, odd number of pixel tiles
+    (64, 64, 8, 3, 19, 70, True),          # single-CTA 64-wide tiles (tiny configs), 8 channels per group
+    (64, 128, 2, 1, 37, 45, False),        # 64 channels per group (a chunk lies inside one group)
+])
+def test_conv_epilogue_group_statistics_equal_the_separate_pass(cin, cout, groups, T, H, W, res):
+    """tg_conv_args.stats: the sums the epilogue accumulates are those of the STORED output — compared with tg_vae_group_stats
+    over that output (fp64 sums of the same bf16 values: equal up to the fp32 partial-sum order) and with torch on the host."""
+    from tokensgen_b200 import _ext as E
+    from tokensgen_b200.vae import _PackedConv
+    g = torch.Generator().manual_seed(cin + cout + W)
+    conv = torch.nn.Conv3d(cin, cout, 3)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (27 * cin) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    conv = conv.to(torch.bfloat16)
+    x = (torch.randn(1, cin, T + 2, H, W, generator=g) + 0.3).bfloat16()
+    r = torch.randn(T, H, W, cout, generator=g).bfloat16().cuda() if res else None
+    w, b = _PackedConv().get(conv.cuda())
+    assert E.conv_stats_supported(cout, groups)
+    stats = torch.zeros(2 * groups, device="cuda", dtype=torch.float64)
+    xin = x[0].permute(1, 2, 3, 0).contiguous().cuda()
+    y = E.vae_conv(xin, w, b, cout, 3, 3, 3, T, H, W, residual=r, stats=stats, stat_groups=groups)
+    y_plain = E.vae_conv(xin, w, b, cout, 3, 3, 3, T, H, W, residual=r)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y_plain)                                   # the statistics do not touch the output
+    want = E.vae_group_stats(y, groups)
+    yg = y.double().cpu().reshape(-1, groups, cout // groups)
+    host = torch.cat([yg.sum(dim=(0, 2)), (yg * yg).sum(dim=(0, 2))])
+    torch.cuda.synchronize()
+    scale = host[groups:].abs().max().item()
+    assert (stats.cpu() - host).abs().max().item() < 1e-5 * scale, (stats.cpu() - host).abs().max().item() / scale
+    assert (want.cpu() - host).abs().max().item() < 1e-5 * scale
+    # a second launch accumulates on top (the decoder's frame batches share nothing, but the contract is "+=")
+    E.vae_conv(xin, w, b, cout, 3, 3, 3, T, H, W, residual=r, stats=stats, stat_groups=groups)
+    torch.cuda.synchronize()
+    assert (stats.cpu() - 2 * host).abs().max().item() < 2e-5 * scale
+
+
+def test_fused_statistics_leave_the_coder_output_within_rounding(env):
+    """Whole decoder / encoder with the statistics taken from the conv epilogues vs the separate statistics pass."""
+    ov, cfg, sd, vae = env
+    from tokensgen_b200 import vae as V
+    g = torch.Generator().manual_seed(12)
+    z = torch.randn(1, 16, 5, 12, 10, generator=g).bfloat16().cuda()
+    x = (torch.rand(1, 3, 9, 96, 80, generator=g) * 2 - 1).bfloat16().cuda()
+    vae.disable_tiling()
+    outs = {}
+    try:
+        for fused in (True, False):
+            V._FUSED_STATS = fused
+            outs[fused] = (vae.decode(z).sample.clone(), vae.encode(x).latent_dist.parameters.clone())
+    finally:
+        V._FUSED_STATS = True
+    assert rel_l2(outs[True][0], outs[False][0]) < 2e-3 and rel_l2(outs[True][1], outs[False][1]) < 2e-3

@@ -53,7 +53,7 @@ class DpmStepArgs(C.Structure):
                 ("sample", C.c_void_p), ("old_x0", C.c_void_p), ("old_x0_f32", C.c_void_p),
                 ("noise1", C.c_void_p), ("noise2", C.c_void_p), ("coef", C.c_void_p),
                 ("prev_sample", C.c_void_p), ("x0_out", C.c_void_p), ("x0_out_f32", C.c_void_p),
-                ("F", C.c_int), ("chw", C.c_int64), ("mode", C.c_int)]
+                ("F", C.c_int), ("chw", C.c_int64), ("mode", C.c_int), ("guidance_scale2", C.c_float)]
 
 
 class ConvArgs(C.Structure):
@@ -61,7 +61,8 @@ class ConvArgs(C.Structure):
                 ("w", C.c_void_p), ("bias", C.c_void_p), ("Cout", C.c_int), ("Cout_pad", C.c_int),
                 ("kt", C.c_int), ("kh", C.c_int), ("kw", C.c_int), ("stride_hw", C.c_int), ("pad_h0", C.c_int), ("pad_w0", C.c_int),
                 ("T_out", C.c_int), ("H_out", C.c_int), ("W_out", C.c_int), ("residual", C.c_void_p), ("ld_res", C.c_int64),
-                ("y", C.c_void_p), ("ldy", C.c_int64), ("plane_stride", C.c_int64), ("layout", C.c_int)]
+                ("y", C.c_void_p), ("ldy", C.c_int64), ("plane_stride", C.c_int64), ("layout", C.c_int),
+                ("stats", C.c_void_p), ("stat_groups", C.c_int)]
 
 
 class NormArgs(C.Structure):
@@ -384,8 +385,9 @@ def unpatchify(rows: torch.Tensor, B: int, F: int, Cc: int, H: int, W: int, p: i
 
 
 def cfg_dpm_step(noise_pred: torch.Tensor, sample: torch.Tensor, old_x0: Optional[torch.Tensor], noise1: torch.Tensor,
-                 noise2: torch.Tensor, coef: torch.Tensor, guidance_scale: float, mode: int):
-    """noise_pred [n_branches,F,...], sample/noise [F,...] bf16; coef fp32 [F,8] (device).  Returns (prev, x0)."""
+                 noise2: torch.Tensor, coef: torch.Tensor, guidance_scale: float, mode: int, guidance_scale2: float = 0.0):
+    """noise_pred [n_branches,F,...], sample/noise [F,...] bf16; coef fp32 [F,8] (device).  Returns (prev, x0).
+    Three branches (use_separate_guidance): guidance_scale / guidance_scale2 = (g_txt - 1) / (g_img - 1)."""
     lib = load()
     nb, F = noise_pred.shape[0], noise_pred.shape[1]
     chw = sample.numel() // F
@@ -399,6 +401,7 @@ def cfg_dpm_step(noise_pred: torch.Tensor, sample: torch.Tensor, old_x0: Optiona
         a.noise_pred = _bf16_cuda(noise_pred, "noise_pred").data_ptr()
     a.n_branches = nb
     a.guidance_scale = float(guidance_scale)
+    a.guidance_scale2 = float(guidance_scale2)
     a.sample = _bf16_cuda(sample, "sample").data_ptr()
     a.noise1 = _bf16_cuda(noise1, "noise1").data_ptr()
     a.noise2 = _bf16_cuda(noise2, "noise2").data_ptr()
@@ -436,9 +439,11 @@ def queue_shift_renoise(queue: torch.Tensor, x0_queue: Optional[torch.Tensor], n
 def vae_conv(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor], cout: int, kt: int, kh: int, kw: int,
              t_out: int, h_out: int, w_out: int, *, stride: int = 1, pad_h0: int = 1, pad_w0: int = 1,
              residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-             planes_out: Optional[torch.Tensor] = None, plane_stride: int = 0) -> torch.Tensor:
+             planes_out: Optional[torch.Tensor] = None, plane_stride: int = 0, stats: Optional[torch.Tensor] = None,
+             stat_groups: int = 0) -> torch.Tensor:
     """x [T_in,H,W,Cin] (causal frames in front), w2d [Cout_pad, kt*kh*kw*Cin].  Returns channels-last [t_out,h_out,w_out,cout]
-    (or writes channel planes into `planes_out`, a view whose first element is (n=0, t=0, h=0, w=0))."""
+    (or writes channel planes into `planes_out`, a view whose first element is (n=0, t=0, h=0, w=0)).
+    `stats` (zeroed fp64 [2 * stat_groups]): GroupNorm sums of the output accumulated by the epilogue (conv_stats_supported)."""
     lib = load()
     a = ConvArgs()
     T_in, H_in, W_in, Cin = x.shape
@@ -456,9 +461,21 @@ def vae_conv(x: torch.Tensor, w2d: torch.Tensor, bias: Optional[torch.Tensor], c
             out = torch.empty(t_out, h_out, w_out, cout, device=x.device, dtype=torch.bfloat16)
         a.y, a.layout, a.ldy = out.data_ptr(), 0, out.stride(2)
         ret = out
+    if stats is not None:
+        if stats.dtype != torch.float64 or stats.numel() != 2 * stat_groups or not stats.is_cuda:
+            raise TokensGenError("vae_conv: stats must be a CUDA float64 tensor of 2 * stat_groups elements")
+        a.stats, a.stat_groups = stats.data_ptr(), stat_groups
     with _Timed(f"vae_conv[{t_out}x{h_out}x{w_out},{Cin}->{cout},k{kt}{kh}{kw}s{stride}]", 1):
         _check(lib.tg_vae_conv(C.byref(a), _stream()), "tg_vae_conv")
     return ret
+
+
+def conv_stats_supported(cout: int, groups: int) -> bool:
+    """Shapes for which tg_vae_conv can accumulate the consumer GroupNorm's statistics in its epilogue."""
+    if groups <= 0 or groups > 64 or cout % 32 or cout % groups:
+        return False
+    cg = cout // groups
+    return cg in (4, 8, 16) or cg % 32 == 0
 
 
 def vae_group_stats(x: torch.Tensor, groups: int) -> torch.Tensor:

@@ -36,7 +36,48 @@ struct ConvParams {
     int64_t ldy;              // layout 0: channel stride between pixels
     int64_t plane_stride;     // layout 1: elements between channel planes; pixel (t,h,w) at (t*H_out + h)*W_out + w
     int layout;               // 0 channels-last, 1 channel planes
+    // GroupNorm statistics of the OUTPUT, accumulated in the epilogue (replaces the tg_vae_group_stats pass over the tensor the
+    // next GroupNorm / SpatialNorm reads): stats[g] += sum, stats[groups + g] += sum of squares of the bf16-ROUNDED outputs of
+    // group g's Cout / groups channels.  Null = off.  Channels-last layout with Cout % 32 == 0 and 32 % (Cout / groups) == 0 or
+    // (Cout / groups) % 32 == 0 only (checked by the host).
+    double* stats;
+    int stat_groups;
 };
+
+constexpr int CV_MAX_GROUPS = 64;
+
+// Per-chunk GroupNorm partials: v[32] are this pixel's bf16-rounded outputs of channels [n0, n0 + 32); the warp's 32 pixels are
+// summed with a butterfly and lane i adds value i to the CTA's shared fp64 accumulators (sh[g] sums, sh[G + g] squares).
+template <int CG>   // channels per group inside the chunk: 4, 8, 16 or 32 (= the whole chunk belongs to one group)
+__device__ __forceinline__ void conv_chunk_stats(const float (&v)[32], int n0, int cg_total, int groups, double* sh) {
+    constexpr int NG = 32 / CG;
+    float s[NG], q[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        s[g] = 0.f;
+        q[g] = 0.f;
+#pragma unroll
+        for (int i = 0; i < CG; ++i) {
+            s[g] += v[g * CG + i];
+            q[g] = fmaf(v[g * CG + i], v[g * CG + i], q[g]);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+            s[g] += __shfl_xor_sync(0xffffffffu, s[g], m);
+            q[g] += __shfl_xor_sync(0xffffffffu, q[g], m);
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    const int g0 = n0 / cg_total;   // first group of this chunk (CG == 32: the one group the chunk lies in)
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        if (lane == 2 * g) atomicAdd(&sh[g0 + g], double(s[g]));
+        if (lane == 2 * g + 1) atomicAdd(&sh[groups + g0 + g], double(q[g]));
+    }
+}
 
 template <int BLOCK_N>
 struct ConvCfg {
@@ -64,19 +105,24 @@ __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int tile, 
 }
 
 // Epilogue of one accumulator row (one output pixel): BLOCK_N columns starting at output channel nt * BLOCK_N.
+// Called by whole warps (all 32 lanes, `ok` may differ per lane): the statistics path shuffles.
 template <int BLOCK_N>
-__device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int nt, bool ok, int64_t pix) {
+__device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int nt, bool ok, int64_t pix,
+                                                  double* sh_stats) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
             uint32_t r[32];
             tmem_ld32(t_row + c, r);
             tmem_wait_ld();
             const int n0 = nt * BLOCK_N + c;
-            if (!ok || n0 >= p.Cout) continue;
+            if (n0 >= p.Cout) continue;                       // warp-uniform
+            const bool fast = p.layout == 0 && n0 + 32 <= p.Cout;
+            if (!ok && !(fast && p.stats != nullptr)) continue;
             float v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-            if (p.layout == 0 && n0 + 32 <= p.Cout) {
+            if (fast) {
+                if (ok) {
                 if (p.bias != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 8) {
@@ -105,6 +151,23 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
                     o.x = pack_bf16x2(v[i * 8], v[i * 8 + 1]); o.y = pack_bf16x2(v[i * 8 + 2], v[i * 8 + 3]);
                     o.z = pack_bf16x2(v[i * 8 + 4], v[i * 8 + 5]); o.w = pack_bf16x2(v[i * 8 + 6], v[i * 8 + 7]);
                     yp[i] = o;
+                    if (p.stats != nullptr) {   // the statistics are those of the STORED (bf16) tensor, like the separate pass
+                        v[i * 8] = bf16_lo(o.x); v[i * 8 + 1] = bf16_hi(o.x); v[i * 8 + 2] = bf16_lo(o.y); v[i * 8 + 3] = bf16_hi(o.y);
+                        v[i * 8 + 4] = bf16_lo(o.z); v[i * 8 + 5] = bf16_hi(o.z); v[i * 8 + 6] = bf16_lo(o.w); v[i * 8 + 7] = bf16_hi(o.w);
+                    }
+                }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 0.f;   // pixel outside the image: contributes nothing
+                }
+                if (p.stats != nullptr) {
+                    const int cg = p.Cout / p.stat_groups;
+                    switch (cg) {
+                        case 4: conv_chunk_stats<4>(v, n0, cg, p.stat_groups, sh_stats); break;
+                        case 8: conv_chunk_stats<8>(v, n0, cg, p.stat_groups, sh_stats); break;
+                        case 16: conv_chunk_stats<16>(v, n0, cg, p.stat_groups, sh_stats); break;
+                        default: conv_chunk_stats<32>(v, n0, cg, p.stat_groups, sh_stats); break;   // cg % 32 == 0
+                    }
                 }
             } else {
                 // narrow outputs (conv_out: 3 image channels / 32 moment channels) and channel-plane layout
@@ -118,6 +181,20 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
         }
 }
 
+// The CTA's statistics accumulators: zeroed before the tile loop, flushed to p.stats (fp64 atomics) after it.  Called by all
+// 128 epilogue threads (warps 4..7); named barrier 1.
+__device__ __forceinline__ void conv_stats_begin(const ConvParams& p, double* sh) {
+    if (p.stats == nullptr) return;
+    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128) sh[i] = 0.0;
+    named_bar_sync(1, 128);
+}
+__device__ __forceinline__ void conv_stats_end(const ConvParams& p, double* sh) {
+    if (p.stats == nullptr) return;
+    named_bar_sync(1, 128);
+    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128)
+        if (sh[i] != 0.0) atomicAdd(&p.stats[i], sh[i]);
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1)
 conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -125,6 +202,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     using Cfg = ConvCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
+    __shared__ double sh_stats[2 * CV_MAX_GROUPS];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -229,6 +307,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
         const int ew = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        conv_stats_begin(p, sh_stats);
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int nt, wt, ht, t;
             conv_tile_coords(p, tile, nt, wt, ht, t);
@@ -241,7 +320,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 const bool ok = h < p.H_out && w < p.W_out;
                 const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
                 const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + half * BLOCK_N);
-                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix);
+                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix, sh_stats);
             }
             tc_fence_before();
             __syncwarp();
@@ -251,6 +330,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
                 acc_phase ^= 1u;
             }
         }
+        conv_stats_end(p, sh_stats);
     }
 
     tc_fence_before();
@@ -286,6 +366,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     using Cfg = Conv2Cfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
+    __shared__ double sh_stats[2 * CV_MAX_GROUPS];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -405,6 +486,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         const int ew = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        conv_stats_begin(p, sh_stats);
         for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
             int nt, wt, ht, t;
             my_coords(tile, nt, wt, ht, t);
@@ -417,7 +499,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 const bool ok = t < p.T_out && h < p.H_out && w < p.W_out;
                 const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
                 const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + half * BLOCK_N);
-                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix);
+                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix, sh_stats);
             }
             tc_fence_before();
             __syncwarp();
@@ -427,6 +509,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 acc_phase ^= 1u;
             }
         }
+        conv_stats_end(p, sh_stats);
     }
 
     tc_fence_before();
@@ -466,6 +549,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     constexpr int BLOCK_N = 128;
     constexpr int STAGES = C3_STAGES;
     extern __shared__ uint8_t smem_raw[];
+    __shared__ double sh_stats[2 * CV_MAX_GROUPS];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * C3_STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -588,6 +672,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
         const int ew = warp & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        conv_stats_begin(p, sh_stats);
         for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
             int nt, wt, ht, t;
             my_coords(tile, nt, wt, ht, t);
@@ -599,7 +684,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 const bool ok = t < p.T_out && h < p.H_out && w < p.W_out;
                 const int64_t pix = (int64_t(t) * p.H_out + h) * p.W_out + w;
                 const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * 2 * BLOCK_N + row * BLOCK_N);
-                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix);
+                conv_epilogue_row<BLOCK_N>(p, t_row, nt, ok, pix, sh_stats);
             }
             tc_fence_before();
             __syncwarp();
@@ -609,6 +694,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 acc_phase ^= 1u;
             }
         }
+        conv_stats_end(p, sh_stats);
     }
 
     tc_fence_before();
@@ -688,6 +774,15 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
         return fail(-10, "vae_conv: y must be 16-byte aligned");
     if (a->residual != nullptr && a->Cout % 32 == 0 && ((reinterpret_cast<uintptr_t>(a->residual) & 15) || a->ld_res % 8 != 0))
         return fail(-10, "vae_conv: residual must be 16-byte aligned with ld_res %% 8 == 0");
+    if (a->stats != nullptr) {
+        const int G = a->stat_groups;
+        if (a->layout != 0 || G <= 0 || G > CV_MAX_GROUPS || a->Cout % 32 != 0 || a->Cout % G != 0)
+            return fail(-11, "vae_conv: epilogue statistics need layout 0, Cout %% 32 == 0 and 1 <= stat_groups <= %d dividing Cout", CV_MAX_GROUPS);
+        const int cg = a->Cout / G;
+        if (!(cg == 4 || cg == 8 || cg == 16 || cg % 32 == 0))
+            return fail(-11, "vae_conv: epilogue statistics need Cout / stat_groups in {4, 8, 16} or a multiple of 32 (got %d)", cg);
+        if (reinterpret_cast<uintptr_t>(a->stats) & 7) return fail(-11, "vae_conv: stats must be 8-byte aligned");
+    }
     const int s = a->stride_hw;
     CUtensorMap tx, tw;
     {
@@ -717,6 +812,8 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
             p.ldy = a->ldy;
             p.plane_stride = a->plane_stride;
             p.layout = a->layout;
+            p.stats = a->stats;
+            p.stat_groups = a->stat_groups;
             return launch_conv3(tx, tw, p, static_cast<cudaStream_t>(stream));
         }
     }
@@ -749,6 +846,8 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     p.ldy = a->ldy;
     p.plane_stride = a->plane_stride;
     p.layout = a->layout;
+    p.stats = a->stats;
+    p.stat_groups = a->stat_groups;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (pair) return bn == 256 ? launch_conv2<256>(tx, tw, p, st) : launch_conv2<128>(tx, tw, p, st);
     return bn == 128 ? launch_conv<128>(tx, tw, p, st) : launch_conv<64>(tx, tw, p, st);

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(const __grid_constant
     const int64_t branch_stride = int64_t(a.F) * a.chw;
     for (int64_t vi = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; vi < nvec; vi += int64_t(gridDim.x) * blockDim.x) {
         const int64_t off = frame_off + vi * 8;
-        float u[8], c[8], smp[8], nz[8], old[8], mo[8], x0[8], ps[8];
+        float u[8], c[8], c3[8], smp[8], nz[8], old[8], mo[8], x0[8], ps[8];
         if (a.noise_pred_f32 != nullptr) {
             const float4 o0 = *reinterpret_cast<const float4*>(a.noise_pred_f32 + off);
             const float4 o1 = *reinterpret_cast<const float4*>(a.noise_pred_f32 + off + 4);
@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(const __grid_constant
         }
         unpack8(*reinterpret_cast<const uint4*>(a.sample + off), smp);
         unpack8(*reinterpret_cast<const uint4*>((second ? a.noise2 : a.noise1) + off), nz);
-        if (a.n_branches == 2) unpack8(*reinterpret_cast<const uint4*>(a.noise_pred + branch_stride + off), c);
+        if (a.n_branches >= 2) unpack8(*reinterpret_cast<const uint4*>(a.noise_pred + branch_stride + off), c);
+        if (a.n_branches == 3) unpack8(*reinterpret_cast<const uint4*>(a.noise_pred + 2 * branch_stride + off), c3);
         if (second) {
             if (a.mode == TG_DPM_BF16_CHAIN) {
                 unpack8(*reinterpret_cast<const uint4*>(a.old_x0 + off), old);
@@ -329,7 +330,14 @@ __global__ void __launch_bounds__(256) cfg_dpm_step_kernel(const __grid_constant
             // (cogvideo_sampling_mp_fifo.py:531-533; scheduling_dpm_cogvideox.py:439-463)
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                mo[j] = (a.n_branches == 2) ? rb(u[j] + rb(a.guidance_scale * rb(c[j] - u[j]))) : u[j];
+                if (a.n_branches == 3) {
+                    // use_separate_guidance (cogvideo_sampling_mp_fifo.py:528-530): u = uncond_txt, c = uncond_img, c3 = txt_img;
+                    // txt_img + (g - 1) * (txt_img - uncond_txt) + (g_img - 1) * (txt_img - uncond_img), left to right
+                    const float t1 = rb(c3[j] + rb(a.guidance_scale * rb(c3[j] - u[j])));
+                    mo[j] = rb(t1 + rb(a.guidance_scale2 * rb(c3[j] - c[j])));
+                } else {
+                    mo[j] = (a.n_branches == 2) ? rb(u[j] + rb(a.guidance_scale * rb(c[j] - u[j]))) : u[j];
+                }
                 x0[j] = rb(rb(sa * smp[j]) - rb(sb * mo[j]));
                 const float mz = rb(mn * nz[j]);
                 if (!second) {
@@ -516,7 +524,9 @@ extern "C" int tg_cfg_dpm_step(const tg_dpm_step_args* a, void* stream) {
         return fail(-1, "cfg_dpm_step: null pointer");
     if (a->noise_pred_f32 && (a->noise_pred || a->n_branches != 1 || a->mode != TG_DPM_BASE_CHAIN))
         return fail(-6, "cfg_dpm_step: noise_pred_f32 is for the base chain with n_branches = 1 and no bf16 noise_pred");
-    if (a->n_branches != 1 && a->n_branches != 2) return fail(-2, "cfg_dpm_step: n_branches must be 1 or 2");
+    if (a->n_branches < 1 || a->n_branches > 3) return fail(-2, "cfg_dpm_step: n_branches must be 1, 2 or 3");
+    if (a->n_branches == 3 && a->mode != TG_DPM_BF16_CHAIN)
+        return fail(-2, "cfg_dpm_step: three guidance branches are the FIFO worker's bf16 chain only (the base stage guides in fp32 on the host side)");
     if (a->F <= 0 || a->chw <= 0 || a->chw % 8 != 0) return fail(-3, "cfg_dpm_step: F=%d chw=%lld (chw %% 8 == 0)", a->F, (long long)a->chw);
     if (a->mode == TG_DPM_BF16_CHAIN) {
         if (a->old_x0_f32 || a->x0_out_f32) return fail(-4, "cfg_dpm_step: bf16 chain takes bf16 x0 buffers");

@@ -318,7 +318,7 @@ class VipBook:
 
 
 def make_step_fn(transformer, scheduler, prompt_embeds: torch.Tensor, image_rotary_emb, vip: Optional[VipBook],
-                 guidance_scale: float, head_dim: int = 64, noise_override=None):
+                 guidance_scale: float, head_dim: int = 64, noise_override=None, guidance_scale_img: Optional[float] = None):
     """fifo_onestep_per_gpu (:408-579) for one window on this rank's GPU: DiT forward (CFG pair, per-frame timesteps)
     then the fused CFG + per-frame DPM step."""
     from .rope import get_3d_rotary_pos_embed_v2
@@ -336,7 +336,8 @@ def make_step_fn(transformer, scheduler, prompt_embeds: torch.Tensor, image_rota
         noise_pred = transformer(hidden_states=torch.cat([latents] * B), encoder_hidden_states=prompt_embeds, timestep=ts,
                                  image_rotary_emb=image_rotary_emb, return_dict=False, **kw)[0]
         return scheduler.window_step(noise_pred, latents, old_x0, t, prev_t, next_t, guidance_scale, generator=gen,
-                                     noise=None if noise_override is None else noise_override(w))
+                                     noise=None if noise_override is None else noise_override(w),
+                                     guidance_scale_img=guidance_scale_img if B == 3 else None)
 
     return step
 
@@ -491,8 +492,10 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
     sp = dict(base_output.sampling_params or {})
     if sp.get("use_sliding_window_embedding"):
         raise NotImplementedError("use_sliding_window_embedding calls an undefined function in the reference (:150)")
-    if base_output.use_separate_guidance or base_output.use_dynamic_cfg:
-        raise NotImplementedError("the FIFO worker of the shipped configs runs plain two-branch CFG")
+    if base_output.use_dynamic_cfg:
+        raise NotImplementedError("use_dynamic_cfg is off in the FIFO stage of both shipped configs (infer_cogvideo_mp_fifo.py:316)")
+    if base_output.use_separate_guidance and base_output.prompt_embeds.shape[0] != 3:
+        raise ValueError("use_separate_guidance expects the three-branch bundle [uncond_txt, uncond_img, txt_img]")
     if base_output.cache_idx:
         raise NotImplementedError("cache_idx (debug dumps of intermediate queue slots) is empty in the shipped configs")
     nf, T = base_output.nf_per_chunk, base_output.num_inference_steps
@@ -508,7 +511,8 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
     # (tests/test_fifo_stage_gpu.py feeds the draws of the reference-sampler golden); default: the (seed, iteration, rank) streams
     step_fn = make_step_fn(pipe.transformer, pipe.scheduler, base_output.prompt_embeds, base_output.image_rotary_emb, vip,
                            base_output.guidance_scale if base_output.do_classifier_free_guidance else 1.0,
-                           noise_override=kwargs.get("window_noise"))
+                           noise_override=kwargs.get("window_noise"),
+                           guidance_scale_img=base_output.guidance_scale_img if base_output.use_separate_guidance else None)
     shift_latents = make_shift_fn(pipe.scheduler, noise_override=kwargs.get("shift_noise"))
 
     def shift(q, gen):

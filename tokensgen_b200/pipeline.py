@@ -369,8 +369,6 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
                  vip_scale=1.0, sampling_mode: str = None, sampling_params: Dict[str, Any] = None, cache_idx=(),
                  video_ipadapter_start_frame_idx: Optional[int] = 1000, cfg_parallel_group=None,
                  sequence_parallel_group=None):
-        if use_separate_guidance:
-            raise NotImplementedError("use_separate_guidance (3-branch CFG) is off in both shipped configs (edit.yaml:11, gen.yaml)")
         if callback_on_step_end is not None:
             raise NotImplementedError("step callbacks are not used on the reproduced path")
         nf_per_chunk = num_frames_per_chunk
@@ -399,8 +397,12 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         prompt_embeds, negative_prompt_embeds = self.encode_prompt(
             prompt, negative_prompt, do_cfg, num_videos_per_prompt=1, prompt_embeds=prompt_embeds,
             negative_prompt_embeds=negative_prompt_embeds, max_sequence_length=max_sequence_length, device=device)
+        use_separate_guidance = bool(use_separate_guidance) and do_cfg
         if do_cfg:
-            prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
+            if use_separate_guidance:   # :1026-1027 — branches (uncond_txt, uncond_img, txt_img)
+                prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds, prompt_embeds], dim=0)
+            else:
+                prompt_embeds = torch.cat([negative_prompt_embeds, prompt_embeds], dim=0)
         prompt_embeds = prompt_embeds.to(torch.bfloat16)
 
         timesteps, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, device, timesteps)
@@ -432,7 +434,9 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
         fifo_old: List[Optional[torch.Tensor]] = []
         old_x0 = None
         ts = [int(t) for t in timesteps]
-        B = 2 if do_cfg else 1
+        B = (3 if use_separate_guidance else 2) if do_cfg else 1
+        if use_separate_guidance and cfg_parallel_group is not None:
+            cfg_parallel_group = None   # the two-rank split is for the two-branch bundle; three branches run on one rank
         # CFG-parallel base stage: the two guidance branches are independent until they are combined, so with
         # `cfg_parallel_group` (two ranks that call this method with identical arguments) each rank runs ONE branch through the
         # DiT (B = 1) and the pair all-gathers the 2.25 MB predictions over NVLink; everything else (latents, scheduler
@@ -476,11 +480,15 @@ class MPFIFOVideoIPAdapterCogVideoXPipeline:
                                               image_rotary_emb=image_rotary_emb, attention_kwargs=attention_kwargs,
                                               return_dict=False, **kw)[0]
                 noise_pred = noise_pred.float()
-            g = guidance_scale
+            g, g_img = guidance_scale, guidance_scale_img
             if use_dynamic_cfg:
-                g = 1 + guidance_scale * ((1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2)
+                ramp = (1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2
+                g, g_img = 1 + guidance_scale * ramp, 1 + guidance_scale_img * ramp
                 self._guidance_scale = g
-            if do_cfg:
+            if do_cfg and use_separate_guidance:     # :1261-1263
+                ut, ui, a = noise_pred.chunk(3)
+                noise_pred = a + (g - 1) * (a - ut) + (g_img - 1) * (a - ui)
+            elif do_cfg:
                 u, c = noise_pred.chunk(2)
                 noise_pred = u + g * (c - u)
             prev_t = ts[i + 1] if i + 1 < len(ts) else -1

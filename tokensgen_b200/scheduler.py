@@ -160,9 +160,12 @@ class CogVideoXDPMScheduler:
 
     def window_step(self, noise_pred: torch.Tensor, latents: torch.Tensor, old_x0: Sequence[Optional[torch.Tensor]],
                     t: Sequence[int], prev_t: Sequence[int], next_t: Sequence[int], guidance_scale: float,
-                    noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, generator=None):
-        """noise_pred [2,F,C,H,W] (uncond, cond) or [1,F,...]; latents [1,F,C,H,W] bf16; old_x0: F entries ([1,1,C,H,W] or
-        None); t/prev_t/next_t: the window's rows of the FIFO timestep tables (next_t <= 0 means no history step).
+                    noise: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, generator=None,
+                    guidance_scale_img: Optional[float] = None):
+        """noise_pred [2,F,C,H,W] (uncond, cond), [1,F,...], or [3,F,...] (uncond_txt, uncond_img, txt_img — the reference's
+        use_separate_guidance, cogvideo_sampling_mp_fifo.py:528-530, which needs `guidance_scale_img`); latents [1,F,C,H,W]
+        bf16; old_x0: F entries ([1,1,C,H,W] or None); t/prev_t/next_t: the window's rows of the FIFO timestep tables
+        (next_t <= 0 means no history step).
         Returns (latents_out [1,F,...], [x0_j [1,1,...]] * F) exactly as the reference worker's loop does."""
         F = latents.shape[1]
         dev = latents.device
@@ -182,9 +185,14 @@ class CogVideoXDPMScheduler:
             if rows[j][7]:
                 old[j].copy_(old_x0[j].reshape(frame_shape))
         nb = noise_pred.shape[0]
+        g1, g2 = float(guidance_scale), 0.0
+        if nb == 3:
+            if guidance_scale_img is None:
+                raise ValueError("three guidance branches need guidance_scale_img")
+            g1, g2 = float(guidance_scale) - 1.0, float(guidance_scale_img) - 1.0     # python doubles, like the reference
         prev, x0 = E.cfg_dpm_step(noise_pred.reshape(nb, F, -1).contiguous(), latents.reshape(F, -1).contiguous(),
                                   old.view(F, -1), n1.reshape(F, -1).contiguous(), n2.reshape(F, -1).contiguous(), coef,
-                                  float(guidance_scale), E.DPM_BF16_CHAIN)
+                                  g1, E.DPM_BF16_CHAIN, guidance_scale2=g2)
         x0 = x0.view((F, 1, 1) + tuple(frame_shape))
         return prev.view(latents.shape), [x0[j] for j in range(F)]
 

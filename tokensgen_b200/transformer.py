@@ -426,7 +426,16 @@ class CogVideoXBlock(nn.Module):
         in the order norm1(6d) | norm2(6d) | vip_norm1(3d) | vip_norm2(3d)."""
         d = self.dim
         rows = E.rows_local(rowmap)  # all rows, or this rank's shard (sequence parallel)
-        proc = self.attn1.processor if self.use_vip else None
+        installed = self.attn1.processor
+        if type(installed) not in (CogVideoXAttnProcessor2_0, VideoIPAdapterCogVideoXAttnProcessor2_0) or \
+                isinstance(installed, VideoIPAdapterCogVideoXAttnProcessor2_0) != self.use_vip:
+            # the fused engine runs the two built-in processors' kernel sequence on the resident stream; a processor installed
+            # with Attention.set_processor is honoured by Attention.forward (the plugin API), never silently replaced here
+            raise E.TokensGenError(
+                f"attn1.processor is {type(installed).__name__}: the fused model forward only executes the built-in "
+                "CogVideoXAttnProcessor2_0 / VideoIPAdapterCogVideoXAttnProcessor2_0; call the block's modules through "
+                "Attention.forward to run a custom processor")
+        proc = installed if self.use_vip else None
         X2, Y2 = bufs.X.view(B * rows, d), bufs.Y.view(B * rows, d)
         c = lambda i: ada[:, col0 + i * d: col0 + (i + 1) * d]
         vip = self.use_vip and rowmap.n_vip > 0

@@ -209,7 +209,24 @@ class CogVideoXDecoder3D(nn.Module):
 
 
 # =================================================================================================== engine (channels-last)
-def _causal_conv(mod: CogVideoXCausalConv3d, buf: torch.Tensor, T: int, cout: int, residual=None, planes_out=None, plane_stride=0):
+class _Act:
+    """A channels-last activation [T, H, W, C] together with the GroupNorm sums of it that the producing convolution's epilogue
+    accumulated (`sums` for `groups` groups; None when the producer could not, e.g. narrow widths) — so the consumer norm does
+    not read the tensor once more just for its statistics (tg_vae_group_stats)."""
+    __slots__ = ("x", "sums", "groups")
+
+    def __init__(self, x, sums=None, groups=0):
+        self.x, self.sums, self.groups = x, sums, groups
+
+
+def _stats_for(cout: int, groups: int, device):
+    if groups and E.conv_stats_supported(cout, groups):
+        return torch.zeros(2 * groups, device=device, dtype=torch.float64)
+    return None
+
+
+def _causal_conv(mod: CogVideoXCausalConv3d, buf: torch.Tensor, T: int, cout: int, residual=None, planes_out=None, plane_stride=0,
+                 stats=None, stat_groups=0):
     """buf: [kt-1+T, H, W, Cin_pad]; frames [kt-1, kt-1+T) already hold this call's input.  Fills the causal frames from the conv
     cache (or with copies of the first frame, autoencoder_kl_cogvideox.py:120-127), convolves, saves the new cache (:139)."""
     kt = mod.time_kernel_size
@@ -223,7 +240,7 @@ def _causal_conv(mod: CogVideoXCausalConv3d, buf: torch.Tensor, T: int, cout: in
                 buf[i].copy_(buf[kt - 1])
     y = E.vae_conv(buf, w, b, cout, kt, mod.conv.kernel_size[1], mod.conv.kernel_size[2], T, H, W,
                    pad_h0=mod.conv.kernel_size[1] // 2, pad_w0=mod.conv.kernel_size[2] // 2, residual=residual,
-                   planes_out=planes_out, plane_stride=plane_stride)
+                   planes_out=planes_out, plane_stride=plane_stride, stats=stats, stat_groups=stat_groups)
     if kt > 1:
         mod.conv_cache = buf[T:T + kt - 1].clone()
     return y
@@ -264,37 +281,61 @@ class _ZqTables:
         return [conv._pack.linear(conv.conv, rows).view(Tz, hz, wz, -1) for conv in (norm.conv_y, norm.conv_b)]
 
 
-def _norm_silu_into(norm, x: torch.Tensor, out: torch.Tensor, zq: Optional[_ZqTables]):
+def _groups(norm) -> int:
+    return (norm.norm_layer if isinstance(norm, CogVideoXSpatialNorm3D) else norm).num_groups
+
+
+def _norm_silu_into(norm, x, out: torch.Tensor, zq: Optional[_ZqTables]):
+    """x: a channels-last tensor, or an _Act whose producer already accumulated this norm's group sums."""
     if isinstance(norm, CogVideoXSpatialNorm3D):
         gn = norm.norm_layer
         zy, zb = zq.tables(norm)
     else:
         gn, zy, zb = norm, None, None
-    sums = E.vae_group_stats(x, gn.num_groups)
+    if isinstance(x, _Act):
+        sums = x.sums if (x.sums is not None and x.groups == gn.num_groups) else None
+        x = x.x
+    else:
+        sums = None
+    if sums is None:
+        sums = E.vae_group_stats(x, gn.num_groups)
     E.vae_norm_act(x, sums, gn.num_groups, gn.eps, gn.weight, gn.bias, out, zy, zb, silu=True)
 
 
-def _resnet(blk: CogVideoXResnetBlock3D, x: torch.Tensor, zq: Optional[_ZqTables]) -> torch.Tensor:
-    """CogVideoXResnetBlock3D.forward (:276-309): norm1 -> SiLU -> conv1 -> norm2 -> SiLU -> conv2 (+ shortcut(x))."""
+_FUSED_STATS = True   # GroupNorm statistics in the producing convolution's epilogue (False: the separate statistics pass)
+
+
+def _resnet(blk: CogVideoXResnetBlock3D, xa, zq: Optional[_ZqTables], next_groups: int = 0) -> "_Act":
+    """CogVideoXResnetBlock3D.forward (:276-309): norm1 -> SiLU -> conv1 -> norm2 -> SiLU -> conv2 (+ shortcut(x)).
+    `xa`: tensor or _Act; returns an _Act carrying the sums the NEXT norm (`next_groups` groups) needs."""
+    x = xa.x if isinstance(xa, _Act) else xa
     T, H, W, cin = x.shape
     cout = blk.out_channels
     buf = torch.empty(T + 2, H, W, cin, device=x.device, dtype=torch.bfloat16)
-    _norm_silu_into(blk.norm1, x, buf[2:], zq)
-    h = _causal_conv(blk.conv1, buf, T, cout)
+    _norm_silu_into(blk.norm1, xa, buf[2:], zq)
+    g2 = _groups(blk.norm2)
+    st1 = _stats_for(cout, g2, x.device) if _FUSED_STATS else None
+    h = _causal_conv(blk.conv1, buf, T, cout, stats=st1, stat_groups=g2)
     buf2 = torch.empty(T + 2, H, W, cout, device=x.device, dtype=torch.bfloat16)
-    _norm_silu_into(blk.norm2, h, buf2[2:], zq)
+    _norm_silu_into(blk.norm2, _Act(h, st1, g2), buf2[2:], zq)
     if cin != cout:
         res = blk._sc_pack.linear(blk.conv_shortcut, x.view(-1, cin)).view(T, H, W, cout)
     else:
         res = x
-    return _causal_conv(blk.conv2, buf2, T, cout, residual=res)
+    st2 = _stats_for(cout, next_groups, x.device) if _FUSED_STATS else None
+    y = _causal_conv(blk.conv2, buf2, T, cout, residual=res, stats=st2, stat_groups=next_groups)
+    return _Act(y, st2, next_groups)
 
 
-def _conv2d(mod, x: torch.Tensor, stride: int, pad0: int) -> torch.Tensor:
+def _conv2d(mod, x: torch.Tensor, stride: int, pad0: int, next_groups: int = 0) -> "_Act":
     T, H, W, c = x.shape
     w, b = mod._pack.get(mod.conv)
     h_out, w_out = (H // 2, W // 2) if stride == 2 else (H, W)
-    return E.vae_conv(x, w, b, mod.conv.out_channels, 1, 3, 3, T, h_out, w_out, stride=stride, pad_h0=pad0, pad_w0=pad0)
+    cout = mod.conv.out_channels
+    st = _stats_for(cout, next_groups, x.device) if _FUSED_STATS else None
+    y = E.vae_conv(x, w, b, cout, 1, 3, 3, T, h_out, w_out, stride=stride, pad_h0=pad0, pad_w0=pad0, stats=st,
+                   stat_groups=next_groups)
+    return _Act(y, st, next_groups)
 
 
 class DiagonalGaussianDistribution:
@@ -398,19 +439,24 @@ class AutoencoderKLCogVideoX(nn.Module):
         C, T, H, W = x_cf.shape
         buf = torch.empty(T + 2, H, W, 64, device=x_cf.device, dtype=torch.bfloat16)
         E.vae_to_channels_last(x_cf, 64, buf[2:])
-        h = _causal_conv(enc.conv_in, buf, T, enc.conv_in.conv.out_channels)
+        G = _groups(enc.norm_out)      # every GroupNorm of a coder has the same group count (norm_num_groups)
+        c0 = enc.conv_in.conv.out_channels
+        st = _stats_for(c0, G, x_cf.device) if _FUSED_STATS else None
+        h = _Act(_causal_conv(enc.conv_in, buf, T, c0, stats=st, stat_groups=G), st, G)
         for blk in enc.down_blocks:
-            for r in blk.resnets:
-                h = _resnet(r, h, None)
+            for i, r in enumerate(blk.resnets):
+                last = i == len(blk.resnets) - 1 and blk.downsamplers is not None
+                h = _resnet(r, h, None, 0 if last else G)      # a down-sampler, not a norm, reads the block's last output
             if blk.downsamplers is not None:
                 d = blk.downsamplers[0]
+                x = h.x
                 if d.compress_time:
-                    h = E.vae_avgpool_time(h)
-                h = _conv2d(d, h, 2, 0)
+                    x = E.vae_avgpool_time(x)
+                h = _conv2d(d, x, 2, 0, G)
         for r in enc.mid_block.resnets:
-            h = _resnet(r, h, None)
-        T2, H2, W2, c = h.shape
-        buf = torch.empty(T2 + 2, H2, W2, c, device=h.device, dtype=torch.bfloat16)
+            h = _resnet(r, h, None, G)
+        T2, H2, W2, c = h.x.shape
+        buf = torch.empty(T2 + 2, H2, W2, c, device=h.x.device, dtype=torch.bfloat16)
         _norm_silu_into(enc.norm_out, h, buf[2:], None)
         _causal_conv(enc.conv_out, buf, T2, enc.conv_out.conv.out_channels, planes_out=out_planes, plane_stride=plane_stride)
         return T2
@@ -429,18 +475,22 @@ class AutoencoderKLCogVideoX(nn.Module):
         buf = torch.empty(T + 2, H, W, 64, device=z_cf.device, dtype=torch.bfloat16)
         E.vae_to_channels_last(z_cf, 64, buf[2:])
         zq = _ZqTables(buf[2:], self._spatial_norms())
-        h = _causal_conv(dec.conv_in, buf, T, dec.conv_in.conv.out_channels)
+        G = _groups(dec.norm_out)
+        c0 = dec.conv_in.conv.out_channels
+        st = _stats_for(c0, G, z_cf.device) if _FUSED_STATS else None
+        h = _Act(_causal_conv(dec.conv_in, buf, T, c0, stats=st, stat_groups=G), st, G)
         # buf[2:] (zq) stays alive and unmodified: the conv only rewrites the two causal frames in front of it
         for r in dec.mid_block.resnets:
-            h = _resnet(r, h, zq)
+            h = _resnet(r, h, zq, G)
         for blk in dec.up_blocks:
-            for r in blk.resnets:
-                h = _resnet(r, h, zq)
+            for i, r in enumerate(blk.resnets):
+                last = i == len(blk.resnets) - 1 and blk.upsamplers is not None
+                h = _resnet(r, h, zq, 0 if last else G)        # an up-sampler, not a norm, reads the block's last output
             if blk.upsamplers is not None:
                 u = blk.upsamplers[0]
-                h = _conv2d(u, E.vae_upsample(h, u.compress_time), 1, 1)
-        T2, H2, W2, c = h.shape
-        buf2 = torch.empty(T2 + 2, H2, W2, c, device=h.device, dtype=torch.bfloat16)
+                h = _conv2d(u, E.vae_upsample(h.x, u.compress_time), 1, 1, G)
+        T2, H2, W2, c = h.x.shape
+        buf2 = torch.empty(T2 + 2, H2, W2, c, device=h.x.device, dtype=torch.bfloat16)
         _norm_silu_into(dec.norm_out, h, buf2[2:], zq)
         _causal_conv(dec.conv_out, buf2, T2, dec.conv_out.conv.out_channels, planes_out=out_planes, plane_stride=plane_stride)
         return T2
