@@ -296,7 +296,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     E.load()
-    for key in ("attn_spec", "attn_emu"):      # developer A/B knobs (dev builds of the library only; see profiles/r02_ab_*.md)
+    for key in ("attn_spec", "attn_emu"):      # A/B knobs of the DEVELOPER build only (TG_LIB_PATH=.../libtokensgen_b200_dev.so)
         if os.environ.get("TG_" + key.upper()) is not None:
             E.set_tuning(key, int(os.environ["TG_" + key.upper()]))
 

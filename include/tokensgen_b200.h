@@ -7,7 +7,8 @@
  *
  * Conventions
  *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in `_host`.
- *   - the caller owns every buffer (including workspaces); the library allocates nothing.
+ *   - the caller owns every buffer; the library allocates nothing and keeps no state between calls except a mutex-guarded
+ *     cache of CUtensorMap descriptors keyed by (pointer, shape).
  *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no internal synchronisation,
  *     so every call is CUDA-graph capturable.
  *   - return 0 = ok; negative = argument error (nothing was launched); positive = cudaError_t / CUresult.
@@ -33,10 +34,13 @@ typedef uint16_t tg_bf16; /* raw bfloat16 bits */
 
 int tg_version(void);
 const char* tg_last_error(void);
-/* Developer tuning knobs (process-wide, not thread-safe; defaults are the shipped configuration):
- *   "attn_impl" 1|2 : attention kernel generation;  "attn_emu" 0..4 : exponentials per 8 evaluated by polynomial on the
- *   FMA pipe instead of MUFU.EX2 (tg_attn_fwd).  Returns 0, or -2 for an unknown key. */
-int tg_set_tuning(const char* key, int value);
+/* There are no process-wide settings: the shipped library has one fixed kernel configuration.  (A developer build,
+ * `python -m tokensgen_b200.build --dev` -> libtokensgen_b200_dev.so, additionally exports tg_set_tuning / tg_set_gemm_impl /
+ * tg_set_conv_impl / tg_debug_attn_trace for the A/B tools under tools/; they are not part of this ABI.)
+ *
+ * Workspaces: NO entry point needs hidden scratch memory.  Every intermediate an operation needs is an explicit argument
+ * (`scratch` of tg_time_embedding, the `sums` / `stats` arrays of the GroupNorm statistics, the output tensors), so there is
+ * no tg_*_workspace_bytes query: sizes follow from the documented shapes. */
 
 /* Row layout of the residual stream, shared by the fused epilogues:
  * row r of a batch is text if r < n_text, video if r < n_text + n_video (frame = (r - n_text) / hw), else vip. */

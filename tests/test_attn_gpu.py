@@ -86,17 +86,21 @@ def test_speculative_reference_overflow_takes_the_exact_redo(nq, nkv, top):
     q, k, v = _steep(1, 2, nq, nkv, top, seed=nq)
     ref = ref_attn(q, k, v)
     outs = {}
+    modes = (1, 0) if E.has_tuning() else (1,)      # the exact-only mode is a knob of the developer build
     try:
-        for spec in (1, 0):
-            E.set_tuning("attn_spec", spec)
+        for spec in modes:
+            if E.has_tuning():
+                E.set_tuning("attn_spec", spec)
             out = torch.full((1, nq, 128), 7.0, device="cuda", dtype=torch.bfloat16)
             E.attn_fwd(q, k, v, out)
             torch.cuda.synchronize()
             outs[spec] = out
     finally:
-        E.set_tuning("attn_spec", 1)
+        if E.has_tuning():
+            E.set_tuning("attn_spec", 1)
     assert torch.isfinite(outs[1].float()).all()
-    assert torch.equal(outs[1], outs[0])
+    if 0 in outs:
+        assert torch.equal(outs[1], outs[0])
     assert rel_l2(outs[1].float(), ref) < 5e-3
 
 
@@ -115,9 +119,11 @@ def test_speculative_redo_in_accumulate_and_pair_modes():
     k2 = k2.bfloat16()
     scale2 = 0.6015625
     res = {}
+    modes = (1, 0) if E.has_tuning() else (1,)
     try:
-        for spec in (1, 0):
-            E.set_tuning("attn_spec", spec)
+        for spec in modes:
+            if E.has_tuning():
+                E.set_tuning("attn_spec", spec)
             a = torch.zeros(B, rows, H * 64, device="cuda", dtype=torch.bfloat16)
             E.attn_fwd(q, k, v, a, out_row0=0)
             E.attn_fwd(q2, k2, v2, a, q_row0=0, q_rows=n_tv, kv_row0=n_tv, kv_rows=n_vip, out_row0=0, accumulate=True, out_scale=scale2)
@@ -126,14 +132,16 @@ def test_speculative_redo_in_accumulate_and_pair_modes():
             torch.cuda.synchronize()
             res[spec] = (a, b)
     finally:
-        E.set_tuning("attn_spec", 1)
+        if E.has_tuning():
+            E.set_tuning("attn_spec", 1)
     ref = ref_attn(q, k, v) + scale2 * ref_attn(q2[:, :, :n_tv], k2[:, :, n_tv:], v2[:, :, n_tv:])
-    for spec in (1, 0):
+    for spec in modes:
         a, b = res[spec]
         assert torch.equal(a, b), spec
         assert rel_l2(b[:, :n_tv].float(), ref) < 5e-3, spec
     # pass 0 (benign) ran speculatively the first time and exactly in the redo: the two modes differ only by rounding there
-    assert rel_l2(res[1][1][:, :n_tv].float(), res[0][1][:, :n_tv].float()) < 5e-3
+    if 0 in res:
+        assert rel_l2(res[1][1][:, :n_tv].float(), res[0][1][:, :n_tv].float()) < 5e-3
 
 
 def test_speculative_and_exact_modes_agree_on_ordinary_inputs():
@@ -141,6 +149,8 @@ def test_speculative_and_exact_modes_agree_on_ordinary_inputs():
     g = torch.Generator(device="cuda").manual_seed(5)
     q, k, v = (torch.randn(2, 4, 1000, 64, generator=g, device="cuda").bfloat16() for _ in range(3))
     ref = ref_attn(q, k, v)
+    if not E.has_tuning():
+        pytest.skip("exact-only mode is a knob of the developer build (TG_LIB_PATH=.../libtokensgen_b200_dev.so)")
     errs = {}
     try:
         for spec in (1, 0):

@@ -80,7 +80,6 @@ _VP, _I, _I64, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SYMBOLS = {
     "tg_version": (C.c_int, []),
     "tg_last_error": (C.c_char_p, []),
-    "tg_set_tuning": (C.c_int, [C.c_char_p, C.c_int]),
     "tg_time_embedding": (C.c_int, [_VP, _I, _I, _I, _I, _F, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "tg_ln_modulate": (C.c_int, [_VP, _VP, _I, _I, C.POINTER(RowMap), _VP, _VP, _VP, _VP, _F, _VP, _VP, _F,
                                  C.POINTER(ModVec), C.POINTER(ModVec), _VP]),
@@ -160,16 +159,27 @@ def load() -> C.CDLL:
             fn.argtypes = args
         if lib.tg_version() != 1:
             raise TokensGenError(f"ABI version mismatch: library reports {lib.tg_version()}")
-        if _os.environ.get("TG_GEMM_IMPL"):  # developer A/B switch: 1 = single-CTA tiles, 2 = CTA pairs (default)
-            lib.tg_set_gemm_impl(int(_os.environ["TG_GEMM_IMPL"]))
-        if _os.environ.get("TG_CONV_IMPL"):
-            lib.tg_set_conv_impl(int(_os.environ["TG_CONV_IMPL"]))
+        if hasattr(lib, "tg_set_tuning"):      # developer build only
+            if _os.environ.get("TG_GEMM_IMPL"):  # A/B switch: 1 = single-CTA tiles, 2 = CTA pairs (default)
+                lib.tg_set_gemm_impl(int(_os.environ["TG_GEMM_IMPL"]))
+            if _os.environ.get("TG_CONV_IMPL"):
+                lib.tg_set_conv_impl(int(_os.environ["TG_CONV_IMPL"]))
         _lib = lib
     return _lib
 
 
+def has_tuning() -> bool:
+    """True when the loaded library is a developer build (-DTG_DEVELOPER: `python -m tokensgen_b200.build --dev`,
+    TG_LIB_PATH=.../libtokensgen_b200_dev.so).  The shipped library has one fixed configuration and no knobs."""
+    return hasattr(load(), "tg_set_tuning")
+
+
 def set_tuning(key: str, value: int) -> None:
-    _check(load().tg_set_tuning(key.encode(), int(value)), "tg_set_tuning")
+    if not has_tuning():
+        raise TokensGenError("tuning knobs exist only in the developer build (python -m tokensgen_b200.build --dev; TG_LIB_PATH)")
+    lib = load()
+    lib.tg_set_tuning.restype, lib.tg_set_tuning.argtypes = C.c_int, [C.c_char_p, C.c_int]
+    _check(lib.tg_set_tuning(key.encode(), int(value)), "tg_set_tuning")
 
 
 def _check(rc: int, what: str) -> None:

@@ -1,7 +1,11 @@
 """Builds libtokensgen_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
 
-Usage: python -m tokensgen_b200.build [--force] [--verbose]
+Usage: python -m tokensgen_b200.build [--force] [--verbose] [--dev]
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+
+--dev builds libtokensgen_b200_dev.so with -DTG_DEVELOPER: the same kernels plus the earlier attention generations and the
+tg_set_tuning / tg_set_gemm_impl / tg_set_conv_impl / tg_debug_attn_trace hooks the A/B tools under tools/ use
+(TG_LIB_PATH=tokensgen_b200/libtokensgen_b200_dev.so python tools/...).  The shipped library has none of them.
 """
 from __future__ import annotations
 
@@ -13,6 +17,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libtokensgen_b200.so"
+DEV_LIB_PATH = PKG_DIR / "libtokensgen_b200_dev.so"
 SOURCES = ["common.cu", "gemm.cu", "attn.cu", "elementwise.cu", "conv.cu", "vae.cu"]
 HEADERS = ["common.h", "ptx.cuh", "../../include/tokensgen_b200.h"]
 NVCC_FLAGS = [
@@ -31,24 +36,26 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def needs_build() -> bool:
-    if not LIB_PATH.exists():
+def needs_build(dev: bool = False) -> bool:
+    lib = DEV_LIB_PATH if dev else LIB_PATH
+    if not lib.exists():
         return True
-    t = LIB_PATH.stat().st_mtime
+    t = lib.stat().st_mtime
     deps = [CSRC / s for s in SOURCES] + [(CSRC / h).resolve() for h in HEADERS] + [Path(__file__)]
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
-        return LIB_PATH
+def build(force: bool = False, verbose: bool = False, dev: bool = False) -> Path:
+    lib_path = DEV_LIB_PATH if dev else LIB_PATH
+    if not force and not needs_build(dev):
+        return lib_path
     objs = []
-    build_dir = PKG_DIR / "build"
-    build_dir.mkdir(exist_ok=True)
+    build_dir = PKG_DIR / "build" / ("dev" if dev else "ship")
+    build_dir.mkdir(parents=True, exist_ok=True)
     procs = []
     for s in SOURCES:
         obj = build_dir / (s.replace(".cu", ".o"))
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / s), "-o", str(obj)]
+        cmd = [_nvcc(), *NVCC_FLAGS, *(["-DTG_DEVELOPER"] if dev else []), "-c", str(CSRC / s), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas")
             cmd.insert(2, "-v")
@@ -62,11 +69,11 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc compilation failed")
-    link = [_nvcc(), "-shared", "-cudart", "static", "-o", str(LIB_PATH), *objs]
+    link = [_nvcc(), "-shared", "-cudart", "static", "-o", str(lib_path), *objs]
     subprocess.run(link, check=True)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, dev="--dev" in sys.argv)
     print(path)

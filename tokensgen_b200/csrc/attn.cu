@@ -63,6 +63,7 @@ __device__ __forceinline__ __nv_bfloat16* attn_out_row(const AttnParams& p, int 
     return p.out + ((int64_t(b) * p.out_rows_alloc + p.out_row0 + q_row) * p.H + h) * AT_D;
 }
 
+#ifdef TG_DEVELOPER  // kernel generations 1 and 2: kept for tools/attn_time.py / attn_trace.py comparisons, not shipped
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ AttnParams p) {
@@ -704,6 +705,8 @@ attn2_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 }
 
 
+#endif  // TG_DEVELOPER (v1 / v2)
+
 // =====================================================================================================================
 // v3: v2's tiling and warp roles, with the three things the v2 timeline (tools/attn_trace.py) showed were missing:
 //   * the two query tiles TAKE TURNS on the MUFU pipe, per SM sub-partition: the two warps of tile t on sub-partition q
@@ -949,8 +952,9 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int pair_bar = 1 + t * 4 + wq;
         uint32_t xs_mine = xch_smem + uint32_t(((t * 2 + half) * 128 + row_in_tile) * 4);        // + parity * 2048
         uint32_t xs_other = xch_smem + uint32_t(((t * 2 + (half ^ 1)) * 128 + row_in_tile) * 4);
+        uint32_t lane_pin = uint32_t(lane);   // `lane == 0` re-derived from %tid costs S2R + LOP3 at every arrive
         A3_PIN(s_addr); A3_PIN(o_addr); A3_PIN(p_addr); A3_PIN(bar_sfull); A3_PIN(bar_sfree); A3_PIN(bar_pfull);
-        A3_PIN(bar_odone); A3_PIN(pair_bar); A3_PIN(xs_mine); A3_PIN(xs_other);
+        A3_PIN(bar_odone); A3_PIN(pair_bar); A3_PIN(xs_mine); A3_PIN(xs_other); A3_PIN(lane_pin);
         auto sts_f32 = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
         auto lds_f32 = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; };
         const float c = p.scale_log2;
@@ -963,8 +967,10 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         if (pi == n_pass && *redo_flag_ptr == 0u) break;   // every softmax thread read the final flag after the last vote
         const int pass = pi >= n_pass ? pi - n_pass : pi;
         const bool exact = p.spec == 0 || pi >= n_pass;
-        const int n_blocks = pass_blocks(pass);
+        int n_blocks = pass_blocks(pass);
         const int kv_rows = pass == 0 ? p.kv_rows : p.kv_rows2;
+        int valid = kv_rows - half * 64;   // score columns of this thread's half that are real keys, from block j on
+        A3_PIN(n_blocks); A3_PIN(valid);
         float mc = 0.f;    // reference max in log2 units, integer-valued
         float smin = 0.f;  // scores below this are clamped before an emulated exponential (2^-126)
         float l = 0.f;
@@ -982,13 +988,13 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_sfree);
-            const int valid = kv_rows - j * AT_BLOCK_KV - half * 64;
+            if (lane_pin == 0) mbar_arrive(bar_sfree);
             if (valid < 64) {
 #pragma unroll
                 for (int i = 0; i < 64; ++i)
                     if (i >= valid) r[i] = 0xff800000u;  // -inf
             }
+            valid -= AT_BLOCK_KV;
 #ifdef A3_FIXED_TEST  // developer experiment: upper bound of what an a-priori row bound (no running max) would buy
             bool waited = false;
             if (j == 0) { mc = float(A3_FIXED_TEST); smin = (mc - 126.0f) * inv_c; }
@@ -1088,7 +1094,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             tmem_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_pfull);
+            if (lane_pin == 0) mbar_arrive(bar_pfull);
             const uint64_t a = add_f32x2(add_f32x2(ps2[0], ps2[1]), add_f32x2(ps2[2], ps2[3]));
             l += f32x2_lo(a) + f32x2_hi(a);
         }
@@ -1159,15 +1165,25 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
     }
 }
 
-static int g_attn_impl = 3;  // 1 = v1 (8 softmax warps), 2 = v2 (16), 3 = v3 (16, alternating tiles)
-static int g_attn_emu = 0;   // v3: eighths of the exponentials evaluated on the FMA pipe (1 is ~2 % faster in a burst, 0 wins at the power cap)
+// Kernel selection.  The shipped library has ONE configuration (constants below: no process-wide mutable state); a developer
+// build (-DTG_DEVELOPER, `python -m tokensgen_b200.build --dev`) turns them into knobs behind tg_set_tuning for A/B runs.
+#ifdef TG_DEVELOPER
+#define TG_KNOB static int
+#else
+#define TG_KNOB static constexpr int
+#endif
+TG_KNOB g_attn_impl = 3;  // 1 = v1 (8 softmax warps), 2 = v2 (16), 3 = v3 (16, two tiles per CTA)
+TG_KNOB g_attn_emu = 0;   // v3: eighths of the exponentials evaluated on the FMA pipe (1 is ~2 % faster in a burst, 0 wins at the power cap)
+TG_KNOB g_attn_alt = 0;   // v3: the two query tiles take turns on the MUFU pipe
+TG_KNOB g_attn_spec = 1;  // v3: speculative softmax reference + exact in-kernel redo (see attn3_fwd_kernel)
+#ifdef TG_DEVELOPER
 static int g_attn_stagger = 0;
 static long long* g_attn_trace = nullptr;
 static int g_attn_mutex = 0;
 static int g_attn_packed = 1;
-static int g_attn_alt = 0;   // v3: the two query tiles take turns on the MUFU pipe
-static int g_attn_spec = 1;  // v3: speculative softmax reference + exact in-kernel redo (see attn3_fwd_kernel)
+#endif
 
+#ifdef TG_DEVELOPER
 template <int EMU, bool MUTEX, bool TRACE, bool PACKED>
 static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                         const AttnParams& p) {
@@ -1181,6 +1197,8 @@ static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const
     kern<<<grid, A2_THREADS, A2_SMEM_BYTES, st>>>(tq, tk, tv, p);
     return check_launch("attn_fwd");
 }
+
+#endif
 
 template <int EMU8, bool ALT>
 static int launch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -1260,29 +1278,35 @@ static int attn_fwd_impl(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0,
     p.out_scale = out_scale;
     p.n_pass = 1;
     p.spec = g_attn_spec;
+#ifdef TG_DEVELOPER
     p.stagger = g_attn_stagger;
     p.trace = g_attn_trace;
     p.mutex = g_attn_mutex;
+#endif
     if (scatter != nullptr) {
         rc = set_scatter(p, scatter, out_row0, q_rows, H);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
-        if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_set = true;
-    }
     dim3 grid((q_rows + 2 * AT_BLOCK_Q - 1) / (2 * AT_BLOCK_Q), BH);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (g_attn_impl == 3) return dispatch_attn3(grid, st, tq, tk, tv, tq, tk, tv, p);
+#ifdef TG_DEVELOPER
     if (g_attn_impl == 2) {
         if (g_attn_trace != nullptr) return launch_attn2<0, false, true, false>(grid, st, tq, tk, tv, p);
         return g_attn_packed ? launch_attn2<0, false, false, true>(grid, st, tq, tk, tv, p)
                              : launch_attn2<0, false, false, false>(grid, st, tq, tk, tv, p);
     }
-    attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(tq, tk, tv, p);
-    return check_launch("attn_fwd");
+    if (g_attn_impl == 1) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM_BYTES);
+            if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            attr_set = true;
+        }
+        attn_fwd_kernel<<<grid, AT_THREADS, AT_SMEM_BYTES, st>>>(tq, tk, tv, p);
+        return check_launch("attn_fwd");
+    }
+#endif
+    return dispatch_attn3(grid, st, tq, tk, tv, tq, tk, tv, p);
 }
 
 extern "C" int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
@@ -1304,6 +1328,7 @@ extern "C" int tg_attn_fwd_sp(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_
 
 static int tg::dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                               const CUtensorMap& tq2, const CUtensorMap& tk2, const CUtensorMap& tv2, const AttnParams& p) {
+#ifdef TG_DEVELOPER
 #define TG_A3(E)                                                                                      \
     case E:                                                                                           \
         return g_attn_alt ? launch_attn3<E, true>(grid, st, tq, tk, tv, tq2, tk2, tv2, p)             \
@@ -1313,6 +1338,9 @@ static int tg::dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq,
         default: return fail(-7, "attn_fwd: attn_emu must be 0..4 (eighths of the exponentials on the FMA pipe)");
     }
 #undef TG_A3
+#else
+    return launch_attn3<g_attn_emu, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);   // the one shipped instantiation
+#endif
 }
 
 static int attn_fwd_pair_impl(const tg_bf16* q, const tg_bf16* k, const tg_bf16* v, int64_t rows_alloc, int q_rows, int kv_rows,
@@ -1331,7 +1359,9 @@ static int attn_fwd_pair_impl(const tg_bf16* q, const tg_bf16* k, const tg_bf16*
         return fail(-5, "attn_fwd_pair: pointers must be 16-byte aligned");
     const int BH = B * H;
     if (BH > 65535) return fail(-6, "attn_fwd_pair: B*H too large");
+#ifdef TG_DEVELOPER
     if (g_attn_impl != 3) return fail(-8, "attn_fwd_pair: needs attention kernel generation 3");
+#endif
     CUtensorMap tq, tk, tv, tq2, tk2, tv2;
     int rc;
     auto mk = [&](CUtensorMap* m, const tg_bf16* base, int64_t row0, int rows, int64_t alloc, int box_rows) {
@@ -1383,6 +1413,8 @@ extern "C" int tg_attn_fwd_pair_sp(const tg_bf16* q, const tg_bf16* k, const tg_
                               softmax_scale, out_scale2, out, stream);
 }
 
+#ifdef TG_DEVELOPER
+// Developer hooks (tools/attn_*.py, tools/ab_bench.sh): present only in libtokensgen_b200_dev.so, never in the shipped library.
 extern "C" int tg_debug_attn_trace(void* device_buffer) {  // developer hook, not in the public header
     g_attn_trace = static_cast<long long*>(device_buffer);
     return 0;
@@ -1400,3 +1432,4 @@ extern "C" int tg_set_tuning(const char* key, int value) {
     if (k == "attn_spec") { g_attn_spec = value; return 0; }
     return fail(-2, "set_tuning: unknown key %s", key);
 }
+#endif  // TG_DEVELOPER

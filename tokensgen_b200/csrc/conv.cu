@@ -46,36 +46,46 @@ struct ConvParams {
 
 constexpr int CV_MAX_GROUPS = 64;
 
-// Per-chunk GroupNorm partials: v[32] are this pixel's bf16-rounded outputs of channels [n0, n0 + 32); the warp's 32 pixels are
-// summed with a butterfly and lane i adds value i to the CTA's shared fp64 accumulators (sh[g] sums, sh[G + g] squares).
+// Per-chunk GroupNorm partials: v[32] are this pixel's bf16-rounded outputs of channels [n0, n0 + 32).  The warp's 32 pixels are
+// summed with a transpose-reduce butterfly (2 NG values in log2(2 NG) halving steps + the remaining full steps: 2 NG shuffles in
+// all instead of 5 per value), which leaves value i on the lanes whose upper bits spell i; one native fp32 shared-memory atomic
+// per warp adds them to the CTA's accumulators (sh[g] sums, sh[G + g] squares), flushed to fp64 once per CTA.
 template <int CG>   // channels per group inside the chunk: 4, 8, 16 or 32 (= the whole chunk belongs to one group)
-__device__ __forceinline__ void conv_chunk_stats(const float (&v)[32], int n0, int cg_total, int groups, double* sh) {
+__device__ __forceinline__ void conv_chunk_stats(const float (&v)[32], int n0, int cg_total, int groups, float* sh) {
     constexpr int NG = 32 / CG;
-    float s[NG], q[NG];
+    constexpr int NV = 2 * NG;       // 16, 8, 4 or 2
+    float a[NV];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-        s[g] = 0.f;
-        q[g] = 0.f;
+        float s = 0.f, q = 0.f;
 #pragma unroll
         for (int i = 0; i < CG; ++i) {
-            s[g] += v[g * CG + i];
-            q[g] = fmaf(v[g * CG + i], v[g * CG + i], q[g]);
+            s += v[g * CG + i];
+            q = fmaf(v[g * CG + i], v[g * CG + i], q);
         }
-    }
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-            s[g] += __shfl_xor_sync(0xffffffffu, s[g], m);
-            q[g] += __shfl_xor_sync(0xffffffffu, q[g], m);
-        }
+        a[g] = s;
+        a[NG + g] = q;
     }
     const int lane = threadIdx.x & 31;
-    const int g0 = n0 / cg_total;   // first group of this chunk (CG == 32: the one group the chunk lies in)
+    int m = 16;
 #pragma unroll
-    for (int g = 0; g < NG; ++g) {
-        if (lane == 2 * g) atomicAdd(&sh[g0 + g], double(s[g]));
-        if (lane == 2 * g + 1) atomicAdd(&sh[groups + g0 + g], double(q[g]));
+    for (int n = NV; n > 1; n >>= 1, m >>= 1) {
+        const bool hi = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < n / 2; ++i) {
+            const float send = hi ? a[i] : a[i + n / 2];
+            const float keep = hi ? a[i + n / 2] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+#pragma unroll
+    for (; m > 0; m >>= 1) a[0] += __shfl_xor_sync(0xffffffffu, a[0], m);
+    constexpr int SHIFT = (NV == 16) ? 1 : (NV == 8) ? 2 : (NV == 4) ? 3 : 4;   // 5 - log2(NV)
+    if ((lane & ((1 << SHIFT) - 1)) == 0) {
+        const int idx = lane >> SHIFT;                 // which of the NV values this lane holds
+        const int g0 = n0 / cg_total;                  // first group of this chunk (CG == 32: the group the chunk lies in)
+        const int slot = idx < NG ? g0 + idx : groups + g0 + (idx - NG);
+        atomicAdd(&sh[slot], a[0]);
     }
 }
 
@@ -108,7 +118,7 @@ __device__ __forceinline__ void conv_tile_coords(const ConvParams& p, int tile, 
 // Called by whole warps (all 32 lanes, `ok` may differ per lane): the statistics path shuffles.
 template <int BLOCK_N>
 __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t t_row, int nt, bool ok, int64_t pix,
-                                                  double* sh_stats) {
+                                                  float* sh_stats) {
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 32) {
             uint32_t r[32];
@@ -183,16 +193,16 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
 
 // The CTA's statistics accumulators: zeroed before the tile loop, flushed to p.stats (fp64 atomics) after it.  Called by all
 // 128 epilogue threads (warps 4..7); named barrier 1.
-__device__ __forceinline__ void conv_stats_begin(const ConvParams& p, double* sh) {
+__device__ __forceinline__ void conv_stats_begin(const ConvParams& p, float* sh) {
     if (p.stats == nullptr) return;
-    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128) sh[i] = 0.0;
+    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128) sh[i] = 0.f;
     named_bar_sync(1, 128);
 }
-__device__ __forceinline__ void conv_stats_end(const ConvParams& p, double* sh) {
+__device__ __forceinline__ void conv_stats_end(const ConvParams& p, float* sh) {
     if (p.stats == nullptr) return;
     named_bar_sync(1, 128);
     for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128)
-        if (sh[i] != 0.0) atomicAdd(&p.stats[i], sh[i]);
+        if (sh[i] != 0.f) atomicAdd(&p.stats[i], double(sh[i]));
 }
 
 template <int BLOCK_N>
@@ -202,7 +212,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     using Cfg = ConvCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ double sh_stats[2 * CV_MAX_GROUPS];
+    __shared__ float sh_stats[2 * CV_MAX_GROUPS];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -366,7 +376,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     using Cfg = Conv2Cfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ double sh_stats[2 * CV_MAX_GROUPS];
+    __shared__ float sh_stats[2 * CV_MAX_GROUPS];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -549,7 +559,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     constexpr int BLOCK_N = 128;
     constexpr int STAGES = C3_STAGES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ double sh_stats[2 * CV_MAX_GROUPS];
+    __shared__ float sh_stats[2 * CV_MAX_GROUPS];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * C3_STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -718,7 +728,11 @@ static int launch_conv3(const CUtensorMap& tx, const CUtensorMap& tw, const Conv
     return check_launch("vae_conv");
 }
 
+#ifdef TG_DEVELOPER
 static int g_conv_impl = 3;  // 1 = single-CTA tiles, 2 = CTA pairs, 3 = CTA pairs + kw-tap reuse where stride 1 / kw 3 allow
+#else
+static constexpr int g_conv_impl = 3;  // the shipped configuration (no process-wide mutable state)
+#endif
 
 template <int BLOCK_N>
 static int launch_conv2(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
@@ -853,8 +867,10 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     return bn == 128 ? launch_conv<128>(tx, tw, p, st) : launch_conv<64>(tx, tw, p, st);
 }
 
+#ifdef TG_DEVELOPER
 extern "C" int tg_set_conv_impl(int impl) {  // developer hook (1 = single-CTA tiles, 2 = CTA pairs); not in the public header
     if (impl < 1 || impl > 3) return fail(-1, "conv impl must be 1, 2 or 3");
     g_conv_impl = impl;
     return 0;
 }
+#endif

@@ -630,7 +630,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------- host side
+#ifdef TG_DEVELOPER
 static int g_gemm_impl = 2;  // 1 = single-CTA 128 x BLOCK_N tiles, 2 = CTA pairs (256 x 256) where the shape allows
+#else
+static constexpr int g_gemm_impl = 2;  // the shipped configuration (no process-wide mutable state)
+#endif
 
 template <int EPI>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
@@ -827,8 +831,10 @@ extern "C" int tg_qkv_rope_gemm_sp(const tg_bf16* A, int64_t lda, const tg_bf16*
     return qkv_rope_gemm_impl(A, lda, W, bias, B, H, K, map, proj, nproj, ln_eps, scatter, stream);
 }
 
+#ifdef TG_DEVELOPER
 extern "C" int tg_set_gemm_impl(int impl) {  // developer hook (1 = single-CTA tiles, 2 = CTA pairs); not in the public header
     if (impl != 1 && impl != 2) return tg::fail(-1, "gemm impl must be 1 or 2");
     tg::g_gemm_impl = impl;
     return 0;
 }
+#endif

@@ -302,7 +302,9 @@ def _norm_silu_into(norm, x, out: torch.Tensor, zq: Optional[_ZqTables]):
     E.vae_norm_act(x, sums, gn.num_groups, gn.eps, gn.weight, gn.bias, out, zy, zb, silu=True)
 
 
-_FUSED_STATS = True   # GroupNorm statistics in the producing convolution's epilogue (False: the separate statistics pass)
+# GroupNorm statistics in the producing convolution's epilogue (False: the separate statistics pass, tg_vae_group_stats)
+import os as _os
+_FUSED_STATS = _os.environ.get("TG_VAE_FUSED_STATS", "1") != "0"
 
 
 def _resnet(blk: CogVideoXResnetBlock3D, xa, zq: Optional[_ZqTables], next_groups: int = 0) -> "_Act":
