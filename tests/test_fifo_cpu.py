@@ -331,3 +331,50 @@ def test_streaming_decode_hands_every_chunk_to_its_owner_as_soon_as_it_is_comple
     assert r["ready_it"] == {c: 39 + 13 * (c + 1) - 1 for c in range(5)}
     after = torch.cat([_ToyPipe.decode_latents(r["latents"][:, c * 13:(c + 1) * 13], 13) for c in range(5)], dim=2)
     assert torch.equal(r["video"], after)
+
+
+# ------------------------------------------------------------------------------------------------ ramp sharding
+def _ramp_worker(rank, world, port, num_frames, out_path):
+    from tokensgen_b200.fifo import RampSharding
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        sched = FifoSchedule(num_frames, _timesteps())
+        entered = []
+        ramp = RampSharding(world, rank, heads=48, enter=lambda g: entered.append(dist.get_world_size(g)), leave=lambda: None)
+        em = run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3, rank=rank, world=world, ramp=ramp)
+        sizes = [None] * world
+        dist.all_gather_object(sizes, entered)
+        if rank == 0:
+            torch.save({"video": torch.cat(em[52 - 13:], dim=1), "entered": sizes}, out_path)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ramp_sharding_reproduces_the_single_process_result(tmp_path, world):
+    """during the ramp-up the few active windows are dealt to GROUPS of ranks (their DiT forward runs
+    sequence-parallel over the group on the GPU; here the step is a deterministic toy, so only the hand-off logic is under
+    test): same video as one process, and every rank entered groups of the sizes the plan says."""
+    num_frames = 26
+    sched = FifoSchedule(num_frames, _timesteps())
+    ref = torch.cat(run_fifo(sched, _make_queue(), _toy_step, _toy_shift, seed=3)[52 - 13:], dim=1)
+    out = str(tmp_path / "ramp.pt")
+    port = 29500 + (os.getpid() % 2000) + 120 + world
+    mp.spawn(_ramp_worker, args=(world, port, num_frames, out), nprocs=world, join=True)
+    r = torch.load(out, weights_only=False)
+    assert torch.equal(r["video"], ref)
+    # windows active per iteration: 1, then 2 from iteration 1, 3 from 7, 4 from 14, 5 from 20 (Appendix A of the survey)
+    n_active = [len(sched.windows(i)) for i in range(sched.num_iterations)]
+    assert n_active[0] == 1 and n_active[1] == 2 and n_active[7] == 3 and n_active[14] == 4 and n_active[20] == 5
+    want = {r_: [] for r_ in range(world)}
+    for a in n_active:
+        g = max([g for g in (8, 4, 2) if g <= world and a * g <= world] or [1])
+        if g > 1:
+            for r_ in range(world):
+                if r_ // g < a:
+                    want[r_].append(g)
+    assert r["entered"] == [want[r_] for r_ in range(world)]
+    if world == 8:
+        assert want[0][:1] == [8] and want[0].count(4) == 6 and want[0].count(2) == 13      # 1 + 6 + (7 + 6) iterations

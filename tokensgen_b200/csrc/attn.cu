@@ -1173,7 +1173,9 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
 #define TG_KNOB static constexpr int
 #endif
 TG_KNOB g_attn_impl = 3;  // 1 = v1 (8 softmax warps), 2 = v2 (16), 3 = v3 (16, two tiles per CTA)
-TG_KNOB g_attn_emu = 0;   // v3: eighths of the exponentials evaluated on the FMA pipe (1 is ~2 % faster in a burst, 0 wins at the power cap)
+TG_KNOB g_attn_emu = 1;   // v3: eighths of the exponentials evaluated on the FMA pipe.  With the speculative reference (fewer issue
+                          // slots per score) 1 wins at the power cap too: step 829.5 vs 839.9 ms, 813.6 with the fused pair
+                          // launch; 2 loses (825.2) — profiles/r02_ab_bench_2.jsonl
 TG_KNOB g_attn_alt = 0;   // v3: the two query tiles take turns on the MUFU pipe
 TG_KNOB g_attn_spec = 1;  // v3: speculative softmax reference + exact in-kernel redo (see attn3_fwd_kernel)
 #ifdef TG_DEVELOPER

@@ -124,6 +124,42 @@ class FifoQueue:
         return lat, old
 
 
+class RampSharding:
+    """Idle GPUs join the active windows during the FIFO ramp-up.
+
+    For the first T - l_nf iterations fewer windows are active than the 2 x num_partitions the queue eventually feeds
+    (cogvideo_sampling_mp_fifo.py:243-244 skips windows left of `queue_start_idx`): 1 window in iteration 0, 2 from
+    iteration 1, 3 from 7, ... 8 from 40.  The reference — and plain window parallelism — leaves the other GPUs idle there,
+    which bounds the 8-GPU speed-up of a 24-chunk video at 7.6x and of short videos far lower.  Here, while `a` active
+    windows satisfy a * g <= P for a power-of-two group size g >= 2, the P ranks form P / g groups of g neighbours, group i
+    runs window i with its DiT forward SEQUENCE-PARALLEL over the group (tokensgen_b200/seqpar.py: bit-identical to the
+    unsharded forward, all-to-alls fused into kernel epilogues over NVLink), and every window's written slots are broadcast
+    from its group so that all queue replicas stay whole.  From the first iteration with a * 2 > P on, the usual
+    one-window-per-rank assignment with its neighbour exchange takes over.  Results do not depend on P."""
+
+    def __init__(self, world: int, rank: int, heads: int = 48, enter: Optional[Callable] = None,
+                 leave: Optional[Callable] = None, make_group: Optional[Callable] = None, min_rows: int = 0):
+        """enter(group) / leave(): switch the transformer's sequence-parallel mode (defaults: no-ops, for host-logic tests);
+        make_group(ranks) -> process group (default torch.distributed.new_group; collective: every rank creates every group)."""
+        import torch.distributed as dist
+        self.world, self.rank = world, rank
+        self.enter, self.leave = enter or (lambda g: None), leave or (lambda: None)
+        make_group = make_group or (lambda ranks: dist.new_group(ranks))
+        self.groups: Dict[int, list] = {}
+        for g in (8, 4, 2):
+            if g <= world and world % g == 0 and heads % g == 0:
+                self.groups[g] = [make_group(list(range(i * g, (i + 1) * g))) for i in range(world // g)]
+
+    def group_size(self, n_active: int) -> int:
+        for g in sorted(self.groups, reverse=True):
+            if n_active * g <= self.world:
+                return g
+        return 1
+
+    def my_group(self, g: int):
+        return self.groups[g][self.rank // g]
+
+
 def run_fingerprint(*parts) -> str:
     """Identity of one FIFO run for checkpoint matching: ints / floats / strings / lists are hashed by repr, tensors by their
     bytes (CPU copy).  Two runs share checkpoints only if every part agrees."""
@@ -198,7 +234,8 @@ class FifoCheckpoint:
 def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn, seed: int = 0, rank: int = 0,
              world: int = 1, group=None, progress: Optional[Callable[[int], None]] = None,
              checkpoint: Optional[FifoCheckpoint] = None, on_resume: Optional[Callable[[int], None]] = None,
-             on_emit: Optional[Callable[[int, List[torch.Tensor]], None]] = None) -> List[torch.Tensor]:
+             on_emit: Optional[Callable[[int, List[torch.Tensor]], None]] = None,
+             ramp: Optional[RampSharding] = None) -> List[torch.Tensor]:
     """The controller loop (:230-359).  `step_fn(window, latents[1,13,...], old_x0 list, t, prev_t, next_t, generator)`
     returns (latents_out [1,13,...], x0 list); `shift_fn(queue, noise_generator)` advances the queue by one slot and
     re-noises the tail.  Returns the emitted frames (slot r_nf of every iteration) as seen by this rank; rank 0's list is
@@ -206,7 +243,8 @@ def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn
     `checkpoint`: save the stage state every `checkpoint.every` iterations and resume from the newest state all ranks
     hold; `on_resume(k)` lets the caller fast-forward its own per-iteration bookkeeping (VipBook.shift) by k iterations.
     `on_emit(it, emitted)`: called on EVERY rank right after iteration `it` appended its frame (the list is complete on
-    rank 0 only) and before the queue shifts — the hook of the streaming decode (`StreamingDecoder`)."""
+    rank 0 only) and before the queue shifts — the hook of the streaming decode (`StreamingDecoder`).
+    `ramp`: share the few windows of the ramp-up iterations among groups of ranks (`RampSharding`)."""
     import torch.distributed as dist
     emitted = []
     dev = queue.latents.device
@@ -224,20 +262,44 @@ def run_fifo(schedule: FifoSchedule, queue: FifoQueue, step_fn: StepFn, shift_fn
                 on_resume(start_it)
     for it in range(start_it, schedule.num_iterations):
         wins = schedule.windows(it)
-        mine = [w for w in wins if w.rank % world == rank]
+        g_ramp = ramp.group_size(len(wins)) if (ramp is not None and world > 1) else 1
+        if g_ramp > 1:      # ramp-up: window i of this iteration belongs to the i-th group of g_ramp neighbouring ranks
+            gi = rank // g_ramp
+            mine = [wins[gi]] if gi < len(wins) else []
+            if mine:
+                ramp.enter(ramp.my_group(g_ramp))
+        else:
+            mine = [w for w in wins if w.rank % world == rank]
         results = []
         for w in mine:  # all windows read the pre-iteration queue (:232,258) -> compute first, write back after
             lat, old = queue.window_inputs(w)
             gen = torch.Generator(device=dev).manual_seed((seed * 1000003 + it) * 64 + w.rank)
             t, pt, nt = schedule.t[w.start:w.end], schedule.prev_t[w.start:w.end], schedule.next_t[w.start:w.end]
             results.append(step_fn(w, lat.clone(), old, t, pt, nt, gen))
+        if g_ramp > 1 and mine:
+            ramp.leave()
         for w, (out_lat, out_x0) in zip(mine, results):
             n = w.write_hi - w.write_lo
             queue.latents[:, w.write_lo:w.write_hi] = out_lat[:, w.out_lo:w.out_lo + n]
             for k in range(n):
                 queue.x0[w.write_lo + k].copy_(out_x0[w.out_lo + k].reshape(queue.x0[0].shape))
                 queue.x0_valid[w.write_lo + k] = True
-        if world > 1:
+        if g_ramp > 1:
+            # every replica is made whole again: the slots window i wrote travel from the first rank of its group to all
+            # (<= 4 broadcasts of <= 13 frames x 2 x 346 KB per iteration; the regular neighbour plan assumes the regular owners)
+            for i, w in enumerate(wins):
+                n = w.write_hi - w.write_lo
+                if rank // g_ramp == i:
+                    buf = torch.stack([queue.latents[0, w.write_lo:w.write_hi], queue.x0[w.write_lo:w.write_hi]]).contiguous()
+                else:
+                    buf = torch.empty((2, n) + tuple(queue.x0.shape[1:]), device=dev, dtype=queue.x0.dtype)
+                dist.broadcast(buf, src=i * g_ramp if group is None else dist.get_global_rank(group, i * g_ramp), group=group)
+                if rank // g_ramp != i:
+                    queue.latents[0, w.write_lo:w.write_hi] = buf[0]
+                    queue.x0[w.write_lo:w.write_hi] = buf[1]
+                    for s_ in range(w.write_lo, w.write_hi):
+                        queue.x0_valid[s_] = True
+        elif world > 1:
             ops, recvs = [], []
             for (src, dst, lo, hi) in schedule.transfers(it, world):
                 if src == rank:
@@ -540,8 +602,22 @@ def cogvideo_fifo_mp_v2(pipe_list, base_output, seed: int = 0, progress=None, **
     streamer = None
     if kwargs.get("streaming_decode") and base_output.output_type != "latent":
         streamer = StreamingDecoder(pipe, nf, T - nf, rank, world)
+    # `ramp_sharding` (default on with >= 2 ranks): idle ranks join the active windows of the ramp-up iterations through the
+    # sequence-parallel forward (RampSharding).  The groups are created once per pipeline (collective).
+    ramp = None
+    if world > 1 and kwargs.get("ramp_sharding", True):
+        ramp = getattr(pipe, "_tg_ramp", None)
+        if ramp is None or ramp.world != world:
+            tr = pipe.transformer
+            ramp = RampSharding(world, rank, heads=tr.config.num_attention_heads, enter=tr.enable_sequence_parallel,
+                                leave=tr.disable_sequence_parallel)
+            try:
+                pipe._tg_ramp = ramp
+            except AttributeError:
+                pass
     emitted = run_fifo(schedule, queue, step_fn, shift, seed=seed, rank=rank, world=world, progress=progress,
-                       checkpoint=ckpt, on_resume=fast_forward, on_emit=None if streamer is None else streamer.on_emit)
+                       checkpoint=ckpt, on_resume=fast_forward, on_emit=None if streamer is None else streamer.on_emit,
+                       ramp=ramp)
     latents = torch.cat(emitted[(T - nf):], dim=1).contiguous()           # :367 (slot r_nf belongs to window rank 0 -> process 0)
     if world > 1 and streamer is None:
         dist.broadcast(latents, src=0)

@@ -324,10 +324,12 @@ def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
     sp.barrier()
 
 
-# Both measured neutral on the power-capped step (839.8 ms either way, profiles/r01_energy.md): off by default so that the
-# per-kernel event timings of bench.py stay one kernel per stream.
-_SIDE_STREAM = os.environ.get("TG_SIDE_STREAM", "0") != "0"
-_FUSE_PAIR = os.environ.get("TG_FUSE_PAIR", "0") != "0"
+# Round 1 measured both neutral on the power-capped step (839.8 ms either way, profiles/r01_energy.md).  With the round-2
+# attention kernel (speculative reference, 1/8 of the exponentials on the FMA pipe) they pay: 829.5 ms with three launches,
+# 813.6 with K4 + K5 in one launch, 806.0 with K6 on the side stream as well (profiles/r02_ab_bench_2.jsonl) — both on.
+# The fused pair is also what the sequence-parallel forward runs, so sharded and unsharded forwards stay bit-identical.
+_SIDE_STREAM = os.environ.get("TG_SIDE_STREAM", "1") != "0"
+_FUSE_PAIR = os.environ.get("TG_FUSE_PAIR", "1") != "0"
 
 
 class _Buffers:
@@ -654,7 +656,7 @@ class CogVideoXTransformer3DModel(nn.Module):
             spc = self.__dict__.setdefault("_tg_bufs_sp", {})
             skey = key + (id(sp),)
             if skey not in spc:
-                while len(spc) >= 2:          # base stage + T2To geometries; older ones are dropped
+                while len(spc) >= 6:          # base stage / T2To geometries and the FIFO ramp's 2-, 4-, 8-rank groups; older ones are dropped
                     spc.pop(next(iter(spc)))
                 spc[skey] = ShardedBuffers(sp, B, rowmap, d, cfg.num_attention_heads, ff_dim, use_vip, dev)
             bufs = spc[skey]
