@@ -41,7 +41,9 @@ def attn_dram_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of ONE self-attention launch of this shape, from the committed
     `ncu --set full` capture summary (profiles/r01_attn3_full_summary.md); None if the summary is missing."""
     import re
-    path = os.path.join(ROOT, "profiles", "r01_attn3_full_summary.md")
+    path = os.path.join(ROOT, "profiles", "r02_attn_pair_full_summary.md")     # the shipped pair launch (round 2)
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r01_attn3_full_summary.md")
     if not os.path.exists(path):
         return None
     txt = open(path).read()
@@ -236,8 +238,15 @@ def fifo_schedule_stats(chunks: int, world: int):
     forwards = sum(len(w) for w in wins)
     rounds = sum(max(sum(1 for x in w if x.rank % world == r) for r in range(world)) for w in wins)
     ramp = sum(1 for w in wins if len(w) < 8)
+    # with RampSharding: an iteration whose `a` active windows allow groups of g = 2^k ranks (a * g <= P) costs 1 / g of a step
+    sizes = [g for g in (8, 4, 2) if g <= world and world % g == 0]
+    sharded = 0.0
+    for w in wins:
+        g = max([g for g in sizes if len(w) * g <= world] or [1])
+        sharded += 1.0 / g if g > 1 else max(sum(1 for x in w if x.rank % world == r) for r in range(world))
     return {"iterations": s.num_iterations, "window_forwards": forwards, "rounds": rounds, "ramp_iterations": ramp,
-            "schedule_bound_speedup": forwards / rounds}
+            "schedule_bound_speedup": forwards / rounds, "rounds_with_ramp_sharding": sharded,
+            "bound_speedup_with_ramp_sharding": forwards / sharded}
 
 
 def run_fifo_stage(model, sch, dev, world, rank, chunks: int, barrier):
@@ -486,7 +495,8 @@ def run_ours(args):
                              "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)",
                              "frac_of_burst_peak": achieved / tf_burst, "avg_launch_ms": avg_ms,
                              "share_of_step": per[dom] / ms_step, "traffic": attn_dram_traffic(),
-                             "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_attn3_full_summary.md)",
+                             "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of one launch; "
+                                             "profiles/r02_attn_pair_full_summary.md, else round 1's capture of the self-attention alone)",
                              "algorithmic_bytes": alg_bytes},
                 "kernel_ms_per_step": {k: round(v, 3) for k, v in sorted(per.items(), key=lambda kv: -kv[1])},
                 "clocks": clocks}

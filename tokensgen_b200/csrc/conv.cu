@@ -48,8 +48,10 @@ constexpr int CV_MAX_GROUPS = 64;
 
 // Per-chunk GroupNorm partials: v[32] are this pixel's bf16-rounded outputs of channels [n0, n0 + 32).  The warp's 32 pixels are
 // summed with a transpose-reduce butterfly (2 NG values in log2(2 NG) halving steps + the remaining full steps: 2 NG shuffles in
-// all instead of 5 per value), which leaves value i on the lanes whose upper bits spell i; one native fp32 shared-memory atomic
-// per warp adds them to the CTA's accumulators (sh[g] sums, sh[G + g] squares), flushed to fp64 once per CTA.
+// all instead of 5 per value), which leaves value i on the lanes whose upper bits spell i; those lanes add it to THIS WARP's
+// row of the CTA's accumulators (sh[warp][g] sums, sh[warp][G + g] squares; plain read-modify-write, one lane per slot, program
+// order — no atomics, so a CTA's partial sums do not depend on how its four epilogue warps interleave and the statistics are
+// reproducible run to run; the rows are folded in fp64 and flushed with fp64 atomics once per CTA).
 template <int CG>   // channels per group inside the chunk: 4, 8, 16 or 32 (= the whole chunk belongs to one group)
 __device__ __forceinline__ void conv_chunk_stats(const float (&v)[32], int n0, int cg_total, int groups, float* sh) {
     constexpr int NG = 32 / CG;
@@ -85,8 +87,10 @@ __device__ __forceinline__ void conv_chunk_stats(const float (&v)[32], int n0, i
         const int idx = lane >> SHIFT;                 // which of the NV values this lane holds
         const int g0 = n0 / cg_total;                  // first group of this chunk (CG == 32: the group the chunk lies in)
         const int slot = idx < NG ? g0 + idx : groups + g0 + (idx - NG);
-        atomicAdd(&sh[slot], a[0]);
+        float* mine = sh + ((threadIdx.x >> 5) & 3) * (2 * CV_MAX_GROUPS) + slot;
+        *mine += a[0];
     }
+    __syncwarp();
 }
 
 template <int BLOCK_N>
@@ -195,14 +199,17 @@ __device__ __forceinline__ void conv_epilogue_row(const ConvParams& p, uint32_t 
 // 128 epilogue threads (warps 4..7); named barrier 1.
 __device__ __forceinline__ void conv_stats_begin(const ConvParams& p, float* sh) {
     if (p.stats == nullptr) return;
-    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128) sh[i] = 0.f;
+    for (int i = threadIdx.x - 128; i < 4 * 2 * CV_MAX_GROUPS; i += 128) sh[i] = 0.f;
     named_bar_sync(1, 128);
 }
 __device__ __forceinline__ void conv_stats_end(const ConvParams& p, float* sh) {
     if (p.stats == nullptr) return;
     named_bar_sync(1, 128);
-    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128)
-        if (sh[i] != 0.f) atomicAdd(&p.stats[i], double(sh[i]));
+    for (int i = threadIdx.x - 128; i < 2 * p.stat_groups; i += 128) {
+        const double v = double(sh[i]) + double(sh[2 * CV_MAX_GROUPS + i]) + double(sh[4 * CV_MAX_GROUPS + i]) +
+                         double(sh[6 * CV_MAX_GROUPS + i]);
+        if (v != 0.0) atomicAdd(&p.stats[i], v);
+    }
 }
 
 template <int BLOCK_N>
@@ -212,7 +219,7 @@ conv_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ 
     using Cfg = ConvCfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ float sh_stats[2 * CV_MAX_GROUPS];
+    __shared__ float sh_stats[4 * 2 * CV_MAX_GROUPS];   // one row per epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -376,7 +383,7 @@ conv2_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     using Cfg = Conv2Cfg<BLOCK_N>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ float sh_stats[2 * CV_MAX_GROUPS];
+    __shared__ float sh_stats[4 * 2 * CV_MAX_GROUPS];   // one row per epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -559,7 +566,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     constexpr int BLOCK_N = 128;
     constexpr int STAGES = C3_STAGES;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ float sh_stats[2 * CV_MAX_GROUPS];
+    __shared__ float sh_stats[4 * 2 * CV_MAX_GROUPS];   // one row per epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + STAGES * C3_STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
