@@ -118,10 +118,7 @@ int tg_gemm_gate_residual(const tg_bf16* A, int64_t lda, const tg_bf16* W, const
  * epilogue computes y = A@W_p,h^T + bias; if ln_w: y = LN_64(y)*ln_w+ln_b (eps); then RoPE on interleaved pairs
  * (x0,x1)->(x0*c0 - x1*s0, x1*c1 + x0*s1) with cos/sin rows taken from cos_video[r-n_text] for video rows and
  * cos_vip[r-n_text-n_video] for vip rows (NULL table = no RoPE for that segment; text rows never rotate);
- * result stored at out[((b*H + h)*out_rows + r)*64 ..] iff r < out_rows.
- * out_scale (0 = 1): the fp32 result is multiplied by it before the single rounding to bf16.  The model passes
- * softmax_scale * log2(e) for the QUERY projections, so that Q K^T is the softmax exponent in log2 units and the attention
- * kernel needs no multiply per score (tg_attn_fwd with softmax_scale = 0). */
+ * result stored at out[((b*H + h)*out_rows + r)*64 ..] iff r < out_rows. */
 typedef struct {
     tg_bf16* out;    /* [B, H, out_rows, 64] */
     int out_rows;    /* rows of each batch kept for this projection (prefix of the batch's rows) */
@@ -131,7 +128,6 @@ typedef struct {
     const float* sin_video;
     const float* cos_vip;   /* [n_vip, 64] fp32 or NULL */
     const float* sin_vip;
-    float out_scale;
 } tg_qkv_proj;
 
 int tg_qkv_rope_gemm(const tg_bf16* A, int64_t lda, const tg_bf16* W, const tg_bf16* bias, int B, int H, int K,
@@ -158,11 +154,7 @@ int tg_qkv_rope_gemm_sp(const tg_bf16* A, int64_t lda, const tg_bf16* W, const t
  * (and :1939 for the plain processor).
  * q: [B,H,*,64] with q_rows queries starting at row q_row0 of a tensor with q_rows_alloc rows per head; k, v likewise.
  * out: [B, out_rows_alloc, H*64] token-major; query i is written to row out_row0 + i.
- * accumulate != 0: out = out + out_scale * attn (the `hidden + scale * text_video_hidden` of :2134), else out = attn.
- * softmax_scale == 0: q is PRE-SCALED (it already carries softmax_scale * log2(e), see tg_qkv_proj.out_scale): the kernel
- * computes softmax_2(Q K^T) = 2^s / sum 2^s with no per-score multiply and, because such scores are bounded for
- * LayerNormed q / k, without a running row maximum; a row whose sum leaves [2^-100, 2^100] is recomputed exactly (running
- * maximum) inside the same launch, so the result is the exact softmax for any input. */
+ * accumulate != 0: out = out + out_scale * attn (the `hidden + scale * text_video_hidden` of :2134), else out = attn. */
 int tg_attn_fwd(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0, int q_rows, const tg_bf16* k,
                 const tg_bf16* v, int64_t kv_rows_alloc, int64_t kv_row0, int kv_rows, tg_bf16* out,
                 int64_t out_rows_alloc, int64_t out_row0, int B, int H, float softmax_scale, int accumulate,

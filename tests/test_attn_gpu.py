@@ -162,59 +162,3 @@ def test_speculative_and_exact_modes_agree_on_ordinary_inputs():
     finally:
         E.set_tuning("attn_spec", 1)
     assert errs[1] < 5e-3 and errs[0] < 5e-3 and abs(errs[1] - errs[0]) < 1e-3
-
-
-# ------------------------------------------------------------------------------------------------ pre-scaled queries
-def ref_attn_log2(q, k, v):
-    """softmax_2(Q K^T) V: the scores ARE the exponents in log2 units (queries carry softmax_scale * log2 e)."""
-    s = torch.einsum("bhqd,bhkd->bhqk", q.double(), k.double())
-    p = torch.softmax(s * 0.6931471805599453, dim=-1)
-    return torch.einsum("bhqk,bhkd->bhqd", p, v.double()).permute(0, 2, 1, 3).flatten(2)
-
-
-@pytest.mark.parametrize("B,H,nq,nkv", [(1, 2, 127, 129), (2, 3, 300, 1000), (2, 48, 706, 2500)])
-def test_prescaled_queries_reference_free_path(B, H, nq, nkv):
-    """softmax_scale = 0: q is bf16(q * head_dim^-0.5 * log2 e) as the Q/K/V GEMM epilogue writes it (tg_qkv_proj.out_scale);
-    the kernel exponentiates the MMA result directly.  Against the fp64 softmax of the same pre-scaled tensors, and against
-    the explicit-scale path on the unscaled queries (they differ by the one extra bf16 rounding of q only)."""
-    from tokensgen_b200 import _ext as E
-    g = torch.Generator(device="cuda").manual_seed(B * 100 + nq)
-    q = torch.randn(B, H, nq, 64, generator=g, device="cuda").bfloat16()
-    k = torch.randn(B, H, nkv, 64, generator=g, device="cuda").bfloat16()
-    v = torch.randn(B, H, nkv, 64, generator=g, device="cuda").bfloat16()
-    qs = (q.float() * (64 ** -0.5 * 1.4426950408889634)).bfloat16()
-    out = torch.zeros(B, nq, H * 64, device="cuda", dtype=torch.bfloat16)
-    E.attn_fwd(qs, k, v, out, softmax_scale=0.0)
-    out2 = torch.zeros_like(out)
-    E.attn_fwd(q, k, v, out2)
-    torch.cuda.synchronize()
-    assert rel_l2(out.float(), ref_attn_log2(qs, k, v)) < 5e-3
-    assert rel_l2(out.float(), out2.float()) < 5e-3 and rel_l2(out.float(), ref_attn(q, k, v)) < 6e-3
-
-
-@pytest.mark.parametrize("kind", ["overflow", "underflow", "steep"])
-def test_prescaled_path_out_of_range_rows_take_the_exact_redo(kind):
-    """Rows whose exponents leave the fp32 range without a reference (all scores << -126, some >> 127, or climbing by
-    hundreds along kv) are detected by the CTA vote and recomputed with the running-max path: exact for any input."""
-    from tokensgen_b200 import _ext as E
-    g = torch.Generator(device="cuda").manual_seed(3)
-    nq, nkv = 300, 1500
-    q = torch.randn(1, 2, nq, 64, generator=g, device="cuda")
-    q = q / q.norm(dim=-1, keepdim=True) * 8
-    k = torch.randn(1, 2, nkv, 64, generator=g, device="cuda")
-    if kind == "overflow":
-        k[:, :, 700:710] += q[:, :, :10] * 6.0                 # a few keys aligned with a few queries: scores ~ +380
-    elif kind == "underflow":
-        k = k * 0.5 - q.mean(dim=2, keepdim=True) * 30.0        # every score strongly negative for most rows
-        q = q + q.mean(dim=2, keepdim=True) * 3.0
-    else:
-        k = k * torch.linspace(0.05, 40.0, nkv, device="cuda").view(1, 1, -1, 1)
-    q, k = q.bfloat16(), k.bfloat16()
-    v = torch.randn(1, 2, nkv, 64, generator=g, device="cuda").bfloat16()
-    s = torch.einsum("bhqd,bhkd->bhqk", q.double(), k.double())
-    assert (s.max().item() > 150) if kind != "underflow" else (s.max(dim=-1).values.min().item() < -150)
-    out = torch.full((1, nq, 128), 3.0, device="cuda", dtype=torch.bfloat16)
-    E.attn_fwd(q, k, v, out, softmax_scale=0.0)
-    torch.cuda.synchronize()
-    assert torch.isfinite(out.float()).all()
-    assert rel_l2(out.float(), ref_attn_log2(q, k, v)) < 5e-3

@@ -32,8 +32,7 @@ class ModVec(C.Structure):
 
 class QkvProj(C.Structure):
     _fields_ = [("out", C.c_void_p), ("out_rows", C.c_int), ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
-                ("cos_video", C.c_void_p), ("sin_video", C.c_void_p), ("cos_vip", C.c_void_p), ("sin_vip", C.c_void_p),
-                ("out_scale", C.c_float)]
+                ("cos_video", C.c_void_p), ("sin_video", C.c_void_p), ("cos_vip", C.c_void_p), ("sin_vip", C.c_void_p)]
 
 
 MAX_PEERS = 8

@@ -19,8 +19,6 @@
 #include <string>
 
 #include "common.h"
-#include <type_traits>
-
 #include "ptx.cuh"
 
 namespace tg {
@@ -46,7 +44,6 @@ struct AttnParams {
     int kv_rows2;      // v3 pass 1
     float out_scale2;  // v3 pass 1: out += out_scale2 * attn2
     int spec;          // v3: speculative softmax reference (block 0's row max, never updated) with an exact in-kernel redo
-    int prescaled;     // v3: softmax_scale == 0 -> q carries softmax_scale * log2(e); scale_log2 = 1
     int mutex;    // v2: the two tiles take turns on the MUFU pipe (named-barrier hand-off) instead of sharing it
     int stagger;  // v2: cycles by which tile 1 starts after tile 0 (keeps the two tiles' softmax phases interleaved)
     // sequence-parallel scatter of the output rows (tg_attn_fwd_sp): sp_world > 0 -> row g of a batch goes to its owner rank
@@ -745,11 +742,7 @@ __device__ __forceinline__ constexpr bool a3_emulated(int pair) {  // EMU8 of ev
     return ((pair + 1) * EMU8) / 8 != (pair * EMU8) / 8;
 }
 
-// PRE: the queries are pre-scaled (tg_qkv_proj.out_scale = softmax_scale * log2 e), i.e. S = Q K^T IS the exponent in log2
-// units.  In speculative mode the reference is then simply 0 — p = 2^s straight from the TMEM load, no multiply, no
-// subtraction, no row max at all (|s| <= |q||k| * scale * log2 e is a few tens for LayerNormed q / k; the CTA vote below
-// catches sums outside [2^-100, 2^100] and redoes the passes with the running-max path, so any input stays exact).
-template <int EMU8, bool ALT, bool PRE>
+template <int EMU8, bool ALT>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                  const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_q2,
@@ -964,7 +957,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         A3_PIN(bar_odone); A3_PIN(pair_bar); A3_PIN(xs_mine); A3_PIN(xs_other); A3_PIN(lane_pin);
         auto sts_f32 = [](uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); };
         auto lds_f32 = [](uint32_t addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory"); return v; };
-        const float c = PRE ? 1.0f : p.scale_log2;
+        const float c = p.scale_log2;
         const float inv_c = 1.0f / c;
         const uint64_t c2 = pack_f32x2(c, c);
         constexpr float MAGIC = 12582912.0f;  // 1.5 * 2^23
@@ -979,7 +972,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         int valid = kv_rows - half * 64;   // score columns of this thread's half that are real keys, from block j on
         A3_PIN(n_blocks); A3_PIN(valid);
         float mc = 0.f;    // reference max in log2 units, integer-valued
-        float smin = -126.0f * inv_c;  // scores below this are clamped before an emulated exponential (2^-126)
+        float smin = 0.f;  // scores below this are clamped before an emulated exponential (2^-126)
         float l = 0.f;
 
         for (int j = 0; j < n_blocks; ++j, ++g) {
@@ -1007,7 +1000,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             if (j == 0) { mc = float(A3_FIXED_TEST); smin = (mc - 126.0f) * inv_c; }
 #else
             bool waited = false;
-            if (exact || (j == 0 && !PRE)) {
+            if (exact || j == 0) {
             float pm[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) pm[k] = fmaxf(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
@@ -1055,10 +1048,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
             const uint64_t K2 = pack_f32x2(Kf, Kf);
             uint64_t ps2[4] = {0ull, 0ull, 0ull, 0ull};
             if (ALT && (g > 0 || t == 1)) mbar_wait_fast(bar_my_turn, uint32_t((t == 1 ? g : g - 1) & 1));
-            // exponentials: a pure (FFMA2 /) MUFU.EX2 / FADD2 stream (nothing in it waits on a MUFU result except the row sum).
-            // DIRECT (pre-scaled queries, speculative pass): the TMEM value IS the exponent — MUFU.EX2 on it, nothing else.
-            auto exponentials = [&](auto direct_tag) {
-            constexpr bool DIRECT = decltype(direct_tag)::value;
+            // exponentials: a pure FFMA2 / MUFU.EX2 / FADD2 stream (nothing in it waits on a MUFU result except the row sum)
 #pragma unroll
             for (int ch = 0; ch < 4; ++ch) {
 #pragma unroll
@@ -1076,9 +1066,6 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                         p2 = fma_f32x2(p2, f2, pack_f32x2(1.0f, 1.0f));
                         e0 = __int_as_float(int(uint32_t(p2)) + (int(uint32_t(t2)) << 23));
                         e1 = __int_as_float(int(uint32_t(p2 >> 32)) + (int(uint32_t(t2 >> 32)) << 23));
-                    } else if constexpr (DIRECT) {
-                        e0 = fast_exp2(__uint_as_float(r[i]));
-                        e1 = fast_exp2(__uint_as_float(r[i + 1]));
                     } else {
                         const uint64_t x2 = fma_f32x2(pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), c2, nmc2);
                         e0 = fast_exp2(f32x2_lo(x2));
@@ -1093,9 +1080,6 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
                     if (lane == 0) mbar_arrive(bar_other_turn);
                 }
             }
-            };
-            if (PRE && !exact) exponentials(std::true_type{});
-            else exponentials(std::false_type{});
 #pragma unroll
             for (int i = 0; i < 64; i += 2)
                 ps2[(i >> 1) & 3] = add_f32x2(ps2[(i >> 1) & 3], pack_f32x2(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
@@ -1125,8 +1109,7 @@ attn3_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_consta
         bool skip = false;
         if (!exact) {
             // CTA-wide vote on this pass's speculative result (sticky across the passes of a pair launch)
-            // sum outside [2^-100, 2^100] (also inf / NaN; the lower bound matters for the reference-free PRE pass only)
-            if (!(l < 1.2676506e30f) || (PRE && !(l > 7.8886091e-31f))) *redo_flag_ptr = 1u;
+            if (!(l < 1.2676506e30f)) *redo_flag_ptr = 1u;  // 2^100; also catches inf / NaN
             named_bar_sync(9, 512);
             skip = *redo_flag_ptr != 0u;
             if (pi == n_pass - 1) {
@@ -1219,11 +1202,11 @@ static int launch_attn2(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const
 
 #endif
 
-template <int EMU8, bool ALT, bool PRE>
+template <int EMU8, bool ALT>
 static int launch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
                         const CUtensorMap& tq2, const CUtensorMap& tk2, const CUtensorMap& tv2, const AttnParams& p) {
     static bool attr_set = false;
-    auto kern = attn3_fwd_kernel<EMU8, ALT, PRE>;
+    auto kern = attn3_fwd_kernel<EMU8, ALT>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM_BYTES);
         if (e != cudaSuccess) return fail(int(e), "attn_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -1292,8 +1275,7 @@ static int attn_fwd_impl(const tg_bf16* q, int64_t q_rows_alloc, int64_t q_row0,
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.out_rows_alloc = out_rows_alloc;
     p.out_row0 = out_row0;
-    p.prescaled = softmax_scale == 0.0f;
-    p.scale_log2 = p.prescaled ? 1.0f : softmax_scale * 1.4426950408889634f;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.accumulate = accumulate;
     p.out_scale = out_scale;
     p.n_pass = 1;
@@ -1351,18 +1333,15 @@ static int tg::dispatch_attn3(dim3 grid, cudaStream_t st, const CUtensorMap& tq,
 #ifdef TG_DEVELOPER
 #define TG_A3(E)                                                                                      \
     case E:                                                                                           \
-        if (p.prescaled) return launch_attn3<E, false, true>(grid, st, tq, tk, tv, tq2, tk2, tv2, p); \
-        return g_attn_alt ? launch_attn3<E, true, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p)      \
-                          : launch_attn3<E, false, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);
+        return g_attn_alt ? launch_attn3<E, true>(grid, st, tq, tk, tv, tq2, tk2, tv2, p)             \
+                          : launch_attn3<E, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);
     switch (g_attn_emu) {
         TG_A3(0) TG_A3(1) TG_A3(2) TG_A3(3) TG_A3(4)
         default: return fail(-7, "attn_fwd: attn_emu must be 0..4 (eighths of the exponentials on the FMA pipe)");
     }
 #undef TG_A3
 #else
-    // the two shipped instantiations: pre-scaled queries (the DiT) and an explicit softmax scale (Resampler, plugin callers)
-    if (p.prescaled) return launch_attn3<g_attn_emu, false, true>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);
-    return launch_attn3<g_attn_emu, false, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);
+    return launch_attn3<g_attn_emu, false>(grid, st, tq, tk, tv, tq2, tk2, tv2, p);   // the one shipped instantiation
 #endif
 }
 
@@ -1404,8 +1383,7 @@ static int attn_fwd_pair_impl(const tg_bf16* q, const tg_bf16* k, const tg_bf16*
     p.out = reinterpret_cast<__nv_bfloat16*>(out);
     p.out_rows_alloc = out_rows_alloc;
     p.out_row0 = 0;
-    p.prescaled = softmax_scale == 0.0f;
-    p.scale_log2 = p.prescaled ? 1.0f : softmax_scale * 1.4426950408889634f;
+    p.scale_log2 = softmax_scale * 1.4426950408889634f;
     p.accumulate = 0;
     p.out_scale = 1.0f;
     p.n_pass = 2;

@@ -37,7 +37,6 @@ struct QkvProjDev {
     const float* sin_video;
     const float* cos_vip;
     const float* sin_vip;
-    float out_scale;
 };
 
 struct GemmParams {
@@ -234,10 +233,6 @@ __device__ __forceinline__ __nv_bfloat16* epi_qkv_compute(const GemmParams& p, f
             acc[i + 2] = x2 * c.z - x3 * s.z;
             acc[i + 3] = x3 * c.w + x2 * s.w;
         }
-    }
-    if (pr.out_scale != 1.0f) {   // query projections: softmax_scale * log2(e) folded in before the one rounding to bf16
-#pragma unroll
-        for (int i = 0; i < 64; ++i) acc[i] *= pr.out_scale;
     }
     __nv_bfloat16* o;
     if constexpr (SP) {  // Ulysses all-to-all fused into the store: the head's owner rank receives the row over NVLink
@@ -815,7 +810,6 @@ static int qkv_rope_gemm_impl(const tg_bf16* A, int64_t lda, const tg_bf16* W, c
         p.proj[i].sin_video = proj[i].sin_video;
         p.proj[i].cos_vip = proj[i].cos_vip;
         p.proj[i].sin_vip = proj[i].sin_vip;
-        p.proj[i].out_scale = proj[i].out_scale == 0.0f ? 1.0f : proj[i].out_scale;
     }
     if (p.sp_world > 1)
         return dispatch<EPI_QKV_SP>(reinterpret_cast<const __nv_bfloat16*>(A), lda, reinterpret_cast<const __nv_bfloat16*>(W),

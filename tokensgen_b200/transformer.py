@@ -28,14 +28,6 @@ import torch.nn as nn
 from . import _ext as E
 
 
-# head_dim^-0.5 * log2(e) folded into the query projections, and the softmax_scale sentinel (0 = "queries are pre-scaled") of the
-# attention entry points.  TG_Q_PRESCALE=0 (developer A/B): unscaled queries + explicit scale, the round-1 arithmetic.
-if os.environ.get("TG_Q_PRESCALE", "1") != "0":
-    _Q_PRESCALE, _PRE = 64 ** -0.5 * 1.4426950408889634, 0.0
-else:
-    _Q_PRESCALE, _PRE = 1.0, None
-
-
 def _bf16_scalar(x: float) -> float:
     """The reference materialises the vip scale as a bf16 tensor (attention_processor.py:2126-2129)."""
     return float(torch.tensor(float(x)).bfloat16())
@@ -220,15 +212,10 @@ class _PackCache:
 def _qkv_projs(attn, proc, outs, rows_tv, rope, img_rope, cond_rope):
     """tg_qkv_proj descriptors in the weight order [to_q,to_k,to_v,(vip_to_q,vip_to_k,vip_to_v)]."""
     projs = []
-    # the QUERY projections carry softmax_scale * log2(e) (one fp32 multiply before their single rounding to bf16): Q K^T is
-    # then the softmax exponent in log2 units and the attention kernel runs its multiply-free, reference-free path
-    # (tg_attn_fwd with softmax_scale = 0; attention_processor.py:2066-2069 scales by head_dim^-0.5 inside SDPA)
-    q_scale = _Q_PRESCALE
 
-    def mk(out, out_rows, norm, video_rope, vip_rope, scale=1.0):
+    def mk(out, out_rows, norm, video_rope, vip_rope):
         p = E.QkvProj()
         p.out, p.out_rows = out.data_ptr(), out_rows
-        p.out_scale = scale
         if norm is not None:
             p.ln_w, p.ln_b = norm.weight.data_ptr(), norm.bias.data_ptr()
         if video_rope is not None:
@@ -237,12 +224,12 @@ def _qkv_projs(attn, proc, outs, rows_tv, rope, img_rope, cond_rope):
             p.cos_vip, p.sin_vip = vip_rope[0].data_ptr(), vip_rope[1].data_ptr()
         return p
 
-    projs.append(mk(outs[0], rows_tv, attn.norm_q, rope, None, q_scale))
+    projs.append(mk(outs[0], rows_tv, attn.norm_q, rope, None))
     projs.append(mk(outs[1], rows_tv, attn.norm_k, rope, None))
     projs.append(mk(outs[2], rows_tv, None, None, None))
     if proc is not None:
         rows_all = outs[3].shape[2]
-        projs.append(mk(outs[3], rows_all, proc.vip_norm_q, img_rope, cond_rope, q_scale))
+        projs.append(mk(outs[3], rows_all, proc.vip_norm_q, img_rope, cond_rope))
         projs.append(mk(outs[4], rows_all, proc.vip_norm_k, img_rope, cond_rope))
         projs.append(mk(outs[5], rows_all, None, None, None))
     return projs
@@ -271,7 +258,7 @@ def _attention_core(attn, proc, y, B, rowmap, rope, img_rope, cond_rope, bufs):
         side = bufs.side_stream
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv, softmax_scale=_PRE)
+            E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
     scales = None
     if proc is not None:
         scale = proc.scale
@@ -280,24 +267,22 @@ def _attention_core(attn, proc, y, B, rowmap, rope, img_rope, cond_rope, bufs):
             scales = [scales[0]] * B  # attention_processor.py:2130-2131
     if scales is not None and len(set(scales)) == 1 and _FUSE_PAIR:
         qv, kv, vv = bufs.qkv[3:]   # K4 + K5 in one launch
-        E.attn_fwd_pair(qb, kb, vb, n_tv, n_tv, qv, kv, vv, n_tv, rowmap.n_vip, bufs.A, _bf16_scalar(scales[0]),
-                        softmax_scale=_PRE)
+        E.attn_fwd_pair(qb, kb, vb, n_tv, n_tv, qv, kv, vv, n_tv, rowmap.n_vip, bufs.A, _bf16_scalar(scales[0]))
     else:
-        E.attn_fwd(qb, kb, vb, bufs.A, out_row0=0, softmax_scale=_PRE)
+        E.attn_fwd(qb, kb, vb, bufs.A, out_row0=0)
     if proc is not None:
         qv, kv, vv = bufs.qkv[3:]
         if len(set(scales)) == 1 and _FUSE_PAIR:
             pass
         elif len(set(scales)) == 1:
             E.attn_fwd(qv, kv, vv, bufs.A, q_row0=0, q_rows=n_tv, kv_row0=n_tv, kv_rows=rowmap.n_vip, out_row0=0,
-                       accumulate=True, out_scale=_bf16_scalar(scales[0]), softmax_scale=_PRE)
+                       accumulate=True, out_scale=_bf16_scalar(scales[0]))
         else:
             for bi, s in enumerate(scales):
                 E.attn_fwd(qv[bi:bi + 1], kv[bi:bi + 1], vv[bi:bi + 1], bufs.A[bi:bi + 1], q_row0=0, q_rows=n_tv,
-                           kv_row0=n_tv, kv_rows=rowmap.n_vip, out_row0=0, accumulate=True, out_scale=_bf16_scalar(s),
-                           softmax_scale=_PRE)
+                           kv_row0=n_tv, kv_rows=rowmap.n_vip, out_row0=0, accumulate=True, out_scale=_bf16_scalar(s))
         if side is None:
-            E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv, softmax_scale=_PRE)
+            E.attn_fwd(qv, kv, vv, bufs.A, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
         else:
             torch.cuda.current_stream().wait_stream(side)
 
@@ -314,7 +299,7 @@ def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
     qb, kb, vb = bufs.qkv[:3]
     out = bufs.attn_scatter
     if proc is None:
-        E.attn_fwd(qb, kb, vb, out, out_row0=0, softmax_scale=_PRE)
+        E.attn_fwd(qb, kb, vb, out, out_row0=0)
     else:
         qv, kv, vv = bufs.qkv[3:]
         # K6 (480 vip queries x all keys) has only 2 * B * H/world CTAs, each walking every key block: on a side stream its
@@ -322,7 +307,7 @@ def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
         main, side = torch.cuda.current_stream(), bufs.side_stream
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            E.attn_fwd(qv, kv, vv, out, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv, softmax_scale=_PRE)
+            E.attn_fwd(qv, kv, vv, out, q_row0=n_tv, q_rows=rowmap.n_vip, out_row0=n_tv)
         scale = proc.scale
         scales = [float(s_) for s_ in (scale if isinstance(scale, (list, tuple)) else [scale])]
         if len(scales) != B:
@@ -330,13 +315,11 @@ def _attention_core_sp(attn, proc, y, w, b, eps, projs, B, rowmap, bufs):
         if len(set(scales)) == 1:
             # K4 + K5 in one launch: the vip cross-attention is added before the row leaves the SM, so the peer buffer is
             # written once instead of read-modified-written over NVLink
-            E.attn_fwd_pair(qb, kb, vb, n_tv, n_tv, qv, kv, vv, n_tv, rowmap.n_vip, out, _bf16_scalar(scales[0]),
-                            softmax_scale=_PRE)
+            E.attn_fwd_pair(qb, kb, vb, n_tv, n_tv, qv, kv, vv, n_tv, rowmap.n_vip, out, _bf16_scalar(scales[0]))
         else:
             for bi, s_ in enumerate(scales):
                 E.attn_fwd_pair(qb[bi:bi + 1], kb[bi:bi + 1], vb[bi:bi + 1], n_tv, n_tv, qv[bi:bi + 1], kv[bi:bi + 1],
-                                vv[bi:bi + 1], n_tv, rowmap.n_vip, bufs.attn_scatter_for_batch(bi), _bf16_scalar(s_),
-                                softmax_scale=_PRE)
+                                vv[bi:bi + 1], n_tv, rowmap.n_vip, bufs.attn_scatter_for_batch(bi), _bf16_scalar(s_))
         main.wait_stream(side)
     sp.barrier()
 

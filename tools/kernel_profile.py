@@ -100,6 +100,13 @@ elif which == "conv":   # decoder up-block 3 at full resolution: 8 frames 480x72
     bias = torch.randn(128, device=dev).bfloat16()
     out = torch.empty(8, 480, 720, 128, device=dev, dtype=torch.bfloat16)
     rep(lambda: E.vae_conv(x, w, bias, 128, 3, 3, 3, 8, 480, 720, out=out))
+elif which == "conv_stats":   # the same layer with the consumer GroupNorm's statistics accumulated in the epilogue (round 2)
+    x = torch.randn(10, 480, 720, 128, device=dev).bfloat16()
+    w = (torch.randn(128, 27 * 128, device=dev) / (27 * 128) ** 0.5).bfloat16()
+    bias = torch.randn(128, device=dev).bfloat16()
+    out = torch.empty(8, 480, 720, 128, device=dev, dtype=torch.bfloat16)
+    stats = torch.zeros(64, device=dev, dtype=torch.float64)
+    rep(lambda: E.vae_conv(x, w, bias, 128, 3, 3, 3, 8, 480, 720, out=out, stats=stats, stat_groups=32))
 elif which == "norm_act":
     x = torch.randn(8, 480, 720, 128, device=dev).bfloat16()
     out = torch.empty_like(x)

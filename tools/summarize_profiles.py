@@ -90,6 +90,9 @@ launches()
 report("attn_full", "tg::attn_fwd_kernel (v1: 8 softmax warps) — self-attention, 1x48 heads x 17776^2 x 64")
 report("attn2_full", "tg::attn2_fwd_kernel (v2: 16 softmax warps) — self-attention, 1x48 heads x 17776^2 x 64")
 report("attn3_full", "tg::attn3_fwd_kernel (v3: lean waits, packed FMA-pipe exponentials 1/8, 112 softmax registers) — self-attention, 2x48 heads x 17776^2 x 64")
+report("attn_pair_full", "tg::attn3_fwd_kernel<1,false> (round 2: speculative softmax reference, 1/8 of the exponentials on the FMA pipe) "
+       "pair launch — self-attention, 2x48 heads x 17776^2 x 64 + cross-attention of the same queries to 480 vip keys")
+report("conv_stats_full", "tg::conv3_kernel with the GroupNorm statistics of the output accumulated in the epilogue (128 -> 128, 8 x 480 x 720)")
 for extra in sys.argv[2:]:
     report(extra, extra)
 print(sorted(os.listdir(out_dir)))
