@@ -273,6 +273,22 @@ def run_fifo_stage(model, sch, dev, world, rank, chunks: int, barrier):
         guidance_scale_img=6.0, extra_step_kwargs={}, video_ipadapter_start_frame_idx=1000, sampling_params={"num_partitions": 4},
         output_type="latent", return_dict=False)
     pipe = SimpleNamespace(transformer=model, scheduler=sch)
+
+    class _WarmedUp(Exception):
+        pass
+
+    def stop_after_ramp_groups(it):   # iterations 0..7 touch every ramp-sharding group size (8, 4, 2 ranks per window)
+        if it == 7:
+            raise _WarmedUp()
+
+    # untimed warm-up, like the W warm-up steps of the window bench: the first use of each sequence-parallel group allocates
+    # and rendezvouses its peer-mapped workspaces (once per process, not per video)
+    import copy
+    try:
+        with torch.no_grad():
+            cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=7, progress=stop_after_ramp_groups)
+    except _WarmedUp:
+        pass
     barrier()
     s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s_ev.record()
