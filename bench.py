@@ -488,7 +488,7 @@ def run_ours(args):
         if pair in per:
             dom, flops_per_launch = pair, 4 * 2 * 48 * 64 * (N * N + N * n_vip)
             dom_name = f"attn3_fwd_kernel, pair launch (self-attention 2x48 heads x {N}^2 x 64 + cross-attention to {n_vip} vip keys)"
-            alg_bytes = (4 * N + 3 * N + 2 * n_vip) * 2 * 48 * 64 * 2      # q,k,v,out + q2 + k2,v2 (bf16)
+            alg_bytes = (4 * N + N + 2 * n_vip) * 2 * 48 * 64 * 2          # q, k, v, out + q2 (N rows) + k2, v2 (480 rows each), bf16
         else:
             dom = self_attn if self_attn in per else max(per, key=per.get)
             flops_per_launch = 4 * 2 * 48 * N * N * 64
