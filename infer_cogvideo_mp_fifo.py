@@ -161,6 +161,11 @@ def main(args):
                     assert item.get("video") is not None
                     video = load_video(item["video"], dps.output_res, args.num_frames_per_chunk, dps.pad_to_fit, dps.sample_fps,
                                        dps.start_t, dps.end_t, dps.max_num_chunks, dps.crop_to_fit)
+            # The reference samples the conditioning clips' VAE posterior from the device's global RNG, which it never seeds
+            # (its set_seed import is unused on this path), so its edit flow is not reproducible run to run.  Same
+            # distribution here, but drawn from a generator seeded by the yaml `seed` on every rank: a job repeats exactly,
+            # and 1 rank and N ranks write the same video.
+            pipe.vae_posterior_generator = torch.Generator(device=device).manual_seed(int(args.seed))
             base_outputs = pipe(frames=video, image_embeddings=image_embeddings,
                                 generator=torch.Generator().manual_seed(args.seed),
                                 cfg_parallel_group=cfg_group if not args.use_2nd_stage else None,   # rank 1 has no T2To tokens
@@ -178,7 +183,9 @@ def main(args):
             checkpoint_every=args.get("fifo_checkpoint_every", 10),
             # `streaming_decode` (schema extension, default on): every 13-frame chunk is decoded on a side stream of rank
             # chunk % P as soon as it has left the queue, instead of all chunks after the loop — same frames, no decode tail
-            streaming_decode=bool(args.get("streaming_decode", True)))
+            streaming_decode=bool(args.get("streaming_decode", True)),
+            # `ramp_sharding` (schema extension, default on): idle ranks join the ramp-up windows (fifo.RampSharding)
+            ramp_sharding=bool(args.get("ramp_sharding", True)))
         if rank == 0:
             tag = prompt[:20]
             if video is not None:

@@ -42,6 +42,19 @@ def test_cli_runs_end_to_end_on_a_tiny_checkpoint(tmp_path):
     assert _frames(src[0]) == (36, (96, 80, 3))      # 4 chunks x 9 frames of the conditioning clip
     assert _frames(orig[0]) == (9, (96, 80, 3))      # the base clip: 3 latent frames -> 9 frames
     assert _frames(fifo[0]) == (36, (96, 80, 3))     # 12 latent frames emitted by the FIFO stage -> 4 x 9 frames
+    # a second process writes the same videos: every draw (initial noise, conditioning-clip posterior, FIFO re-noise) comes
+    # from generators seeded by the yaml, none from the device's unseeded global RNG
+    import numpy as np
+    first = {k: _all_frames(v[0]) for k, v in (("orig", orig), ("fifo", fifo))}
+    import shutil
+    shutil.rmtree(outs[0])
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "infer_cogvideo_mp_fifo.py"), "--config", os.path.join(root, "tiny_edit.yaml")],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    outs = glob.glob(os.path.join(root, "outputs", "tiny_*"))
+    for k in ("orig", "fifo"):
+        again = _all_frames(glob.glob(os.path.join(outs[0], f"clip1_{k}_moving gradients.mp4"))[0])
+        assert np.array_equal(first[k], again), k
 
 
 def _all_frames(path):
