@@ -468,14 +468,18 @@ def run_ours(args):
             fifo = {"what": f"FIFO stage of a {chunks}-chunk gen.yaml video ({chunks * 13} latent frames = {chunks * 49} video frames of "
                             "480x720) through cogvideo_fifo_mp_v2: real controller, NCCL boundary exchange, device-timed, max over ranks",
                     "chunks": chunks, **st, "wall_s": wall, "emitted_latent_frames": emitted, "latents_finite": finite,
-                    "emitted_tokens_per_s": 1350 * emitted / wall, "s_per_round": wall / st["rounds"],
+                    # the schedule costs `rounds_with_ramp_sharding` window-step equivalents on P ranks (a ramp iteration whose
+                    # windows run on groups of g ranks counts 1 / g); the measured wall over that count is the cost of one such
+                    # step inside the stage (window step + boundary exchange + emit / shift), and the bound is forwards / count
+                    "emitted_tokens_per_s": 1350 * emitted / wall, "s_per_step_equivalent": wall / st["rounds_with_ramp_sharding"],
                     "one_gpu_counterpart_s": one_gpu,
                     "one_gpu_counterpart_is": "window_forwards x this run's measured single-window step time (one GPU runs the windows "
                                               "of an iteration back to back); profiles/ holds a measured 1-GPU run of the same stage",
-                    "speedup_vs_one_gpu": one_gpu / wall, "efficiency_vs_schedule_bound": (one_gpu / wall) / st["schedule_bound_speedup"],
-                    "gen_yaml_24_chunks": {**gen, "projected_wall_s": gen["rounds"] * wall / st["rounds"],
-                                           "projected_speedup_vs_one_gpu": gen["window_forwards"] / gen["rounds"] * (one_gpu / wall)
-                                           / st["schedule_bound_speedup"]}}
+                    "speedup_vs_one_gpu": one_gpu / wall,
+                    "efficiency_vs_schedule_bound": (one_gpu / wall) / st["bound_speedup_with_ramp_sharding"],
+                    "gen_yaml_24_chunks": {**gen, "projected_wall_s": gen["rounds_with_ramp_sharding"] * wall / st["rounds_with_ramp_sharding"],
+                                           "projected_speedup_vs_one_gpu": gen["bound_speedup_with_ramp_sharding"] * (one_gpu / wall)
+                                           / st["bound_speedup_with_ramp_sharding"]}}
 
     if rank == 0:
         hbm, tf_burst, tf_sust, src = measured_peaks()
