@@ -24,7 +24,7 @@ def _run(world, out, decode, port):
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
                "127.0.0.1", "--master-port", str(port), tool, out]
     r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-12000:]
     return torch.load(out)
 
 

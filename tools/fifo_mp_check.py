@@ -25,6 +25,38 @@ dev = torch.device("cuda", local)
 if world > 1:
     if one_gpu:
         dist.init_process_group("gloo")
+        # gloo moves device tensors in collectives but not in send / recv: stage those through the host (this tool only —
+        # the product's transport is NCCL)
+        import torch.distributed.distributed_c10d as c10d
+        _isend, _irecv, _send, _recv = c10d.isend, c10d.irecv, c10d.send, c10d.recv
+
+        class _Landing:
+            def __init__(self, work, host, target):
+                self.work, self.host, self.target = work, host, target
+
+            def wait(self):
+                self.work.wait()
+                self.target.copy_(self.host)
+                return True
+
+        def isend(tensor, dst=None, group=None, tag=0, group_dst=None):
+            return _isend(tensor.cpu(), dst=dst, group=group, tag=tag, group_dst=group_dst)
+
+        def irecv(tensor, src=None, group=None, tag=0, group_src=None):
+            host = torch.empty(tensor.shape, dtype=tensor.dtype)
+            return _Landing(_irecv(host, src=src, group=group, tag=tag, group_src=group_src), host, tensor)
+
+        def send(tensor, dst=None, group=None, tag=0, group_dst=None):
+            _send(tensor.cpu(), dst=dst, group=group, tag=tag, group_dst=group_dst)
+
+        def recv(tensor, src=None, group=None, tag=0, group_src=None):
+            host = torch.empty(tensor.shape, dtype=tensor.dtype)
+            r = _recv(host, src=src, group=group, tag=tag, group_src=group_src)
+            tensor.copy_(host)
+            return r
+
+        for mod in (dist, c10d):
+            mod.isend, mod.irecv, mod.send, mod.recv = isend, irecv, send, recv
     else:
         dist.init_process_group("nccl", device_id=dev)
 pipe = _tiny_pipe().to(dev)
