@@ -251,6 +251,67 @@ def test_tiled_decode_and_encode_vs_oracle(env):
     assert rel_l2(d, ref) < 1.5e-2 and rel_l2(m, refm) < 1.5e-2 and psnr(d, ref) >= 40.0
 
 
+def test_tile_streams_do_not_change_the_tiled_coder(env):
+    """The tiles of a tiled decode / encode are spread over CUDA streams (vae._run_tiles); the frames must be the ones the
+    serial tile loop of the reference order (TG_VAE_TILE_STREAMS=1) produces, bit for bit."""
+    ov, cfg, sd, vae = env
+    from tokensgen_b200 import vae as V
+    g = torch.Generator().manual_seed(16)
+    z = torch.randn(1, 16, 13, 12, 10, generator=g).bfloat16().cuda()
+    x = (torch.rand(1, 3, 9, 96, 80, generator=g) * 2 - 1).bfloat16().cuda()
+    vae.enable_tiling()
+    outs = {}
+    keep = V._TILE_STREAMS
+    try:
+        for n in (1, 3, 4):
+            V._TILE_STREAMS = n
+            outs[n] = (vae.decode(z).sample.clone(), vae.encode(x).latent_dist.parameters.clone())
+    finally:
+        V._TILE_STREAMS = keep
+        vae.disable_tiling()
+    for n in (3, 4):
+        assert torch.equal(outs[n][0], outs[1][0]) and torch.equal(outs[n][1], outs[1][1]), n
+
+
+@pytest.mark.parametrize("C,T,H,W,ratio", [(128, 3, 40, 90, 2), (512, 2, 30, 45, 1), (256, 5, 24, 44, 4),
+                                           (192, 3, 40, 77, 0), (128, 2, 64, 96, 0)])
+def test_staged_norm_act_equals_the_register_fed_kernel(C, T, H, W, ratio):
+    """tg_vae_norm_act takes the shared-memory-staged kernel (1-D bulk copies) for dense tensors of >= 1 MB and the register-fed
+    one otherwise (here: an output with a row pitch); same arithmetic, so the same bits.  Shapes with partial 8 KB runs at the
+    row ends, 24 vectors per pixel (C = 192: idle lanes), odd T (first-frame rule of the zq up-sampling)."""
+    from tokensgen_b200 import _ext as E
+    g = torch.Generator().manual_seed(C + W)
+    x = (torch.randn(T, H, W, C, generator=g) * 1.5 + 0.3).bfloat16().cuda()
+    gamma, beta = torch.randn(C, generator=g).bfloat16().cuda(), torch.randn(C, generator=g).bfloat16().cuda()
+    groups = 32
+    sums = E.vae_group_stats(x, groups)
+    zy = zb = None
+    spatial = ratio > 0
+    if spatial:
+        Tz = (T + 1) // 2 if T > 1 else 1
+        table = torch.randn(Tz, H // ratio, W // ratio, 2 * C + 64, generator=g).bfloat16().cuda()
+        zy, zb = table[..., :C], table[..., C + 64:]
+    dense = torch.empty(T, H, W, C, device="cuda", dtype=torch.bfloat16)
+    pitched = torch.empty(T, H, W, C + 8, device="cuda", dtype=torch.bfloat16)[..., :C]
+    E.vae_norm_act(x, sums, groups, 1e-6, gamma, beta, dense, zy, zb, silu=True)
+    E.vae_norm_act(x, sums, groups, 1e-6, gamma, beta, pitched, zy, zb, silu=True)
+    assert torch.isfinite(dense.float()).all() and torch.equal(dense, pitched)
+    # and against plain torch (fp32 GroupNorm over the whole tensor, nearest up-sampling of the tables)
+    xf = x.float().permute(3, 0, 1, 2).unsqueeze(0)
+    ref = torch.nn.functional.group_norm(xf, groups, gamma.float(), beta.float(), 1e-6)
+    if spatial:
+        def up(t_):
+            t_ = t_.float().permute(3, 0, 1, 2).unsqueeze(0)
+            if T > 1 and T % 2 == 1:
+                first = torch.nn.functional.interpolate(t_[:, :, :1], size=(1, H, W))
+                rest = torch.nn.functional.interpolate(t_[:, :, 1:], size=(T - 1, H, W))
+                return torch.cat([first, rest], dim=2)
+            return torch.nn.functional.interpolate(t_, size=(T, H, W))
+        ref = ref * up(zy) + up(zb)
+    ref = torch.nn.functional.silu(ref)[0].permute(1, 2, 3, 0)
+    assert rel_l2(dense, ref) < 5e-3
+
+
 def test_frames_to_rgb8_matches_host_postprocess_bit_exact():
     """K20: GPU uint8 pack == VideoProcessor.postprocess_video("np") followed by the exporter's
     (frame * 255).round().astype(uint8), including out-of-range and half-way values."""

@@ -20,6 +20,75 @@ __device__ __forceinline__ uint4 pack8v(const float (&f)[8]) {
     v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
     return v;
 }
+// x * sigmoid(x) = x / (1 + 2^(-x log2 e)) on the MUFU pipe (ex2.approx, rcp.approx: 2^-22 relative, far inside bf16), five
+// instructions; `__fdividef(x, 1 + __expf(-x))` is the same value with a range check the denominator (>= 1) never needs
+__device__ __forceinline__ float silu_approx(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
+}
+// One 8-channel vector of K16b on PACKED fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: one issue slot per two results):
+// (x * sc + of) [* zy + zb] [-> SiLU] -> bf16.  Per lane the operations and roundings are those of the scalar form
+// fmaf(fmaf(x, sc, of), zy, zb), silu_approx(.); the kernel needs them because at HBM speed the scalar form fills 70 - 80 % of
+// the issue slots and of the MUFU pipe at once (ncu, profiles/r01_norm_act_full_summary.md) and tops out near 0.55 of the copy peak.
+__device__ __forceinline__ void unpack8p(const uint4& v, uint64_t (&p)[4]) {
+    p[0] = pack_f32x2(bf16_lo(v.x), bf16_hi(v.x));
+    p[1] = pack_f32x2(bf16_lo(v.y), bf16_hi(v.y));
+    p[2] = pack_f32x2(bf16_lo(v.z), bf16_hi(v.z));
+    p[3] = pack_f32x2(bf16_lo(v.w), bf16_hi(v.w));
+}
+template <bool SPATIAL>
+__device__ __forceinline__ uint4 norm8(const uint4& xv, const uint64_t (&sc)[4], const uint64_t (&of)[4], const uint4& yv,
+                                       const uint4& bv, bool silu) {
+    uint64_t f[4];
+    unpack8p(xv, f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = fma_f32x2(f[i], sc[i], of[i]);
+    if (SPATIAL) {
+        uint64_t y[4], b[4];
+        unpack8p(yv, y);
+        unpack8p(bv, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) f[i] = fma_f32x2(f[i], y[i], b[i]);
+    }
+    if (silu) {
+        const uint64_t k = pack_f32x2(-1.4426950408889634f, -1.4426950408889634f), one = pack_f32x2(1.0f, 1.0f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint64_t t = mul_f32x2(f[i], k);
+            const uint64_t d = add_f32x2(pack_f32x2(fast_exp2(f32x2_lo(t)), fast_exp2(f32x2_hi(t))), one);
+            float r0, r1;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(f32x2_lo(d)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(f32x2_hi(d)));
+            f[i] = mul_f32x2(f[i], pack_f32x2(r0, r1));
+        }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(f32x2_lo(f[0]), f32x2_hi(f[0]));
+    o.y = pack_bf16x2(f32x2_lo(f[1]), f32x2_hi(f[1]));
+    o.z = pack_bf16x2(f32x2_lo(f[2]), f32x2_hi(f[2]));
+    o.w = pack_bf16x2(f32x2_lo(f[3]), f32x2_hi(f[3]));
+    return o;
+}
+// per-thread constants of K16b: this thread always handles channels [8v, 8v+8)
+__device__ __forceinline__ void norm_consts(const tg_norm_args& a, const float* sh_mean, const float* sh_rstd, int v, int cg,
+                                            uint64_t (&sc2)[4], uint64_t (&of2)[4]) {
+    float gm[8], bt[8], sc[8], of[8];
+    unpack8v(__ldg(reinterpret_cast<const uint4*>(a.gamma) + v), gm);
+    unpack8v(__ldg(reinterpret_cast<const uint4*>(a.beta) + v), bt);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (v * 8 + j) / cg;
+        sc[j] = sh_rstd[g] * gm[j];
+        of[j] = fmaf(-sh_mean[g], sc[j], bt[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sc2[i] = pack_f32x2(sc[2 * i], sc[2 * i + 1]);
+        of2[i] = pack_f32x2(of[2 * i], of[2 * i + 1]);
+    }
+}
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 static inline int grid_for(int64_t work_items, int threads = 256) {
@@ -93,30 +162,13 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ t
     const int ppb = 256 / V;
     const int v = threadIdx.x % V, pl = threadIdx.x / V;
     if (pl >= ppb) return;
-    // per-thread constants: this thread always handles channels [8v, 8v+8)
-    float sc[8], of[8];
-    {
-        float gm[8], bt[8];
-        unpack8v(__ldg(reinterpret_cast<const uint4*>(a.gamma) + v), gm);
-        unpack8v(__ldg(reinterpret_cast<const uint4*>(a.beta) + v), bt);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int g = (v * 8 + j) / cg;
-            sc[j] = sh_rstd[g] * gm[j];
-            of[j] = fmaf(-sh_mean[g], sc[j], bt[j]);
-        }
-    }
+    uint64_t sc[4], of[4];
+    norm_consts(a, sh_mean, sh_rstd, v, cg, sc, of);
     if (a.zy == nullptr) {
+        const uint4 none = make_uint4(0, 0, 0, 0);
         for (int64_t p = int64_t(blockIdx.x) * ppb + pl; p < pixels; p += int64_t(gridDim.x) * ppb) {
-            float f[8];
-            unpack8v(__ldg(reinterpret_cast<const uint4*>(a.x + p * a.ldx) + v), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], of[j]);
-            if (a.silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
-            }
-            reinterpret_cast<uint4*>(a.y + p * a.ldy)[v] = pack8v(f);
+            const uint4 xv = __ldg(reinterpret_cast<const uint4*>(a.x + p * a.ldx) + v);
+            reinterpret_cast<uint4*>(a.y + p * a.ldy)[v] = norm8<false>(xv, sc, of, none, none, a.silu != 0);
         }
         return;
     }
@@ -141,23 +193,154 @@ __global__ void __launch_bounds__(256) norm_act_kernel(const __grid_constant__ t
         const tg_bf16* x_row = a.x + int64_t(row) * a.W * a.ldx;
         tg_bf16* y_row = a.y + int64_t(row) * a.W * a.ldy;
         for (int w = pl; w < a.W; w += ppb) {
-            float f[8], y[8], b[8];
             const int wz = wshift >= 0 ? (w >> wshift) : (w * a.Wz) / a.W;
             const uint4 xv = __ldg(reinterpret_cast<const uint4*>(x_row + int64_t(w) * a.ldx) + v);
             const uint4 yv = __ldg(zy_row + wz * ldz4);
             const uint4 bv = __ldg(zb_row + wz * ldz4);
-            unpack8v(xv, f);
-            unpack8v(yv, y);
-            unpack8v(bv, b);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf(f[j], sc[j], of[j]), y[j], b[j]);
-            if (a.silu) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = __fdividef(f[j], 1.0f + __expf(-f[j]));
-            }
-            reinterpret_cast<uint4*>(y_row + int64_t(w) * a.ldy)[v] = pack8v(f);
+            reinterpret_cast<uint4*>(y_row + int64_t(w) * a.ldy)[v] = norm8<true>(xv, sc, of, yv, bv, a.silu != 0);
         }
     }
+}
+
+// K16b, staged: the same arithmetic for DENSE tensors (ldx == ldy == C) of 128 / 256 / 512 channels, with the activation
+// streamed through shared memory by 1-D bulk copies (`cp.async.bulk`, mbarrier completion).  The register-fed kernel above keeps
+// one 16-byte load per thread in flight — 60 registers x 1024 threads = 16 KB per SM, about a third of what HBM3e's latency x
+// bandwidth needs (3.6 TB/s isolated); here every block keeps NA_STAGES x 16 KB of loads in flight whatever the register count
+// (4 blocks per SM = 192 KB), and the registers only ever hold the vector being normalised.
+// Work item = a 16 KB run of pixels inside one image row (T, H) — rows because the SpatialNorm source indices (tz, hz) are per
+// row; without zq the whole tensor is one "row".  Items are dealt round-robin to the blocks; vector e of a run sits at
+// shared-memory offset 16 e and belongs to thread e % 256, so every address in the loop is a constant offset from a per-run base.
+constexpr int NA_CHUNK = 16384;
+constexpr int NA_STAGES = 3;
+constexpr int NA_SMEM = NA_STAGES * NA_CHUNK + 1024;
+
+template <int V>   // 16-byte vectors per pixel: C = 8 V
+__global__ void __launch_bounds__(256, 4)
+norm_act_staged_kernel(const __grid_constant__ tg_norm_args a, int chunks_per_row, int row_px, int rows) {
+    constexpr int PPB = 256 / V;                     // pixels one pass of the block covers
+    constexpr int PX_CHUNK = NA_CHUNK / (16 * V);    // pixels per full run
+    constexpr int PASSES = PX_CHUNK / PPB;           // = NA_CHUNK / 4096
+    extern __shared__ __align__(128) uint8_t na_smem[];
+    uint8_t* stage_mem = na_smem;
+    uint64_t* full = reinterpret_cast<uint64_t*>(na_smem + NA_STAGES * NA_CHUNK);
+    int64_t* z_off = reinterpret_cast<int64_t*>(na_smem + NA_STAGES * NA_CHUNK + 64);
+    float* sh_mean = reinterpret_cast<float*>(na_smem + NA_STAGES * NA_CHUNK + 128);
+    float* sh_rstd = sh_mean + 64;
+    constexpr int C = 8 * V;
+    const int cg = C / a.groups;
+    const double cnt = double(a.T) * a.H * a.W * cg;
+    for (int g = threadIdx.x; g < a.groups; g += 256) {
+        const double m = a.sums[g] / cnt;
+        double var = a.sums[a.groups + g] / cnt - m * m;
+        if (var < 0) var = 0;
+        sh_mean[g] = float(m);
+        sh_rstd[g] = float(1.0 / sqrt(var + double(a.eps)));
+    }
+    const uint32_t mem0 = smem_u32(stage_mem), bar0 = smem_u32(full);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA_STAGES; ++s) mbar_init(bar0 + 8 * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    // Items advance by gridDim.x per pass: (row, run) is stepped with a carry instead of divided out of the item number
+    const int step_row = int(gridDim.x) / chunks_per_row, step_c = int(gridDim.x) % chunks_per_row;
+    struct Cursor {
+        int row, c;
+    };
+    auto advance = [&](Cursor& q) {
+        q.row += step_row;
+        q.c += step_c;
+        if (q.c >= chunks_per_row) {
+            q.c -= chunks_per_row;
+            ++q.row;
+        }
+    };
+    const bool spatial = a.zy != nullptr;
+    const bool odd_t = a.T > 1 && (a.T & 1);
+    const int64_t ldz = a.ldz > 0 ? a.ldz : C;
+    auto issue = [&](const Cursor& q, int s) {       // thread 0 only
+        const int w0 = q.c * PX_CHUNK;
+        const int npx = min(row_px - w0, PX_CHUNK);
+        if (spatial) {
+            // the divisions of the row's zq source indices happen here, once per item, off the workers' path
+            const int t = q.row / a.H, h = q.row - t * a.H;
+            // nearest source index of F.interpolate; first frame apart when T is odd and > 1 (autoencoder_kl_cogvideox.py:176-186)
+            const int tz = odd_t ? (t == 0 ? 0 : 1 + ((t - 1) * (a.Tz - 1)) / (a.T - 1)) : (t * a.Tz) / a.T;
+            const int hz = (h * a.Hz) / a.H;
+            z_off[s] = (int64_t(tz) * a.Hz + hz) * a.Wz * ldz;   // ordered before the workers' reads by the mbarrier (release / acquire)
+        }
+        const uint32_t bytes = uint32_t(npx) * uint32_t(C) * 2u;
+        mbar_arrive_expect_tx(bar0 + 8 * s, bytes);
+        bulk_load_1d(mem0 + s * NA_CHUNK, a.x + (int64_t(q.row) * row_px + w0) * C, bytes, bar0 + 8 * s);
+    };
+    Cursor cur{int(blockIdx.x) / chunks_per_row, int(blockIdx.x) % chunks_per_row};
+    Cursor ahead = cur;                              // thread 0: the next item to load
+    if (threadIdx.x == 0)
+        for (int k = 0; k < NA_STAGES && ahead.row < rows; ++k, advance(ahead)) issue(ahead, k);
+
+    const int v = threadIdx.x % V, pl = threadIdx.x / V;
+    uint64_t sc[4], of[4];
+    norm_consts(a, sh_mean, sh_rstd, v, cg, sc, of);
+    int wshift = -1;
+    if (spatial && a.W % a.Wz == 0) {
+        const int ratio = a.W / a.Wz;
+        if ((ratio & (ratio - 1)) == 0) wshift = 31 - __clz(ratio);
+    }
+    const int ldz4 = int(ldz / 8);
+    const bool silu = a.silu != 0;
+    const uint4 none = make_uint4(0, 0, 0, 0);
+
+    int s = 0;
+    uint32_t parity = 0;
+    for (; cur.row < rows; advance(cur)) {           // block-uniform
+        const int w0 = cur.c * PX_CHUNK;
+        const int npx = min(row_px - w0, PX_CHUNK);
+        mbar_wait(bar0 + 8 * s, parity, 0x501);
+        const uint4* src = reinterpret_cast<const uint4*>(stage_mem + s * NA_CHUNK) + threadIdx.x;
+        uint4* dst = reinterpret_cast<uint4*>(a.y) + (int64_t(cur.row) * row_px + w0) * V + threadIdx.x;
+        if (!spatial) {
+#pragma unroll
+            for (int k = 0; k < PASSES; ++k)
+                if (pl + k * PPB < npx) dst[k * 256] = norm8<false>(src[k * 256], sc, of, none, none, silu);
+        } else {
+            const int64_t zo = z_off[s];
+            const uint4* zy_row = reinterpret_cast<const uint4*>(a.zy + zo) + v;
+            const uint4* zb_row = reinterpret_cast<const uint4*>(a.zb + zo) + v;
+#pragma unroll
+            for (int k = 0; k < PASSES; ++k) {
+                const int w = w0 + pl + k * PPB;
+                if (pl + k * PPB < npx) {
+                    const int wz = wshift >= 0 ? (w >> wshift) : (w * a.Wz) / a.W;
+                    dst[k * 256] = norm8<true>(src[k * 256], sc, of, __ldg(zy_row + wz * ldz4), __ldg(zb_row + wz * ldz4), silu);
+                }
+            }
+        }
+        __syncthreads();                            // every thread is done with stage s: refill it
+        if (threadIdx.x == 0 && ahead.row < rows) {
+            issue(ahead, s);
+            advance(ahead);
+        }
+        if (++s == NA_STAGES) {
+            s = 0;
+            parity ^= 1u;
+        }
+    }
+}
+
+template <int V>
+static int launch_norm_act_staged(const tg_norm_args* a, cudaStream_t st) {
+    // per launch: the attribute belongs to the current device's copy of the function (a host-side setter, no driver round trip)
+    if (cudaFuncSetAttribute(norm_act_staged_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, NA_SMEM) != cudaSuccess)
+        return fail(-6, "vae_norm_act: cannot reserve %d bytes of shared memory", NA_SMEM);
+    const int64_t pixels = int64_t(a->T) * a->H * a->W;
+    const int px_chunk = NA_CHUNK / (16 * V);
+    const int64_t row_px = a->zy != nullptr ? a->W : pixels;
+    const int64_t rows = a->zy != nullptr ? int64_t(a->T) * a->H : 1;
+    const int64_t cpr = (row_px + px_chunk - 1) / px_chunk;
+    int64_t nb = int64_t(sm_count()) * 4;
+    if (nb > rows * cpr) nb = rows * cpr;
+    norm_act_staged_kernel<V><<<int(nb), 256, NA_SMEM, st>>>(*a, int(cpr), int(row_px), int(rows));
+    return check_launch("vae_norm_act");
 }
 
 // ------------------------------------------------------------------------------------------------ K17 resampling
@@ -308,6 +491,17 @@ extern "C" int tg_vae_norm_act(const tg_norm_args* a, void* stream) {
     if (a->zy != nullptr && (a->Tz <= 0 || a->Hz <= 0 || a->Wz <= 0 || a->Tz > a->T)) return fail(-4, "vae_norm_act: bad latent grid");
     const int ppb = 256 / (a->C / 8);
     const int64_t pixels = int64_t(a->T) * a->H * a->W;
+    if (a->ldx == a->C && a->ldy == a->C && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->y) & 15) == 0 &&
+        pixels * a->C * 2 >= (int64_t(1) << 20) && pixels < (int64_t(1) << 30)) {
+        // dense and large enough to be bandwidth-bound: the staged kernel
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        switch (a->C) {
+            case 128: return launch_norm_act_staged<16>(a, st);
+            case 256: return launch_norm_act_staged<32>(a, st);
+            case 512: return launch_norm_act_staged<64>(a, st);
+            default: break;
+        }
+    }
     int64_t blocks = a->zy != nullptr ? int64_t(a->T) * a->H : (pixels + ppb - 1) / ppb;   // spatial: one image row per block pass
     const int64_t cap = int64_t(sm_count()) * 8;
     if (blocks > cap) blocks = cap;

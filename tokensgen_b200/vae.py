@@ -305,6 +305,8 @@ def _norm_silu_into(norm, x, out: torch.Tensor, zq: Optional[_ZqTables]):
 # GroupNorm statistics in the producing convolution's epilogue (False: the separate statistics pass, tg_vae_group_stats)
 import os as _os
 _FUSED_STATS = _os.environ.get("TG_VAE_FUSED_STATS", "1") != "0"
+# CUDA streams the independent tiles of a tiled encode / decode are spread over (1: the reference's serial tile loop)
+_TILE_STREAMS = int(_os.environ.get("TG_VAE_TILE_STREAMS", "3"))
 
 
 def _resnet(blk: CogVideoXResnetBlock3D, xa, zq: Optional[_ZqTables], next_groups: int = 0) -> "_Act":
@@ -542,6 +544,54 @@ class AutoencoderKLCogVideoX(nn.Module):
             out_rows.append(torch.cat(parts, dim=3))
         return torch.cat(out_rows, dim=2)
 
+    def _causal_convs(self):
+        lst = self.__dict__.get("_tg_causal_convs")
+        if lst is None:
+            lst = [m for m in self.modules() if isinstance(m, CogVideoXCausalConv3d)]
+            self.__dict__["_tg_causal_convs"] = lst
+        return lst
+
+    def _run_tiles(self, tiles, ranges, batch_fn, alloc_fn):
+        """The tiles of a tiled encode / decode are independent causal streams (the reference runs them one after the other,
+        :1256-1285, :1317-1340).  Here their frame batches are issued round-robin onto `_TILE_STREAMS` CUDA streams, each tile
+        with its own conv-cache state, so one tile's small launches (a 30 x 45 latent tile fills 64 of 148 SMs in the 512-channel
+        blocks), launch gaps and wave tails are covered by the other tiles' kernels.  Every kernel's result is independent of
+        what runs beside it: the outputs are those of the serial loop.
+        tiles: input tensors [C, T, h, w]; alloc_fn(tile) -> output planes; batch_fn(tile[:, a:b], out[:, t0:], stride) -> frames."""
+        convs = self._causal_convs()
+        n_streams = max(1, min(_TILE_STREAMS, len(tiles)))
+        main = torch.cuda.current_stream()
+        if n_streams > 1:
+            pool = self.__dict__.setdefault("_tg_tile_streams", {})
+            key = (main.device, n_streams)
+            if key not in pool:
+                pool[key] = [torch.cuda.Stream(device=main.device) for _ in range(n_streams - 1)]
+            streams = [main] + pool[key]
+        else:
+            streams = [main]
+        outs = [alloc_fn(t) for t in tiles]
+        state = [[None] * len(convs) for _ in tiles]
+        t0 = [0] * len(tiles)
+        forked = n_streams == 1
+        for a, b in ranges:
+            for ti, tile in enumerate(tiles):
+                if not forked and ti == 1:
+                    # the first batch of tile 0 (main stream) has packed the weights / zq tables every stream reads from here on
+                    for st in streams[1:]:
+                        st.wait_stream(main)
+                    forked = True
+                with torch.cuda.stream(streams[ti % n_streams]):
+                    for m, c in zip(convs, state[ti]):
+                        m.conv_cache = c
+                    t0[ti] += batch_fn(tile[:, a:b].contiguous(), outs[ti][:, t0[ti]:], outs[ti].stride(0))
+                    state[ti] = [m.conv_cache for m in convs]
+        for st in streams[1:]:
+            main.wait_stream(st)
+        self._clear_fake_context_parallel_cache()
+        for o, n in zip(outs, t0):
+            assert n == o.shape[1], (n, o.shape)
+        return outs
+
     def _tiled_decode_one(self, z: torch.Tensor) -> torch.Tensor:
         lh, lw, sh, sw = self.tile_latent_min_height, self.tile_latent_min_width, self.tile_sample_min_height, self.tile_sample_min_width
         ov_h, ov_w = int(lh * (1 - self.tile_overlap_factor_height)), int(lw * (1 - self.tile_overlap_factor_width))
@@ -549,17 +599,18 @@ class AutoencoderKLCogVideoX(nn.Module):
         T = z.shape[1]
         nf = self.decode_chunk_frames
         fb = self.num_latent_frames_batch_size
-        rows = []
-        for i in range(0, z.shape[2], ov_h):
-            row = []
-            for j in range(0, z.shape[3], ov_w):
-                zt = z[:, :, i:i + lh, j:j + lw]
-                if T % nf == 0:  # in-tree variant (:1317-1337): 13-frame chunks back to back, cache NOT cleared in between
-                    ranges = [(k1 * nf + a, k1 * nf + b) for k1 in range(T // nf) for a, b in self._frame_batches(nf, fb, False)]
-                else:            # the diffusers runtime class: plain frame batching (identical for 13 frames)
-                    ranges = self._frame_batches(T, fb, False)
-                row.append(self._decode_stream(zt, ranges))
-            rows.append(row)
+        if T % nf == 0:  # in-tree variant (:1317-1337): 13-frame chunks back to back, cache NOT cleared in between
+            ranges = [(k1 * nf + a, k1 * nf + b) for k1 in range(T // nf) for a, b in self._frame_batches(nf, fb, False)]
+        else:            # the diffusers runtime class: plain frame batching (identical for 13 frames)
+            ranges = self._frame_batches(T, fb, False)
+        ii, jj = list(range(0, z.shape[2], ov_h)), list(range(0, z.shape[3], ov_w))
+        tiles = [z[:, :, i:i + lh, j:j + lw] for i in ii for j in jj]
+        ratio = 2 ** (len(self.config.block_out_channels) - 1)
+        n_out = sum(self._sample_frames(b - a) for a, b in ranges)
+        alloc = lambda t: torch.empty(self.config.out_channels, n_out, t.shape[2] * ratio, t.shape[3] * ratio, device=z.device,
+                                      dtype=torch.bfloat16)
+        outs = self._run_tiles(tiles, ranges, self._decoder_batch, alloc)
+        rows = [outs[r * len(jj):(r + 1) * len(jj)] for r in range(len(ii))]
         return self._assemble(rows, be_w, be_h, sh - be_h, sw - be_w)
 
     def _decode_stream(self, z: torch.Tensor, ranges) -> torch.Tensor:
@@ -579,12 +630,14 @@ class AutoencoderKLCogVideoX(nn.Module):
         ov_h, ov_w = int(sh * (1 - self.tile_overlap_factor_height)), int(sw * (1 - self.tile_overlap_factor_width))
         be_h, be_w = int(lh * self.tile_overlap_factor_height), int(lw * self.tile_overlap_factor_width)
         ranges = self._frame_batches(x.shape[1], self.num_sample_frames_batch_size, True)
-        rows = []
-        for i in range(0, x.shape[2], ov_h):
-            row = []
-            for j in range(0, x.shape[3], ov_w):
-                row.append(self._encode_one(x[:, :, i:i + sh, j:j + sw], ranges))
-            rows.append(row)
+        ii, jj = list(range(0, x.shape[2], ov_h)), list(range(0, x.shape[3], ov_w))
+        tiles = [x[:, :, i:i + sh, j:j + sw] for i in ii for j in jj]
+        ratio = 2 ** (len(self.config.block_out_channels) - 1)
+        t_lat = sum(self._latent_frames(b - a) for a, b in ranges)
+        alloc = lambda t: torch.empty(2 * self.config.latent_channels, t_lat, t.shape[2] // ratio, t.shape[3] // ratio,
+                                      device=x.device, dtype=torch.bfloat16)
+        outs = self._run_tiles(tiles, ranges, self._encoder_batch, alloc)
+        rows = [outs[r * len(jj):(r + 1) * len(jj)] for r in range(len(ii))]
         return self._assemble(rows, be_w, be_h, lh - be_h, lw - be_w)
 
     # ---- public encode / decode (:1085-1188)

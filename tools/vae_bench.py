@@ -52,6 +52,14 @@ def run(fn, tiled):
             per["gemm_1x1"] = per.get("gemm_1x1", 0.0) + t
         else:
             per[k] = per.get(k, 0.0) + t
+    if os.environ.get("TG_VAE_BY_LAYER") == "1":      # developer view: every distinct launch shape, worst total first
+        rows = []
+        for k, v in prof.items():
+            t = sum(a.elapsed_time(b) for a, b in v)
+            tf = conv_flops(k) * len(v) / t / 1e9 if k.startswith("vae_conv") else 0.0
+            rows.append((t, k, len(v), tf))
+        for t, k, n, tf in sorted(rows, reverse=True)[:40]:
+            print(f"  {t:8.2f} ms  x{n:<4d} {k}" + (f"  {tf:7.1f} TFLOP/s" if tf else ""), file=sys.stderr)
     out = {k: round(v, 2) for k, v in sorted(per.items(), key=lambda kv: -kv[1])}
     for name, (b, t) in hbm.items():
         if t > 0:
