@@ -135,6 +135,35 @@ def test_conv_tap_reuse_kernel(cin, cout, T, H, W, res):
     assert rel_l2(y, ref) < 5e-3
 
 
+@pytest.mark.parametrize("T,H,W", [(3, 150, 301), (8, 240, 360), (1, 20, 40)])
+def test_narrow_output_conv(T, H, W):
+    """The decoder's conv_out (128 -> 3, channel-plane output).  At full resolution the layer is bound by the delivery of its
+    activation boxes, so it runs on the tap-reuse CTA-pair kernel with ONE 32-column tile (conv3_kernel<32>: 9 boxes per pixel
+    tile instead of 27, N = 32 MMAs instead of 64 padded columns); small maps stay on the single-CTA kernel.  Against torch
+    conv3d; the zero-padded weight rows must not leak into the three planes or past them."""
+    from tokensgen_b200 import _ext as E
+    from tokensgen_b200.vae import _PackedConv
+    g = torch.Generator().manual_seed(77 + W)
+    cin, cout = 128, 3
+    conv = torch.nn.Conv3d(cin, cout, 3)
+    with torch.no_grad():
+        conv.weight.copy_(torch.randn(conv.weight.shape, generator=g) / (27 * cin) ** 0.5)
+        conv.bias.copy_(torch.randn(cout, generator=g))
+    conv = conv.to(torch.bfloat16).cuda()
+    x = torch.randn(1, cin, T + 2, H, W, generator=g).bfloat16()
+    ref = torch.nn.functional.conv3d(torch.nn.functional.pad(x.float(), (1, 1, 1, 1)).cuda(), conv.weight.float(), conv.bias.float())[0]
+    xc = x[0].permute(1, 2, 3, 0).contiguous().cuda()
+    w, b = _PackedConv().get(conv)
+    planes = torch.full((cout, T + 1, H, W), 7.0, device="cuda", dtype=torch.bfloat16)   # one spare frame: must stay untouched
+    E.vae_conv(xc, w, b, cout, 3, 3, 3, T, H, W, planes_out=planes, plane_stride=planes.stride(0))
+    torch.cuda.synchronize()
+    assert (planes[:, T] == 7.0).all()
+    assert rel_l2(planes[:, :T], ref) < 5e-3
+    # and channels-last with a row pitch (the generic epilogue path)
+    y = E.vae_conv(xc, w, b, cout, 3, 3, 3, T, H, W)
+    assert y.shape == (T, H, W, cout) and rel_l2(y.permute(3, 0, 1, 2), ref) < 5e-3
+
+
 def test_spatial_norm_silu_vs_oracle(env):
     ov, cfg, sd, vae = env
     from tokensgen_b200 import vae as V

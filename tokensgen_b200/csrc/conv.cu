@@ -553,22 +553,28 @@ constexpr int C3_TW = 128, C3_TH = 2;
 constexpr int C3_ROW_BYTES = (C3_TW + 2) * 128;                       // one h row of the halo'd box: 130 pixels x 64 c
 constexpr int C3_A_BYTES = C3_TH * C3_ROW_BYTES;                       // 33 280 B delivered by the TMA
 constexpr int C3_A_SLOT = (C3_A_BYTES + 1023) / 1024 * 1024;           // 33 792 B
-constexpr int C3_HALF_N = 64;                                           // weight rows (output channels) this CTA loads
-constexpr int C3_B_BYTES = C3_HALF_N * 64 * 2;                          // 8 KB per tap
-constexpr int C3_STAGE_BYTES = C3_A_SLOT + 3 * C3_B_BYTES;             // 58 368 B
-constexpr int C3_STAGE_TX = C3_A_BYTES + 3 * C3_B_BYTES;               // bytes the TMA actually delivers per CTA and stage
-constexpr int C3_STAGES = 3;
-constexpr int C3_SMEM_BYTES = C3_STAGES * C3_STAGE_BYTES + 256 + 1024;
+// BLOCK_N output channels per tile (128; 32 for the narrow conv_out, whose MMAs at N = 128 would cost more than its boxes):
+// each CTA of the pair loads BLOCK_N / 2 weight rows per tap
+template <int BLOCK_N>
+struct Conv3Cfg {
+    static constexpr int HALF_N = BLOCK_N / 2;
+    static constexpr int B_BYTES = HALF_N * 64 * 2;                      // 8 KB (2 KB) per tap
+    static constexpr int STAGE_BYTES = C3_A_SLOT + 3 * B_BYTES;         // 58 368 B (39 936 B)
+    static constexpr int STAGE_TX = C3_A_BYTES + 3 * B_BYTES;           // bytes the TMA actually delivers per CTA and stage
+    static constexpr int STAGES = BLOCK_N == 128 ? 3 : 5;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+};
 
+template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
 conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
              const __grid_constant__ ConvParams p) {
-    constexpr int BLOCK_N = 128;
-    constexpr int STAGES = C3_STAGES;
+    using Cfg = Conv3Cfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     __shared__ float sh_stats[4 * 2 * CV_MAX_GROUPS];   // one row per epilogue warp
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + STAGES * C3_STAGE_BYTES;
+    const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -629,15 +635,15 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                     for (int ih = 0; ih < p.kh; ++ih)
                         for (int cc = 0; cc < p.c_chunks; ++cc) {
                             mbar_wait(empty_bar(stage), phase ^ 1u, 0x4a1);
-                            const uint32_t sa = smem_base + stage * C3_STAGE_BYTES;
+                            const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                             const uint32_t bar = mapa_shared(full_bar(stage), 0);
-                            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C3_STAGE_TX);
+                            if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_TX);
                             tma_load_4d_2cta(sa, &tmap_x, bar, cc * 64, w_in0, h_in0 + ih, t + it);
 #pragma unroll
                             for (int iw = 0; iw < 3; ++iw) {
                                 const int kb = ((it * p.kh + ih) * 3 + iw) * p.c_chunks + cc;
-                                tma_load_2d_2cta(sa + C3_A_SLOT + iw * C3_B_BYTES, &tmap_w, bar, kb * 64,
-                                                 nt * BLOCK_N + rank * C3_HALF_N);
+                                tma_load_2d_2cta(sa + C3_A_SLOT + iw * Cfg::B_BYTES, &tmap_w, bar, kb * 64,
+                                                 nt * BLOCK_N + rank * Cfg::HALF_N);
                             }
                             if (++stage == STAGES) {
                                 stage = 0;
@@ -660,7 +666,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(full_bar(stage), phase, 0x4a3);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + stage * C3_STAGE_BYTES;
+                    const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
                     const uint32_t sb = sa + C3_A_SLOT;
 #pragma unroll
                     for (int row = 0; row < C3_TH; ++row)
@@ -669,7 +675,7 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const uint64_t da = make_smem_desc_sw128(sa + row * C3_ROW_BYTES + iw * 128 + k * 32, 16, 1024);
-                                const uint64_t db = make_smem_desc_sw128(sb + iw * C3_B_BYTES + k * 32, 16, 1024);
+                                const uint64_t db = make_smem_desc_sw128(sb + iw * Cfg::B_BYTES + k * 32, 16, 1024);
                                 umma_ss_2cta(d_tmem + uint32_t(row * BLOCK_N), da, db, idesc, (kb | iw | k) != 0 ? 1u : 0u);
                             }
                     umma_commit_2cta(empty_bar(stage), 0b11);
@@ -722,16 +728,18 @@ conv3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__
     }
 }
 
+template <int BLOCK_N>
 static int launch_conv3(const CUtensorMap& tx, const CUtensorMap& tw, const ConvParams& p, cudaStream_t stream) {
+    using Cfg = Conv3Cfg<BLOCK_N>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES);
-        if (e != cudaSuccess) return fail(int(e), "vae_conv: cudaFuncSetAttribute(smem=%d): %s", C3_SMEM_BYTES, cudaGetErrorString(e));
+        cudaError_t e = cudaFuncSetAttribute(conv3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) return fail(int(e), "vae_conv: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e));
         attr_set = true;
     }
     const int tiles = ((p.T_out * p.h_tiles * p.w_tiles + 1) / 2) * p.n_tiles;
     const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
-    conv3_kernel<<<2 * clusters, 256, C3_SMEM_BYTES, stream>>>(tx, tw, p);
+    conv3_kernel<BLOCK_N><<<2 * clusters, 256, Cfg::SMEM_BYTES, stream>>>(tx, tw, p);
     return check_launch("vae_conv");
 }
 
@@ -809,7 +817,17 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     {
         // tap-reuse kernel: stride 1, kw = 3, 128-channel weight tiles, at least two waves of pair tiles
         const int64_t t3 = int64_t(a->T_out) * ((a->H_out + C3_TH - 1) / C3_TH) * ((a->W_out + C3_TW - 1) / C3_TW);
-        if (g_conv_impl == 3 && s == 1 && a->kw == 3 && a->Cout_pad % 128 == 0 && ((t3 + 1) / 2) * (a->Cout_pad / 128) >= sm_count()) {
+        // ... and a width its 128-pixel tiles cover without much overhang: a 180-wide layer (the 120 x 180 level, every tile of
+        // the tiled coder at 1/4 resolution) computes 256 columns there but 192 with the 8 x 32 tiles of the kernels below,
+        // which more than pays for their three-fold activation traffic (the tap-reuse kernel is ~10 % faster at equal work)
+        const int64_t area3 = int64_t((a->W_out + C3_TW - 1) / C3_TW * C3_TW) * ((a->H_out + C3_TH - 1) / C3_TH * C3_TH);
+        const int64_t area2 = int64_t((a->W_out + CV_TW - 1) / CV_TW * CV_TW) * ((a->H_out + CV_TH - 1) / CV_TH * CV_TH);
+        // narrow outputs (the decoder's 128 -> 3 conv_out): one 32-column tile instead of 64 padded columns
+        const bool narrow = a->Cout <= 32;
+        const int bn3 = narrow ? 32 : 128;
+        const int n_tiles3 = narrow ? 1 : a->Cout_pad / 128;
+        if (g_conv_impl == 3 && s == 1 && a->kw == 3 && (narrow || a->Cout_pad % 128 == 0) && ((t3 + 1) / 2) * n_tiles3 >= sm_count() &&
+            area3 * 100 <= area2 * 112) {
             const uint64_t dims3[4] = {uint64_t(a->Cin), uint64_t(a->W_in), uint64_t(a->H_in), uint64_t(a->T_in)};
             const uint64_t strides3[3] = {uint64_t(a->Cin) * 2, uint64_t(a->W_in) * a->Cin * 2, uint64_t(a->H_in) * a->W_in * a->Cin * 2};
             const uint32_t box3[4] = {64, uint32_t(C3_TW + 2), uint32_t(C3_TH), 1};
@@ -817,7 +835,7 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
             int rc3 = make_tmap_nd(&tx, a->x, 4, dims3, strides3, box3, estr3);
             if (rc3) return rc3;
             const int K3 = a->kt * a->kh * a->kw * a->Cin;
-            rc3 = make_tmap_2d(&tw, a->w, uint64_t(K3), uint64_t(a->Cout_pad), uint64_t(K3) * 2, 64, uint32_t(C3_HALF_N));
+            rc3 = make_tmap_2d(&tw, a->w, uint64_t(K3), uint64_t(a->Cout_pad), uint64_t(K3) * 2, 64, uint32_t(bn3 / 2));
             if (rc3) return rc3;
             ConvParams p{};
             p.T_out = a->T_out; p.H_out = a->H_out; p.W_out = a->W_out; p.Cout = a->Cout;
@@ -825,7 +843,7 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
             p.c_chunks = a->Cin / 64;
             p.h_tiles = (a->H_out + C3_TH - 1) / C3_TH;
             p.w_tiles = (a->W_out + C3_TW - 1) / C3_TW;
-            p.n_tiles = a->Cout_pad / 128;
+            p.n_tiles = n_tiles3;
             p.bias = reinterpret_cast<const __nv_bfloat16*>(a->bias);
             p.residual = reinterpret_cast<const __nv_bfloat16*>(a->residual);
             p.ld_res = a->ld_res;
@@ -835,7 +853,8 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
             p.layout = a->layout;
             p.stats = a->stats;
             p.stat_groups = a->stat_groups;
-            return launch_conv3(tx, tw, p, static_cast<cudaStream_t>(stream));
+            return narrow ? launch_conv3<32>(tx, tw, p, static_cast<cudaStream_t>(stream))
+                          : launch_conv3<128>(tx, tw, p, static_cast<cudaStream_t>(stream));
         }
     }
     const uint64_t dims[4] = {uint64_t(a->Cin), uint64_t(a->W_in), uint64_t(a->H_in), uint64_t(a->T_in)};
@@ -849,7 +868,12 @@ extern "C" int tg_vae_conv(const tg_conv_args* a, void* stream) {
     // where there would be fewer than two waves of pair tiles
     const int64_t px_tiles = int64_t(a->T_out) * ((a->H_out + CV_TH - 1) / CV_TH) * ((a->W_out + CV_TW - 1) / CV_TW);
     const int pair_bn = a->Cout_pad % 256 == 0 ? 256 : 128;
-    const bool pair = g_conv_impl >= 2 && a->Cout_pad % 128 == 0 && ((px_tiles + 1) / 2) * (a->Cout_pad / pair_bn) >= sm_count();
+    // ... unless the pair tiles fit ONE round of the machine where the single-CTA tiles need two or more: a pair CTA computes
+    // twice the output columns from the same activation box (60 x 90 x 512 layers: 96 CTAs x 1 round instead of 192 tiles on 148)
+    const int64_t pair_tiles = ((px_tiles + 1) / 2) * (a->Cout_pad / pair_bn);
+    const int64_t rounds1 = (px_tiles * (a->Cout_pad / 128) + sm_count() - 1) / sm_count();
+    const int64_t rounds2 = (2 * pair_tiles + sm_count() - 1) / sm_count();
+    const bool pair = g_conv_impl >= 2 && a->Cout_pad % 128 == 0 && (pair_tiles >= sm_count() || rounds2 * 4 < rounds1 * 3);
     const int bn = pair ? (a->Cout_pad % 256 == 0 ? 256 : 128) : ((a->Cout_pad % 128 == 0) ? 128 : 64);
     rc = make_tmap_2d(&tw, a->w, uint64_t(K), uint64_t(a->Cout_pad), uint64_t(K) * 2, 64, uint32_t(pair ? bn / 2 : bn));
     if (rc) return rc;

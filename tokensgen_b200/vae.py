@@ -49,10 +49,11 @@ class _PackedConv:
             m = wd.permute(0, 2, 3, 4, 1)
             m = torch.nn.functional.pad(m, (0, _pad64(cin) - cin))
             m = m.reshape(cout, -1)
-            m = torch.nn.functional.pad(m, (0, 0, 0, _pad64(cout) - cout))
+            rows = _pad64(cout)
+            m = torch.nn.functional.pad(m, (0, 0, 0, rows - cout))
             self.w = m.to(torch.bfloat16).contiguous()
             self.b = None if conv.bias is None else conv.bias.detach().to(torch.bfloat16).contiguous()
-            self.b_pad = None if self.b is None else torch.nn.functional.pad(self.b, (0, _pad64(cout) - cout)).contiguous()
+            self.b_pad = None if self.b is None else torch.nn.functional.pad(self.b, (0, rows - cout)).contiguous()
             self.key = key
         return self.w, self.b
 
