@@ -23,6 +23,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
     return v;
 }
+__device__ __forceinline__ void unpack8p(const uint4& v, uint64_t (&p)[4]) {   // eight bf16 -> four packed fp32 pairs
+    p[0] = pack_f32x2(bf16_lo(v.x), bf16_hi(v.x));
+    p[1] = pack_f32x2(bf16_lo(v.y), bf16_hi(v.y));
+    p[2] = pack_f32x2(bf16_lo(v.z), bf16_hi(v.z));
+    p[3] = pack_f32x2(bf16_lo(v.w), bf16_hi(v.w));
+}
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------ K2
@@ -74,40 +80,51 @@ __global__ void __launch_bounds__(256, (NV <= 12) ? 2 : 1) ln_modulate_packed_ke
     uint4 raw[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) raw[i] = __ldg(xr + i * 32);   // all loads of the row in flight at once
-    float s = 0.f;
+    // All arithmetic on packed fp32 pairs (FADD2 / FFMA2 / FMUL2: one issue slot per two results) — at HBM speed the scalar
+    // form needs ~150 issue slots per 16-byte vector and the kernel was bound by them (0.55 of the copy peak in the step).
+    uint64_t acc = 0;                                           // (+0, +0)
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        float f[8];
-        unpack8(raw[i], f);
+        uint64_t f[4];
+        unpack8p(raw[i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[j];
+        for (int j = 0; j < 4; ++j) acc = add_f32x2(acc, f[j]);
     }
     const float inv_d = 1.0f / float(p.d);
-    const float mean = warp_sum(s) * inv_d;
-    float ss = 0.f;
+    const float mean = warp_sum(f32x2_lo(acc) + f32x2_hi(acc)) * inv_d;
+    const uint64_t neg_mean = pack_f32x2(-mean, -mean);
+    acc = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        float f[8];
-        unpack8(raw[i], f);
+        uint64_t f[4];
+        unpack8p(raw[i], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float dlt = f[j] - mean;
-            ss = fmaf(dlt, dlt, ss);
+        for (int j = 0; j < 4; ++j) {
+            const uint64_t dlt = add_f32x2(f[j], neg_mean);
+            acc = fma_f32x2(dlt, dlt, acc);
         }
     }
-    const float rstd = rsqrtf(warp_sum(ss) * inv_d + p.eps);
+    const float rstd = rsqrtf(warp_sum(f32x2_lo(acc) + f32x2_hi(acc)) * inv_d + p.eps);
+    const uint64_t rstd2 = pack_f32x2(rstd, rstd), one2 = pack_f32x2(1.0f, 1.0f);
     uint4* orow = reinterpret_cast<uint4*>(p.out + int64_t(row) * p.d) + lane;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        float f[8], wv[8], bv[8], shv[8], scv[8];
-        unpack8(raw[i], f);
-        unpack8(__ldg(w + i * 32), wv);
-        unpack8(__ldg(bb + i * 32), bv);
-        unpack8(__ldg(shv4 + i * 32), shv);
-        unpack8(__ldg(scv4 + i * 32), scv);
+        uint64_t f[4], wv[4], bv[4], shv[4], scv[4];
+        unpack8p(raw[i], f);
+        unpack8p(__ldg(w + i * 32), wv);
+        unpack8p(__ldg(bb + i * 32), bv);
+        unpack8p(__ldg(shv4 + i * 32), shv);
+        unpack8p(__ldg(scv4 + i * 32), scv);
+        uint4 o;
+        uint32_t* ow = &o.x;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = fmaf(fmaf((f[j] - mean) * rstd, wv[j], bv[j]), 1.0f + scv[j], shv[j]);
-        orow[i * 32] = pack8(f);
+        for (int j = 0; j < 4; ++j) {
+            // fmaf(fmaf((x - mean) * rstd, w, b), 1 + scale, shift), lane by lane
+            const uint64_t n = mul_f32x2(add_f32x2(f[j], neg_mean), rstd2);
+            const uint64_t y = fma_f32x2(fma_f32x2(n, wv[j], bv[j]), add_f32x2(scv[j], one2), shv[j]);
+            ow[j] = pack_bf16x2(f32x2_lo(y), f32x2_hi(y));
+        }
+        orow[i * 32] = o;
     }
 }
 
