@@ -105,6 +105,12 @@ def point(vae, op: str, T: int, tiled: bool, peaks: dict, g=None):
            "tflops_whole_pass": round(fl / ms / 1e9, 1), "frac_of_sustained_peak": round(fl / ms / 1e9 / tf_peak, 3),
            "conv_kernel_tflops": round(fl / per.get("vae_conv", ms) / 1e9, 1),
            "conv_kernel_frac_of_sustained_peak": round(fl / per.get("vae_conv", ms) / 1e9 / tf_peak, 3), "ms_by_op": per}
+    from tokensgen_b200 import vae as V
+    if tiled and V._TILE_STREAMS > 1:
+        # the tiles run on several CUDA streams: the per-op event intervals overlap each other, only the pass time is meaningful
+        out["ms_by_op"] = {"note": f"tiles on {V._TILE_STREAMS} streams: per-op intervals overlap (TG_VAE_TILE_STREAMS=1 for a breakdown)"}
+        del out["conv_kernel_tflops"], out["conv_kernel_frac_of_sustained_peak"]
+        return out
     for name in ("vae_norm_act", "vae_group_stats"):
         if name + "_GBps" in per:
             out[name + "_frac_of_hbm_peak"] = round(per[name + "_GBps"] / hbm_peak, 3)
