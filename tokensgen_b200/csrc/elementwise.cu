@@ -82,18 +82,22 @@ __global__ void __launch_bounds__(256, (NV <= 12) ? 2 : 1) ln_modulate_packed_ke
     for (int i = 0; i < NV; ++i) raw[i] = __ldg(xr + i * 32);   // all loads of the row in flight at once
     // All arithmetic on packed fp32 pairs (FADD2 / FFMA2 / FMUL2: one issue slot per two results) — at HBM speed the scalar
     // form needs ~150 issue slots per 16-byte vector and the kernel was bound by them (0.55 of the copy peak in the step).
-    uint64_t acc = 0;                                           // (+0, +0)
+    // four independent accumulator pairs: with 16 warps per SM a single dependent FADD2 chain (48 links per pass) is latency-,
+    // not issue-bound
+    uint64_t acc[4] = {0, 0, 0, 0};                             // (+0, +0) each
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         uint64_t f[4];
         unpack8p(raw[i], f);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc = add_f32x2(acc, f[j]);
+        for (int j = 0; j < 4; ++j) acc[j] = add_f32x2(acc[j], f[j]);
     }
+    uint64_t tot = add_f32x2(add_f32x2(acc[0], acc[1]), add_f32x2(acc[2], acc[3]));
     const float inv_d = 1.0f / float(p.d);
-    const float mean = warp_sum(f32x2_lo(acc) + f32x2_hi(acc)) * inv_d;
+    const float mean = warp_sum(f32x2_lo(tot) + f32x2_hi(tot)) * inv_d;
     const uint64_t neg_mean = pack_f32x2(-mean, -mean);
-    acc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         uint64_t f[4];
@@ -101,10 +105,11 @@ __global__ void __launch_bounds__(256, (NV <= 12) ? 2 : 1) ln_modulate_packed_ke
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const uint64_t dlt = add_f32x2(f[j], neg_mean);
-            acc = fma_f32x2(dlt, dlt, acc);
+            acc[j] = fma_f32x2(dlt, dlt, acc[j]);
         }
     }
-    const float rstd = rsqrtf(warp_sum(f32x2_lo(acc) + f32x2_hi(acc)) * inv_d + p.eps);
+    tot = add_f32x2(add_f32x2(acc[0], acc[1]), add_f32x2(acc[2], acc[3]));
+    const float rstd = rsqrtf(warp_sum(f32x2_lo(tot) + f32x2_hi(tot)) * inv_d + p.eps);
     const uint64_t rstd2 = pack_f32x2(rstd, rstd), one2 = pack_f32x2(1.0f, 1.0f);
     uint4* orow = reinterpret_cast<uint4*>(p.out + int64_t(row) * p.d) + lane;
 #pragma unroll
