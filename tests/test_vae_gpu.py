@@ -305,9 +305,10 @@ def test_tile_streams_do_not_change_the_tiled_coder(env):
 @pytest.mark.parametrize("C,T,H,W,ratio", [(128, 3, 40, 90, 2), (512, 2, 30, 45, 1), (256, 5, 24, 44, 4),
                                            (192, 3, 40, 77, 0), (128, 2, 64, 96, 0)])
 def test_staged_norm_act_equals_the_register_fed_kernel(C, T, H, W, ratio):
-    """tg_vae_norm_act takes the shared-memory-staged kernel (1-D bulk copies) for dense tensors of >= 1 MB and the register-fed
-    one otherwise (here: an output with a row pitch); same arithmetic, so the same bits.  Shapes with partial 8 KB runs at the
-    row ends, 24 vectors per pixel (C = 192: idle lanes), odd T (first-frame rule of the zq up-sampling)."""
+    """tg_vae_norm_act on dense and on pitched outputs (same bits), against fp32 torch: partial runs at the row ends, 24 vectors
+    per pixel (C = 192: idle lanes), odd T (first-frame rule of the zq up-sampling).  With the DEVELOPER library and
+    TG_NORM_STAGED=1 the dense call takes the shared-memory-staged kernel (1-D bulk copies; not shipped, see csrc/vae.cu) and
+    the pitched one the register-fed kernel — the same arithmetic, so still the same bits."""
     from tokensgen_b200 import _ext as E
     g = torch.Generator().manual_seed(C + W)
     x = (torch.randn(T, H, W, C, generator=g) * 1.5 + 0.3).bfloat16().cuda()

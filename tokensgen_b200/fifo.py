@@ -463,12 +463,21 @@ def decode_latents_parallel(pipe, latents: torch.Tensor, nf: int, rank: int = 0,
     return None if rank != 0 else torch.cat([outs[c] for c in range(chunks)], dim=2)
 
 
+# Streaming decode on a SIDE stream, overlapping the window forwards of the same GPU (TG_STREAM_DECODE_OVERLAP=1).  Off by
+# default: at full size (CogVideoX-5b window forwards on one stream, the tiled 480 x 720 decode on another) the device hung in
+# tools/concurrency_check.py — CTA-pair GEMMs / attention on one side, CTA-pair convolutions on the other; not understood yet,
+# and the tiny-shape tests never showed it.  Without the overlap the decode of a chunk costs its rank one window step's worth of
+# time every 13 iterations (0.5 s in 13 x 8 x 0.8 s), still spread over the ranks and with no decode tail.
+import os as _os
+_DECODE_OVERLAP = _os.environ.get("TG_STREAM_DECODE_OVERLAP", "0") != "0"
+
+
 class StreamingDecoder:
     """Streaming decode under the FIFO loop.  The reference decodes all chunks serially on GPU 0 AFTER the
     loop (cogvideo_sampling_mp_fifo.py:367-385); `decode_latents_parallel` already spreads that tail over the ranks.  Here
     chunk c is decoded as soon as its `nf` latent frames have left the queue — iteration (T - nf) + nf (c + 1) - 1 — on
-    rank c % P, on a SIDE stream, while the main stream goes on denoising: the first 49 frames are available after 52 + 13
-    iterations instead of after the whole stage, and no decode is left for the end except the last chunk's.
+    rank c % P (optionally on a SIDE stream while the main stream goes on denoising, _DECODE_OVERLAP): the first 49 frames are
+    available after 52 + 13 iterations instead of after the whole stage, and no decode is left for the end except the last chunk's.
 
     Every rank runs the same deterministic loop, so the owner knows in which iteration to post its receive: rank 0 (the
     emitting rank: slot r_nf belongs to window rank 0) sends the chunk's latents (2.25 MB) to the owner inside the
@@ -486,6 +495,11 @@ class StreamingDecoder:
     def _decode(self, c: int, latents: torch.Tensor):
         dev = latents.device
         if dev.type != "cuda":      # host tensors (the gloo tests of the hand-off logic): no streams, decode in line
+            self.frames[c] = self.pipe.decode_latents(latents, self.nf)
+            return
+        if not _DECODE_OVERLAP:
+            # in line on the denoising stream: the chunk is still decoded the iteration it completes, on rank c % P, and nothing
+            # is left for the end — but the VAE's kernels never run BESIDE the DiT's on one GPU (see _DECODE_OVERLAP)
             self.frames[c] = self.pipe.decode_latents(latents, self.nf)
             return
         if self.side is None:

@@ -573,6 +573,13 @@ class AutoencoderKLCogVideoX(nn.Module):
         outs = [alloc_fn(t) for t in tiles]
         state = [[None] * len(convs) for _ in tiles]
         t0 = [0] * len(tiles)
+        # tiles differ in size (edge tiles are narrower / shorter): largest first onto the least loaded stream; tile 0 (a full
+        # tile, first in the order) lands on the main stream
+        load, lane = [0] * n_streams, [0] * len(tiles)
+        for ti in sorted(range(len(tiles)), key=lambda i: (-tiles[i].shape[2] * tiles[i].shape[3], i)):
+            lane[ti] = min(range(n_streams), key=lambda k: (load[k], k))
+            load[lane[ti]] += tiles[ti].shape[2] * tiles[ti].shape[3]
+        assert lane[0] == 0
         forked = n_streams == 1
         for a, b in ranges:
             for ti, tile in enumerate(tiles):
@@ -581,7 +588,7 @@ class AutoencoderKLCogVideoX(nn.Module):
                     for st in streams[1:]:
                         st.wait_stream(main)
                     forked = True
-                with torch.cuda.stream(streams[ti % n_streams]):
+                with torch.cuda.stream(streams[lane[ti]]):
                     for m, c in zip(convs, state[ti]):
                         m.conv_cache = c
                     t0[ti] += batch_fn(tile[:, a:b].contiguous(), outs[ti][:, t0[ti]:], outs[ti].stride(0))

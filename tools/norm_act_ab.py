@@ -1,5 +1,6 @@
 """Developer tool: tg_vae_norm_act, shared-memory-staged kernel (dense output) vs register-fed kernel (pitched output) on the
-decoder's activation shapes; 100 back-to-back launches each, CUDA events.  usage: python tools/norm_act_ab.py"""
+decoder's activation shapes; 100 back-to-back launches each, CUDA events.  The staged kernel exists in the developer build only:
+usage: TG_LIB_PATH=tokensgen_b200/libtokensgen_b200_dev.so TG_NORM_STAGED=1 python tools/norm_act_ab.py"""
 import os
 import sys
 
