@@ -72,8 +72,11 @@ def test_base_stage_fifo_stage_and_decode():
 
 
 def test_streaming_decode_under_the_fifo_loop_is_bit_identical():
-    """SURVEY §8-f2: `streaming_decode=True` decodes every chunk on a side stream as soon as its frames have left the queue;
-    the video equals the decode-after-the-loop path bit for bit, and each chunk was dispatched in its own iteration."""
+    """`streaming_decode=True` decodes every chunk as soon as its frames have left the queue — in line on the
+    denoising stream (the shipped default) or on a side stream beside the window forwards (TG_STREAM_DECODE_OVERLAP=1; fine at
+    these shapes, off by default because of a full-size hang); the video equals the decode-after-the-loop path bit
+    for bit, and each chunk was dispatched in its own iteration."""
+    from tokensgen_b200 import fifo as F
     from tokensgen_b200.fifo import cogvideo_fifo_mp_v2
     pipe = _tiny_pipe()
     g = torch.Generator().manual_seed(3)
@@ -87,11 +90,17 @@ def test_streaming_decode_under_the_fifo_loop_is_bit_identical():
                 return_dict=False)
     import copy
     _, ref, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42)
-    log = {}
-    _, got, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, streaming_decode=True, stream_log=log)
-    assert got.shape == ref.shape == (1, 27, 64, 96, 3)
-    assert np.array_equal(got, ref)
-    assert log == {c: (12 - 3) + 3 * (c + 1) - 1 for c in range(3)}      # T = 12, nf = 3
+    keep = F._DECODE_OVERLAP
+    try:
+        for overlap in (False, True):
+            F._DECODE_OVERLAP = overlap
+            log = {}
+            _, got, _ = cogvideo_fifo_mp_v2([pipe], copy.copy(base), seed=42, streaming_decode=True, stream_log=log)
+            assert got.shape == ref.shape == (1, 27, 64, 96, 3)
+            assert np.array_equal(got, ref), overlap
+            assert log == {c: (12 - 3) + 3 * (c + 1) - 1 for c in range(3)}      # T = 12, nf = 3
+    finally:
+        F._DECODE_OVERLAP = keep
 
 
 def test_t2to_pipeline_tail():
