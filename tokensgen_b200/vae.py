@@ -307,7 +307,9 @@ def _norm_silu_into(norm, x, out: torch.Tensor, zq: Optional[_ZqTables]):
 import os as _os
 _FUSED_STATS = _os.environ.get("TG_VAE_FUSED_STATS", "1") != "0"
 # CUDA streams the independent tiles of a tiled encode / decode are spread over (1: the reference's serial tile loop)
-_TILE_STREAMS = int(_os.environ.get("TG_VAE_TILE_STREAMS", "3"))
+# Capped at 4: what has been exercised at full size (with 5 streams of tensor-core kernels active — window forwards
+# beside a 3-lane tiled decode — the device hung; up to 4 never did with the shipped kernels).
+_TILE_STREAMS = max(1, min(4, int(_os.environ.get("TG_VAE_TILE_STREAMS", "3"))))
 
 
 def _resnet(blk: CogVideoXResnetBlock3D, xa, zq: Optional[_ZqTables], next_groups: int = 0) -> "_Act":
