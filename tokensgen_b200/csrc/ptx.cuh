@@ -59,9 +59,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 // Bounded wait: a lost arrive must never hang the GPU box.  ~2^26 try_wait probes (each suspends for
 // a HW-defined slice) is seconds; after that record the site and trap (launch fails, context dies,
 // the host sees cudaErrorLaunchFailure instead of a hang).
+#ifdef TG_DEVELOPER
+// developer build: waits are also bounded in TIME (4 s), so that a stuck CTA reports its wait site instead of spinning through
+// 2^26 probes (each probe may suspend for a hardware-defined slice: minutes in all)
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void wait_watchdog(uint32_t spins, uint64_t& t0, uint32_t site, uint32_t bar, uint32_t parity) {
+    if ((spins & 0xffu) != 0) return;
+    const uint64_t now = globaltimer_ns();
+    if (t0 == 0) {
+        t0 = now;
+    } else if (now - t0 > 4000000000ull) {
+        printf("tokensgen_b200: wait stuck > 4 s (site 0x%x, bar 0x%x, parity %u, block %d,%d, thread %d)\n", site, bar, parity,
+               blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+    }
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, uint32_t site = 0) {
     uint32_t spins = 0;
+#ifdef TG_DEVELOPER
+    uint64_t t0 = 0;
+#endif
     while (!mbar_try_wait(bar, parity)) {
+#ifdef TG_DEVELOPER
+        wait_watchdog(spins, t0, site, bar, parity);
+#endif
         if (++spins > (1u << 26)) {
             printf("tokensgen_b200: mbarrier wait timed out (site 0x%x, block %d,%d, thread %d)\n", site, blockIdx.x,
                    blockIdx.y, threadIdx.x);
@@ -98,7 +124,13 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
 #else
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
+#ifdef TG_DEVELOPER
+    uint64_t t0 = 0;
+#endif
     while (!mbar_try_wait(bar, parity)) {
+#ifdef TG_DEVELOPER
+        wait_watchdog(spins, t0, 0xfa57u, bar, parity);
+#endif
         if (++spins > (1u << 24)) __trap();
     }
 #endif
