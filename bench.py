@@ -303,6 +303,49 @@ def run_fifo_stage(model, sch, dev, world, rank, chunks: int, barrier):
         ms = tt.item()
     return ms / 1e3, int(latents.shape[1]), bool(torch.isfinite(latents.float()).all())
 
+def vae_block(sweep_frames):
+    """The `vae` object of the N = 1 line (runs in the child process started by run_vae_block)."""
+    from tools import vae_bench as vb
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    vae = vb.build_vae()
+    pts = [vb.point(vae, "decode", 13, False, peaks), vb.point(vae, "decode", 13, True, peaks),
+           vb.point(vae, "encode", 49, False, peaks), vb.point(vae, "encode", 49, True, peaks)]
+    sweep = [vb.point(vae, "decode", T, False, peaks) for T in sweep_frames]
+    return {"what": "3D causal VAE, full CogVideoX-5b widths (128,256,256,512), 480x720: decode of one 13-latent-frame "
+                    "clip (49 frames) untiled and tiled 3x3 (the reference CLI's default), encode of 49 frames; "
+                    "`sweep`: configs[4] decode of T latent frames as ONE causal stream",
+            "points": pts, "sweep": [{k: p[k] for k in ("latent_frames", "pixel_frames", "ms", "pixel_frames_per_s",
+                                                         "tflops_whole_pass", "frac_of_sustained_peak")} for p in sweep]}
+
+
+def run_vae_block(sweep_frames, timeout_s: float):
+    """vae_block() in a child process (its own CUDA context on the same GPU), killed with its process group at the time limit."""
+    import signal
+    import subprocess
+    cmd = [sys.executable, os.path.abspath(__file__), "--vae-child", "--vae-sweep"] + [str(t) for t in sweep_frames]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT")}
+    try:
+        p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT, env=env, start_new_session=True)
+    except OSError as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+    try:
+        out, err = p.communicate(timeout=timeout_s)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)     # a process blocked on a hung device does not answer SIGINT / SIGTERM
+        except ProcessLookupError:
+            pass
+        p.wait()
+        return {"error": f"the VAE block did not finish within {timeout_s:.0f} s and was killed"}
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    if p.returncode != 0 or not lines:
+        return {"error": f"child exited with {p.returncode}: {err.strip()[-300:]}"}
+    try:
+        return json.loads(lines[-1])
+    except ValueError as e:
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 # ------------------------------------------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch.distributed as dist
@@ -540,26 +583,12 @@ def run_ours(args):
             except Exception as e:  # noqa: BLE001
                 line["gpu_eager_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1 and not args.no_vae:
-            # configs[4] + the VAE bookends of configs[1]: full-size CogVideoX VAE, random-init weights, this GPU (guarded like the
-            # eager baseline: a failure is recorded, not raised)
-            try:
-                del model
-                torch.cuda.empty_cache()
-                from tools import vae_bench as vb
-                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-                vae = vb.build_vae()
-                pts = [vb.point(vae, "decode", 13, False, peaks), vb.point(vae, "decode", 13, True, peaks),
-                       vb.point(vae, "encode", 49, False, peaks), vb.point(vae, "encode", 49, True, peaks)]
-                sweep = [vb.point(vae, "decode", T, False, peaks) for T in args.vae_sweep]
-                line["vae"] = {"what": "3D causal VAE, full CogVideoX-5b widths (128,256,256,512), 480x720: decode of one 13-latent-frame "
-                                       "clip (49 frames) untiled and tiled 3x3 (the reference CLI's default), encode of 49 frames; "
-                                       "`sweep`: configs[4] decode of T latent frames as ONE causal stream",
-                               "points": pts, "sweep": [{k: p[k] for k in ("latent_frames", "pixel_frames", "ms", "pixel_frames_per_s",
-                                                                              "tflops_whole_pass", "frac_of_sustained_peak")} for p in sweep]}
-                del vae
-                torch.cuda.empty_cache()
-            except Exception as e:  # noqa: BLE001
-                line["vae"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            # configs[4] + the VAE bookends of configs[1]: full-size CogVideoX VAE, random-init weights, this GPU.  Guarded like the
+            # eager baseline (a failure is recorded, not raised) and run in a CHILD process under a time limit: the block must
+            # never cost the bench line, not even by not returning
+            del model
+            torch.cuda.empty_cache()
+            line["vae"] = run_vae_block(args.vae_sweep, args.vae_timeout_s)
         if world == 1 and not args.no_cpu_baseline:
             times, cores, kind = cpu_block_seconds(3, 1)
             sec = float(np.median(times))
@@ -588,7 +617,15 @@ def main():
     ap.add_argument("--fifo-budget-s", type=float, default=320.0, help="N > 1: shorten the FIFO video until it fits this many seconds")
     ap.add_argument("--no-vae", action="store_true", help="N = 1: skip the VAE block")
     ap.add_argument("--vae-sweep", type=int, nargs="*", default=[25, 49], help="N = 1: extra decode points (latent frames, one stream)")
+    ap.add_argument("--vae-timeout-s", type=float, default=300.0, help="N = 1: time limit of the VAE block (child process)")
+    ap.add_argument("--vae-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.vae_child:
+        try:
+            print(json.dumps(vae_block(args.vae_sweep)), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"error": f"{type(e).__name__}: {e}"[:300]}), flush=True)
+        return
     if args.impl == "reference":
         run_reference(args)
     else:

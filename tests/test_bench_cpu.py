@@ -76,3 +76,17 @@ def test_reference_block_equals_the_oracle_port():
         for m in [m for m in sys.modules if m == "longvgen" or m.startswith("longvgen.")]:
             del sys.modules[m]
         sys.path[:] = [p for p in sys.path if "baseline/_ref" not in p]
+
+
+def test_vae_block_runs_in_a_child_that_cannot_cost_the_bench_line():
+    """bench.py's N = 1 `vae` object comes from a child process under a time limit: a child that does not return is killed with
+    its process group and recorded as an error, a child that fails (here: no GPU) hands its error back — the bench line is
+    printed either way."""
+    import time
+    sys.path.insert(0, ROOT)
+    import bench
+    t0 = time.time()
+    out = bench.run_vae_block([], 0.05)
+    assert "did not finish" in out["error"] and time.time() - t0 < 10
+    out = bench.run_vae_block([], 300)
+    assert "error" in out and "NVIDIA" in out["error"] or "CUDA" in out["error"] or "points" in out
