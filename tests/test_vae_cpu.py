@@ -79,3 +79,17 @@ def test_posterior_sample_and_roundtrip_shapes(env):
     assert torch.equal(z, mean + torch.exp(0.5 * logvar.clamp(-30, 20)) * eps)
     assert z.shape == (1, 16, 5, 4, 5)          # 17 frames -> 5 latent frames, /8 spatial
     assert g["dec_f32"].shape == (1, 3, 17, 32, 40)  # 5 latent frames -> 17 frames
+
+
+def test_tile_lanes_balance_the_tiled_coder_over_its_streams():
+    """vae._tile_lanes: the 3 x 3 tiles of a 480 x 720 frame (latent 30x45 full tiles, 18-wide / 10-tall edge tiles) over 1 - 4
+    stream lanes: every tile gets a lane, tile 0 stays on the caller's stream, and the lanes' areas differ by less than one full
+    tile."""
+    from tokensgen_b200.vae import _tile_lanes
+    areas = [h * w for h in (30, 30, 10) for w in (45, 45, 18)]
+    for n in (1, 2, 3, 4):
+        lane = _tile_lanes(areas, n)
+        assert len(lane) == 9 and lane[0] == 0 and set(lane) == set(range(n))
+        load = [sum(a for a, l in zip(areas, lane) if l == k) for k in range(n)]
+        assert sum(load) == sum(areas) and max(load) - min(load) < 30 * 45
+    assert _tile_lanes([], 3) == [] and _tile_lanes([5], 3) == [0]

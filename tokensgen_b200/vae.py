@@ -345,6 +345,18 @@ def _conv2d(mod, x: torch.Tensor, stride: int, pad0: int, next_groups: int = 0) 
     return _Act(y, st, next_groups)
 
 
+def _tile_lanes(areas, n_lanes: int):
+    """Tile -> stream lane.  Tile 0 — first in the issue order: its first batch packs the weights every lane reads — stays on
+    lane 0, the caller's stream; the others go largest first onto the least loaded lane (ties: lowest index)."""
+    load, lane = [0] * n_lanes, [0] * len(areas)
+    if areas:
+        load[0] = areas[0]
+    for ti in sorted(range(1, len(areas)), key=lambda i: (-areas[i], i)):
+        lane[ti] = min(range(n_lanes), key=lambda k: (load[k], k))
+        load[lane[ti]] += areas[ti]
+    return lane
+
+
 class DiagonalGaussianDistribution:
     """diffusers' posterior wrapper (restated): parameters = [mean | logvar] along dim 1."""
 
@@ -577,11 +589,7 @@ class AutoencoderKLCogVideoX(nn.Module):
         t0 = [0] * len(tiles)
         # tiles differ in size (edge tiles are narrower / shorter): largest first onto the least loaded stream; tile 0 (a full
         # tile, first in the order) lands on the main stream
-        load, lane = [0] * n_streams, [0] * len(tiles)
-        for ti in sorted(range(len(tiles)), key=lambda i: (-tiles[i].shape[2] * tiles[i].shape[3], i)):
-            lane[ti] = min(range(n_streams), key=lambda k: (load[k], k))
-            load[lane[ti]] += tiles[ti].shape[2] * tiles[ti].shape[3]
-        assert lane[0] == 0
+        lane = _tile_lanes([t.shape[2] * t.shape[3] for t in tiles], n_streams)
         forked = n_streams == 1
         for a, b in ranges:
             for ti, tile in enumerate(tiles):
